@@ -1,0 +1,171 @@
+/*
+ * nle_b200.h -- C ABI of the B200-native Nystrom spectral-filter library (libnle_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of lightalchemist/nonlocal-image-edit: every entry
+ * point below replaces one function of the reference's src/filter.cpp (cited as filter.cpp:LINE,
+ * header include/filter.hpp as filter.hpp:LINE).  The reference has no FFI layer; its boundary is
+ * the C++ header include/filter.hpp, so the binding a maintainer adds is a replacement translation
+ * unit for src/filter.cpp that implements the unchanged filter.hpp on top of these calls
+ * (see INTEGRATION.md).  Plain pointers and sizes only; no C++/torch types.
+ *
+ * Conventions
+ *   - All matrices are COLUMN-MAJOR doubles (Eigen's default, filter.hpp:10-11) unless stated.
+ *   - Images/channels are row-major (raster) like cv::Mat (utils.hpp:11-14).
+ *   - Pointers are HOST pointers unless the function name ends in _dev.
+ *   - Every function returns 0 on success, a negative nle_b200_status otherwise, and never throws;
+ *     nle_b200_last_error() returns the message for the calling thread.  The reference's
+ *     std::runtime_error messages (filter.cpp:118,415,419,448) are reproduced verbatim there.
+ *   - There is no CPU fallback: without a CUDA device every compute call fails with
+ *     NLE_B200_ERR_CUDA.
+ *   - A filter handle is not thread-safe; distinct handles are independent.
+ */
+#ifndef NLE_B200_H
+#define NLE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    NLE_B200_OK = 0,
+    NLE_B200_ERR_INVALID = -1,     /* bad argument (message mirrors the reference's runtime_error) */
+    NLE_B200_ERR_CUDA = -2,        /* CUDA runtime failure / no device */
+    NLE_B200_ERR_UNSUPPORTED = -3, /* outside the supported envelope (e.g. non-integer luminance) */
+    NLE_B200_ERR_NOCONV = -4       /* eigensolver did not converge */
+} nle_b200_status;
+
+/* Opaque trained filter: the state of nle::NLEFilter (m_eigvecs N x k, m_eigvals k;
+ * filter.hpp:52-53) kept resident in HBM. */
+typedef struct nle_b200_filter nle_b200_filter;
+
+typedef struct {
+    int rows, cols;      /* full image size                                              */
+    int row0, row1;      /* image rows [row0,row1) owned by this handle (sharding)       */
+    int p;               /* number of Nystrom samples (selected.size(), filter.cpp:124)  */
+    int r;               /* #eigenvalues of Ka >= 1e-10 (filter.cpp:213-216,262)         */
+    int r2;              /* #eigenvalues of Wa >= 1e-10 (filter.cpp:287)                 */
+    int k;               /* eigenvectors kept: min(nEigenVectors, #eig(Q)>=1e-10)        */
+    int n_row_samples_eff, n_col_samples_eff; /* grid actually produced by samplePixels  */
+    int eig_sweeps[3];   /* Jacobi sweeps used by the three eigensolves                  */
+} nle_b200_info;
+
+/* Small all-reduce (sum) used by row-sharded training/apply.  `dev_buf` is a DEVICE pointer to
+ * `count` doubles on the calling rank's GPU; the callee must sum it in place across ranks on
+ * `cuda_stream` (a cudaStream_t) or synchronously.  The host language supplies it (the Python host
+ * wraps torch.distributed/NCCL).  Only p-vectors, one p x p Gram and k-vectors ever go through it. */
+typedef int (*nle_b200_allreduce_fn)(void* dev_buf, size_t count, void* cuda_stream, void* user);
+
+const char* nle_b200_last_error(void);
+int nle_b200_version(void);
+int nle_b200_device_count(void);
+
+/* ---- (1) sample selection: samplePixels, filter.cpp:56-80; to1DIndex, utils.hpp:11-14 -------- */
+/* Number of selected pixels p (can exceed nRowSamples*nColSamples). Pure host arithmetic. */
+int nle_b200_sample_count(int rows, int cols, int nRowSamples, int nColSamples, int* p_out);
+/* Raster indices of `selected` (p ints) and, if rest != NULL, of `rest` (rows*cols-p ints), both in
+ * raster order, generated on the GPU.  Bit-exact with the reference (permutation of
+ * filter.cpp:156-164 is [selected; rest]). */
+int nle_b200_sample_indices(int rows, int cols, int nRowSamples, int nColSamples,
+                            int32_t* selected, int32_t* rest);
+
+/* ---- free functions of filter.hpp:20-33 (dense, for the reference's unit tests) ------------- */
+/* computeKernel, filter.cpp:114-167.  channel: rows x cols doubles (integer-valued 0..255, as both
+ * reference callers produce).  Ka: p x p.  Kab: p x (N-p) or NULL.  perm: N ints or NULL. */
+int nle_b200_compute_kernel(const double* channel, int rows, int cols, int nRowSamples,
+                            int nColSamples, double hx, double hy,
+                            int32_t* perm, double* Ka, double* Kab);
+/* eigenDecomposition, filter.cpp:204-228.  Reads the LOWER triangle of M (n x n) like Eigen's
+ * SelfAdjointEigenSolver; eigenvalues descending; *r_out = length of the prefix with D >= eps.
+ * U: n x n (all eigenvectors, first r are the reference's result), D: n. */
+int nle_b200_eigen_decomposition(const double* M, int n, double eps, double* U, double* D,
+                                 int* r_out);
+/* nystromApproximation, filter.cpp:257-280.  eigvals: p, phi: (p+nrest) x p (first r columns
+ * valid), *r_out = rank kept. */
+int nle_b200_nystrom_approximation(const double* Ka, int p, const double* Kab, int nrest,
+                                   double* eigvals, double* phi, int* r_out);
+/* sinkhorn, filter.cpp:230-254.  phi: n x r, eigvals: r.  Wa: r x r, Wab: r x (n-r). */
+int nle_b200_sinkhorn(const double* phi, int n, int r, const double* eigvals, int maxIter,
+                      double* Wa, double* Wab);
+/* orthogonalize, filter.cpp:282-331 (non-Spectra branch).  Wa: p x p, Wab: p x nrest.
+ * V: (p+nrest) x nEigVectors (first *k_out columns valid), S: nEigVectors. */
+int nle_b200_orthogonalize(const double* Wa, int p, const double* Wab, int nrest, int nEigVectors,
+                           double eps, double* V, double* S, int* k_out);
+/* transformEigenValues, filter.cpp:334-347 (host arithmetic, std::pow). */
+int nle_b200_transform_eigenvalues(const double* eigvals, int k, const double* weights, int m,
+                                   double* fS);
+
+/* ---- NLEFilter::trainFilter, filter.cpp:480-502 ---------------------------------------------- */
+/* channel: rows x cols luminance as produced by getLuminanceChannel (filter.cpp:460-469), i.e.
+ * integer-valued doubles in [0,255].  Non-integer input -> NLE_B200_ERR_UNSUPPORTED. */
+int nle_b200_train(const double* channel, int rows, int cols, int nRowSamples, int nColSamples,
+                   double hx, double hy, int nSinkhornIter, int nEigenVectors,
+                   nle_b200_filter** out);
+/* Same, 8-bit luminance (what cvtColor(BGR2Lab) produced before convertTo(CV_64F)). */
+int nle_b200_train_u8(const uint8_t* lum, int rows, int cols, int nRowSamples, int nColSamples,
+                      double hx, double hy, int nSinkhornIter, int nEigenVectors,
+                      nle_b200_filter** out);
+/* Row-sharded training: this rank owns image rows [row0,row1) of the FULL host image `lum`
+ * (every rank passes the same image; only the slab and the p sample values are uploaded).
+ * allreduce may be NULL when the slab is the whole image. */
+int nle_b200_train_u8_sharded(const uint8_t* lum, int rows, int cols, int row0, int row1,
+                              int nRowSamples, int nColSamples, double hx, double hy,
+                              int nSinkhornIter, int nEigenVectors,
+                              nle_b200_allreduce_fn allreduce, void* user,
+                              nle_b200_filter** out);
+/* Device-resident variant: lum_slab_dev points to rows [row0,row1) (row-major u8) already in HBM;
+ * sample_lum holds the p luminances of the selected pixels in raster order (HOST, may be NULL when
+ * the slab is the whole image). */
+int nle_b200_train_u8_dev(const uint8_t* lum_slab_dev, int rows, int cols, int row0, int row1,
+                          const uint8_t* sample_lum, int nRowSamples, int nColSamples, double hx,
+                          double hy, int nSinkhornIter, int nEigenVectors,
+                          nle_b200_allreduce_fn allreduce, void* user, nle_b200_filter** out);
+
+int nle_b200_filter_info(const nle_b200_filter* f, nle_b200_info* info);
+/* m_eigvals (k doubles). */
+int nle_b200_eigenvalues(const nle_b200_filter* f, double* S);
+/* m_eigvecs after the un-permute of filter.cpp:502: (row1-row0)*cols x k, column-major, pixel
+ * (raster) order of the owned slab. */
+int nle_b200_eigenvectors(const nle_b200_filter* f, double* V);
+
+/* ---- NLEFilter::apply, filter.cpp:445-458:  out = V diag(fS) V^T channel ---------------------- */
+/* channel/out: the owned slab, (row1-row0)*cols doubles. */
+int nle_b200_apply(const nle_b200_filter* f, const double* channel, const double* fS, double* out);
+/* enhance on the L channel (filter.cpp:426-436): u8 -> transformEigenValues -> apply ->
+ * max(.,0) -> min(.,255) -> convertTo(CV_8U) (round half to even), fused on the device. */
+int nle_b200_enhance_luminance_u8(const nle_b200_filter* f, const uint8_t* lum,
+                                  const double* weights, int m, uint8_t* out);
+int nle_b200_enhance_luminance_u8_dev(const nle_b200_filter* f, const uint8_t* lum_slab_dev,
+                                      const double* weights, int m, uint8_t* out_slab_dev);
+/* denoise's per-channel step (filter.cpp:378-399): teig = pow(min(S,1),k); apply; clamp; round. */
+int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, double k,
+                                uint8_t* out);
+
+/* ---- stage intermediates for parity tests (SURVEY.md 8b "test hooks") ------------------------ */
+typedef enum {
+    NLE_B200_STAGE_KA = 0,        /* p x p                                   */
+    NLE_B200_STAGE_LAMBDA = 1,    /* r      eigenvalues of Ka kept           */
+    NLE_B200_STAGE_RVEC_HEAD = 2, /* r      final Sinkhorn r on perm[0:r]    */
+    NLE_B200_STAGE_C = 3,         /* (row1-row0)*cols, raster order of slab  */
+    NLE_B200_STAGE_WA = 4,        /* r x r                                   */
+    NLE_B200_STAGE_Q = 5,         /* r x r                                   */
+    NLE_B200_STAGE_LA = 6,        /* r2     eigenvalues of Wa kept           */
+    NLE_B200_STAGE_GRAM = 7,      /* p x p  sum_j c_j^2 k_j k_j^T (rest)     */
+    NLE_B200_STAGE_TIMES_MS = 8   /* 8 doubles: per-stage device milliseconds */
+} nle_b200_stage;
+/* Copies min(cap, size) doubles; *size_out = full size.  Stages are kept only when the filter was
+ * trained with nle_b200_set_keep_stages(1) (default 1; bench turns it off). */
+int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t cap,
+                       size_t* size_out);
+void nle_b200_set_keep_stages(int keep);
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+long long nle_b200_launch_count(int reset);
+
+void nle_b200_free(nle_b200_filter* f);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NLE_B200_H */

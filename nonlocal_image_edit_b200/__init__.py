@@ -1,0 +1,13 @@
+"""nonlocal_image_edit_b200 -- B200-native Nystrom spectral filter (hot path of
+lightalchemist/nonlocal-image-edit) behind the reference's own operator interface.
+
+Host side mirrors include/filter.hpp of the reference: class NLEFilter with trainForEnhancement /
+trainForDenoise / enhance / denoise, and the free functions computeKernel, eigenDecomposition,
+nystromApproximation, sinkhorn, orthogonalize.  All numerics run in libnle_b200.so (hand-written
+CUDA for sm_100a); Python only does what the reference does with OpenCV on the host (imread,
+BGR<->Lab, bilateralFilter)."""
+from .filter import (NLEFilter, computeKernel, eigenDecomposition, nystromApproximation,  # noqa: F401
+                     orthogonalize, sampleIndices, sinkhorn, transformEigenValues)
+from ._lib import NleError, load  # noqa: F401
+
+EPS = 1e-10  # include/filter.hpp:14

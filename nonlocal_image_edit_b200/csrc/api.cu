@@ -1,0 +1,849 @@
+// C ABI of libnle_b200.so (declared in include/nle_b200.h) and the host-side orchestration of the
+// Nystrom spectral-filter pipeline.  Reference: NLEFilter::trainFilter (filter.cpp:480-502),
+// NLEFilter::apply (:445-458), NLEFilter::enhance (:412-443) and the free functions of
+// include/filter.hpp:20-33.  The mathematics follows SURVEY.md Appendix A (factor form); all
+// arithmetic that reaches the output is FP64, as in the reference (filter.hpp:10-14).
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <memory>
+
+#include "../../include/nle_b200.h"
+#include "kernels.cuh"
+
+namespace nle {
+
+static thread_local std::string g_error;
+void set_error(const std::string& msg) { g_error = msg; }
+static int g_keep_stages = 1;
+
+// --------------------------------------------------------------------------------------------
+// filter.cpp:56-80 : selected coordinates along one axis (the test at :68-70 is separable).
+static std::vector<int> sample_axis(int n, int k) {
+    const int step = n / k;                                   // :58-59
+    const int offset = (step - 1 + (n - step * k)) / 2;       // :60-61
+    std::vector<int> out;
+    for (int r = 0; r < n; ++r)
+        if (r >= offset && r <= n - offset && (r - offset) % step == 0) out.push_back(r);
+    return out;
+}
+
+struct Grid {
+    std::vector<int> sel_rows, sel_cols;   // image coordinates of the sample grid
+    std::vector<int> rowa, colb;           // per image row/col: grid index or -1
+    std::vector<int> rowrank, colrank;     // number of selected rows/cols strictly before
+    int nR = 0, nC = 0, p = 0;
+};
+
+static Grid make_grid(int rows, int cols, int nRowSamples, int nColSamples) {
+    if (rows <= 0 || cols <= 0 || nRowSamples <= 0 || nColSamples <= 0)
+        throw InvalidArg{"image size and sample counts must be positive"};
+    if (nRowSamples > rows || nColSamples > cols)
+        throw InvalidArg{"Number of samples per row and col must be <= that of image."};   // filter.cpp:118
+    if ((long long)rows * cols >= (1LL << 31))
+        throw Unsupported{"images with >= 2^31 pixels are not supported (the reference indexes pixels with int, utils.hpp:11)"};
+    Grid g;
+    g.sel_rows = sample_axis(rows, nRowSamples);
+    g.sel_cols = sample_axis(cols, nColSamples);
+    g.nR = (int)g.sel_rows.size();
+    g.nC = (int)g.sel_cols.size();
+    g.p = g.nR * g.nC;
+    g.rowa.assign(rows, -1); g.colb.assign(cols, -1);
+    g.rowrank.assign(rows, 0); g.colrank.assign(cols, 0);
+    for (int a = 0; a < g.nR; ++a) g.rowa[g.sel_rows[a]] = a;
+    for (int b = 0; b < g.nC; ++b) g.colb[g.sel_cols[b]] = b;
+    int cnt = 0;
+    for (int r = 0; r < rows; ++r) { g.rowrank[r] = cnt; if (g.rowa[r] >= 0) ++cnt; }
+    cnt = 0;
+    for (int c = 0; c < cols; ++c) { g.colrank[c] = cnt; if (g.colb[c] >= 0) ++cnt; }
+    return g;
+}
+
+struct Timer {
+    cudaEvent_t a, b;
+    cudaStream_t s;
+    explicit Timer(cudaStream_t st) : s(st) { cudaEventCreate(&a); cudaEventCreate(&b); cudaEventRecord(a, s); }
+    double stop() { cudaEventRecord(b, s); cudaEventSynchronize(b); float ms = 0; cudaEventElapsedTime(&ms, a, b); return ms; }
+    ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
+};
+
+}  // namespace nle
+
+using namespace nle;
+
+struct nle_b200_filter {
+    int rows = 0, cols = 0, row0 = 0, row1 = 0;
+    long long nloc = 0;
+    int p = 0, r = 0, r2 = 0, k = 0, nR = 0, nC = 0;
+    int eig_sweeps[3] = {0, 0, 0};
+    DevBuf<double> V;            // nloc x k, row-major
+    std::vector<double> S;       // k eigenvalues (host copy)
+    DevBuf<double> ascratch, avec;   // apply scratch
+    DevBuf<uint8_t> io8_in, io8_out;
+    DevBuf<double> io64_in, io64_out;
+    // stages
+    DevBuf<double> Ka, lam, rvec_head, c, Wa, Q, la, Gram;
+    double times_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    nle_b200_allreduce_fn allreduce = nullptr;
+    void* user = nullptr;
+    cudaStream_t stream = nullptr;
+};
+
+namespace nle {
+
+static void do_allreduce(nle_b200_filter* f, double* buf, size_t count) {
+    if (!f->allreduce) return;
+    int rc = f->allreduce(buf, count, (void*)f->stream, f->user);
+    if (rc != 0) throw InvalidArg{"allreduce callback failed with code " + std::to_string(rc)};
+}
+
+static int read_int(const int* d, cudaStream_t s) {
+    int v = 0;
+    NLE_CUDA(cudaMemcpyAsync(&v, d, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NLE_CUDA(cudaStreamSynchronize(s));
+    return v;
+}
+
+static void copy_dd(double* dst, const double* src, size_t n, cudaStream_t s) {
+    if (n) NLE_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+
+// small vector helpers used by the Sinkhorn loop
+__global__ void vec_axpy_kernel(double* y, const double* x, const double* scale, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) y[i] = fma(scale[i], x[i], y[i]);
+}
+__global__ void vec_mul_kernel(double* out, const double* a, const double* b, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = a[i] * b[i];
+}
+void vec_axpy(double* y, const double* x, const double* scale, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    vec_axpy_kernel<<<cdiv(n, 256), 256, 0, s>>>(y, x, scale, n);
+    NLE_LAUNCH_CHECK();
+}
+void vec_mul(double* out, const double* a, const double* b, int n, cudaStream_t s) {
+    if (n <= 0) return;
+    vec_mul_kernel<<<cdiv(n, 256), 256, 0, s>>>(out, a, b, n);
+    NLE_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// The training pipeline on one rank's slab.  lum_slab: device, rows [row0,row1).
+static std::unique_ptr<nle_b200_filter>
+train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, const uint8_t* sample_lum_host,
+           int nRowSamples, int nColSamples, double hx, double hy, int T, int nEig,
+           nle_b200_allreduce_fn allreduce, void* user) {
+    if (T < 1) throw InvalidArg{"nSinkhornIter must be >= 1"};
+    if (nEig < 1) throw InvalidArg{"nEigenVectors must be >= 1"};
+    if (!(hx > 0) || !(hy > 0)) throw InvalidArg{"hx and hy must be positive"};
+    if (row0 < 0 || row1 > rows || row0 >= row1) throw InvalidArg{"invalid row slab"};
+    Grid g = make_grid(rows, cols, nRowSamples, nColSamples);
+    const int p = g.p, nR = g.nR, nC = g.nC;
+    if (!sample_lum_host && !(row0 == 0 && row1 == rows))
+        throw InvalidArg{"sample luminances are required when the slab is not the whole image"};
+
+    auto f = std::make_unique<nle_b200_filter>();
+    f->rows = rows; f->cols = cols; f->row0 = row0; f->row1 = row1;
+    f->nloc = (long long)(row1 - row0) * cols;
+    f->p = p; f->nR = nR; f->nC = nC;
+    f->allreduce = allreduce; f->user = user;
+    cudaStream_t s = nullptr;   // legacy default stream: ordered with the caller's work
+    f->stream = s;
+    const long long nloc = f->nloc;
+    const int nrows = row1 - row0;
+
+    Timer t_total(s);
+    Timer t_setup(s);
+    // ---- tables and sample data
+    DevBuf<int> d_selrows(nR), d_selcols(nC), d_rowa(rows), d_colb(cols);
+    d_selrows.upload(g.sel_rows.data(), nR, s);
+    d_selcols.upload(g.sel_cols.data(), nC, s);
+    d_rowa.upload(g.rowa.data(), rows, s);
+    d_colb.upload(g.colb.data(), cols, s);
+    DevBuf<double> Er((size_t)rows * nR), Ec((size_t)cols * nC), EcT((size_t)cols * nC), Gt(256);
+    launch_tables(rows, cols, nR, nC, d_selrows.p, d_selcols.p, hx, hy, Er.p, Ec.p, EcT.p, Gt.p, s);
+    std::vector<int32_t> sel_h(p);
+    for (int a = 0; a < nR; ++a)
+        for (int b = 0; b < nC; ++b) sel_h[a * nC + b] = g.sel_rows[a] * cols + g.sel_cols[b];
+    DevBuf<int32_t> d_sel(p);
+    d_sel.upload(sel_h.data(), p, s);
+    DevBuf<uint8_t> Ysel(p);
+    std::vector<uint8_t> ysel_h;
+    if (sample_lum_host) {
+        Ysel.upload(sample_lum_host, p, s);
+    } else {
+        // whole image on this device: gather the p sample luminances with strided copies
+        ysel_h.resize(p);
+        for (int a = 0; a < nR; ++a)
+            NLE_CUDA(cudaMemcpy2DAsync(ysel_h.data() + (size_t)a * nC, 1,
+                                       lum_slab + (size_t)g.sel_rows[a] * cols + g.sel_cols[0],
+                                       (size_t)(nC > 1 ? g.sel_cols[1] - g.sel_cols[0] : 1), 1, nC,
+                                       cudaMemcpyDeviceToHost, s));
+        NLE_CUDA(cudaStreamSynchronize(s));
+        Ysel.upload(ysel_h.data(), p, s);
+    }
+    AffinityTables tb;
+    tb.rows = rows; tb.cols = cols; tb.row0 = row0; tb.nrows = nrows;
+    tb.nR = nR; tb.nC = nC; tb.p = p;
+    tb.lum = lum_slab; tb.Er = Er.p; tb.Ec = Ec.p; tb.EcT = EcT.p; tb.Gt = Gt.p; tb.Ysel = Ysel.p;
+    tb.rowa = d_rowa.p; tb.colb = d_colb.p;
+
+    // ---- Ka and its eigen-decomposition (filter.cpp:133-137,144,262)
+    DevBuf<double> Ka((size_t)p * p), U((size_t)p * p), lam(p);
+    DevBuf<int> d_cnt(4);
+    launch_ka(p, nC, d_selrows.p, d_selcols.p, Ysel.p, hx, hy, Ka.p, s);
+    f->times_ms[0] = t_setup.stop();
+    Timer t_eig1(s);
+    EigWorkspace ws;
+    f->eig_sweeps[0] = sym_eig(Ka.p, p, p, kEps, /*psd_hint=*/true, U.p, lam.p, d_cnt.p, ws, s);
+    const int r = read_int(d_cnt.p, s);
+    f->times_ms[1] = t_eig1.stop();
+    f->r = r;
+    if (r < 1) throw Unsupported{"Ka has no eigenvalue >= 1e-10"};
+
+    // ---- Sinkhorn on the factors (filter.cpp:230-245)
+    Timer t_sink(s);
+    DevBuf<double> inv_lam(p), xsel(p), ysel(p), svec(p), tvec(p), t2(p), wvec(p), lt(p);
+    DevBuf<double> xfull((size_t)nloc), cfull((size_t)nloc);
+    DevBuf<double> spart(((size_t)nrows + cdiv(nrows, 32) + 1) * p);
+    copy_dd(inv_lam.p, lam.p, p, s);
+    guarded_reciprocal(inv_lam.p, r, kEps, s);            // filter.cpp:265-266
+    // t = phi^T x = U_r^T x_sel + Lam^-1 U_r^T (Kab x_rest)
+    auto phiT_x = [&](const double* x_sel, const double* s_vec) {
+        dgemv_t(p, r, U.p, p, x_sel, tvec.p, s);
+        dgemv_t(p, r, U.p, p, s_vec, t2.p, s);
+        vec_axpy(tvec.p, t2.p, inv_lam.p, r, s);          // tvec += inv_lam o t2
+    };
+    // one half-step: x = recip(K~ applied to the vector whose phi^T image is tvec)
+    auto half_step = [&](double* x_sel_out, bool need_rest) {
+        dgemv_n(p, r, U.p, p, tvec.p, wvec.p, s);          // w = U_r t       (rest pixels: k_j^T w)
+        vec_mul(lt.p, lam.p, tvec.p, r, s);                // Lam t
+        dgemv_n(p, r, U.p, p, lt.p, x_sel_out, s);         // samples: U[s,:] Lam t
+        guarded_reciprocal(x_sel_out, p, kEps, s);
+        if (need_rest) {
+            launch_pass_dot(tb, wvec.p, xfull.p, s);
+            launch_pass_reduce(tb, xfull.p, spart.p, svec.p, s);
+            do_allreduce(f.get(), svec.p, p);
+        }
+    };
+    // initial r = 1 : s0 = Kab 1
+    launch_fill(xfull.p, nloc, 1.0, s);
+    launch_mask_samples(tb, xfull.p, s);
+    launch_pass_reduce(tb, xfull.p, spart.p, svec.p, s);
+    do_allreduce(f.get(), svec.p, p);
+    launch_fill(xsel.p, p, 1.0, s);
+    phiT_x(xsel.p, svec.p);
+    DevBuf<double> csel(p), rsel(p);
+    for (int it = 0; it < T; ++it) {
+        half_step(csel.p, true);                           // c = recip(K~ r)          (:239-240)
+        copy_dd(cfull.p, xfull.p, (size_t)nloc, s);
+        phiT_x(csel.p, svec.p);
+        const bool last = (it == T - 1);
+        half_step(rsel.p, !last);                          // r = recip(K~ c)          (:243-244)
+        if (!last) phiT_x(rsel.p, svec.p);                 // the final r is only used on perm[0:r]
+    }
+    f->times_ms[2] = t_sink.stop();
+
+    // ---- Gram of the rest pixels (filter.cpp:296 "Wab * Wab^T" in factor form, App. A.5)
+    Timer t_gram(s);
+    DevBuf<double> Gp((size_t)p * p);
+    {
+        DevBuf<double> gscratch(gram_scratch_doubles(tb));
+        launch_gram(tb, cfull.p, gscratch.p, Gp.p, s);
+        do_allreduce(f.get(), Gp.p, (size_t)p * p);
+        NLE_CUDA(cudaStreamSynchronize(s));
+    }
+    f->times_ms[3] = t_gram.stop();
+
+    // ---- small algebra: Wa, Wab Wab^T, orthogonalisation (filter.cpp:247-250, 282-327)
+    Timer t_small(s);
+    // phi_top = U[0:r,0:r] (the first r samples are the "landmarks", filter.cpp:247)
+    DevBuf<double> Lm((size_t)r * r), Ct((size_t)r * r), Wa((size_t)r * r), Bm((size_t)r * p),
+        T1((size_t)r * p), WW((size_t)r * r);
+    scale_rows_cols(r, r, U.p, p, rsel.p, lam.p, Lm.p, r, s);          // L = diag(rvec) phi_top Lam
+    scale_rows_cols(r, r, U.p, p, csel.p, nullptr, Ct.p, r, s);        // diag(c) phi_top
+    dgemm(false, true, r, r, r, 1.0, Lm.p, r, Ct.p, r, 0.0, Wa.p, r, s);            // Wa  (:249)
+    // B = diag(rvec) phi_top U_r^T  (r x p): Lambda^-1 of phi cancels against Lambda of L exactly
+    dgemm(false, true, r, p, r, 1.0, U.p, p, U.p, p, 0.0, Bm.p, r, s);
+    scale_rows_cols(r, p, Bm.p, r, rsel.p, nullptr, Bm.p, r, s);
+    dgemm(false, false, r, p, p, 1.0, Bm.p, r, Gp.p, p, 0.0, T1.p, r, s);
+    dgemm(false, true, r, r, p, 1.0, T1.p, r, Bm.p, r, 0.0, WW.p, r, s);            // Wab_rest Wab_rest^T
+    if (p > r) {
+        // samples r..p-1 are demoted to "rest" by filter.cpp:247: add L (dem^T dem) L^T
+        const int nd = p - r;
+        DevBuf<double> dem((size_t)nd * r), D2((size_t)r * r), T3((size_t)r * r);
+        scale_rows_cols(nd, r, U.p + r, p, csel.p + r, nullptr, dem.p, nd, s);
+        dgemm(true, false, r, r, nd, 1.0, dem.p, nd, dem.p, nd, 0.0, D2.p, r, s);
+        dgemm(false, false, r, r, r, 1.0, Lm.p, r, D2.p, r, 0.0, T3.p, r, s);
+        dgemm(false, true, r, r, r, 1.0, T3.p, r, Lm.p, r, 1.0, WW.p, r, s);
+    }
+    // eig(Wa) -> Wa^-1/2 (pseudo-inverse root on lambda >= 1e-10, filter.cpp:287-292)
+    DevBuf<double> Ua((size_t)r * r), la(r), irl(r), UaS((size_t)r * r), irw((size_t)r * r);
+    f->eig_sweeps[1] = sym_eig(Wa.p, r, r, kEps, /*psd_hint=*/false, Ua.p, la.p, d_cnt.p, ws, s);
+    const int r2 = read_int(d_cnt.p, s);
+    f->r2 = r2;
+    if (r2 < 1) throw Unsupported{"Wa has no eigenvalue >= 1e-10"};
+    guarded_inv_sqrt(la.p, irl.p, r2, kEps, s);
+    scale_rows_cols(r, r2, Ua.p, r, nullptr, irl.p, UaS.p, r, s);
+    dgemm(false, true, r, r, r2, 1.0, UaS.p, r, Ua.p, r, 0.0, irw.p, r, s);          // invRootWa (:292)
+    // Q = Wa + invRootWa (Wab Wab^T) invRootWa  (:296)
+    DevBuf<double> T2((size_t)r * r), Q((size_t)r * r);
+    dgemm(false, false, r, r, r, 1.0, irw.p, r, WW.p, r, 0.0, T2.p, r, s);
+    copy_dd(Q.p, Wa.p, (size_t)r * r, s);
+    dgemm(false, false, r, r, r, 1.0, T2.p, r, irw.p, r, 1.0, Q.p, r, s);
+    DevBuf<double> Vq((size_t)r * r), Sq(r);
+    f->eig_sweeps[2] = sym_eig(Q.p, r, r, kEps, /*psd_hint=*/false, Vq.p, Sq.p, d_cnt.p, ws, s);
+    const int nq = read_int(d_cnt.p, s);
+    const int k = std::min(nEig, nq);                                                // :314
+    f->k = k;
+    if (k < 1) throw Unsupported{"Q has no eigenvalue >= 1e-10"};
+    f->S.resize(k);
+    NLE_CUDA(cudaMemcpyAsync(f->S.data(), Sq.p, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s));
+    // Mv = invRootWa Vq Sq^-1/2 (r x k)
+    DevBuf<double> irs(k), VqS((size_t)r * k), Mv((size_t)r * k);
+    guarded_inv_sqrt(Sq.p, irs.p, k, kEps, s);                                       // :319-321
+    scale_rows_cols(r, k, Vq.p, r, nullptr, irs.p, VqS.p, r, s);
+    dgemm(false, false, r, k, r, 1.0, irw.p, r, VqS.p, r, 0.0, Mv.p, r, s);
+    f->times_ms[4] = t_small.stop();
+
+    // ---- extension V = [Wa ; Wab^T] invRootWa Vq Sq^-1/2 (:324-327) and un-permute (:502)
+    Timer t_ext(s);
+    f->V.alloc((size_t)nloc * k);
+    DevBuf<double> Vtop((size_t)r * k), Zr((size_t)r * k), RM((size_t)r * k), Y1((size_t)r * k),
+        Y((size_t)p * k);
+    dgemm(false, false, r, k, r, 1.0, Wa.p, r, Mv.p, r, 0.0, Vtop.p, r, s);          // rows of Wa
+    launch_scatter_rows(tb, d_sel.p, 0, r, Vtop.p, r, k, f->V.p, s);
+    dgemm(true, false, r, k, r, 1.0, Lm.p, r, Mv.p, r, 0.0, Zr.p, r, s);             // Z_rest = L^T Mv
+    if (p > r) {
+        const int nd = p - r;
+        DevBuf<double> Vd((size_t)nd * k);
+        dgemm(false, false, nd, k, r, 1.0, U.p + r, p, Zr.p, r, 0.0, Vd.p, nd, s);
+        scale_rows_cols(nd, k, Vd.p, nd, csel.p + r, nullptr, Vd.p, nd, s);
+        launch_scatter_rows(tb, d_sel.p, r, nd, Vd.p, nd, k, f->V.p, s);
+        NLE_CUDA(cudaStreamSynchronize(s));
+    }
+    // Y = U_r (phi_top^T diag(rvec) Mv)   (p x k); rest pixels: V_j = c_j k_j^T Y
+    scale_rows_cols(r, k, Mv.p, r, rsel.p, nullptr, RM.p, r, s);
+    dgemm(true, false, r, k, r, 1.0, U.p, p, RM.p, r, 0.0, Y1.p, r, s);
+    dgemm(false, false, p, k, r, 1.0, U.p, p, Y1.p, r, 0.0, Y.p, p, s);
+    launch_extension(tb, cfull.p, Y.p, k, f->V.p, s);
+    NLE_CUDA(cudaStreamSynchronize(s));
+    f->times_ms[5] = t_ext.stop();
+    f->times_ms[6] = t_total.stop();
+
+    f->ascratch.alloc((size_t)apply_blocks(nloc) * k + 16);
+    f->avec.alloc(4 * (size_t)k + 16);
+    if (g_keep_stages) {
+        f->Ka = std::move(Ka);
+        f->lam.alloc(r); copy_dd(f->lam.p, lam.p, r, s);
+        f->rvec_head.alloc(r); copy_dd(f->rvec_head.p, rsel.p, r, s);
+        launch_gather_c_sel(tb, d_sel.p, csel.p, cfull.p, s);
+        f->c = std::move(cfull);
+        f->Wa = std::move(Wa);
+        f->Q = std::move(Q);
+        f->la.alloc(r2); copy_dd(f->la.p, la.p, r2, s);
+        f->Gram = std::move(Gp);
+        NLE_CUDA(cudaStreamSynchronize(s));
+    }
+    return f;
+}
+
+// ------------------------------------------------------------------------------------------
+// apply / enhance on device buffers
+static void apply_core(const nle_b200_filter* f, const uint8_t* z8, const double* z64, const double* g_host,
+                       double* out64, uint8_t* out8) {
+    cudaStream_t s = f->stream;
+    const int k = f->k;
+    double* tvec = f->avec.p;
+    double* gvec = f->avec.p + k;
+    double* gmul = f->avec.p + 2 * (size_t)k;
+    launch_vtz(f->nloc, k, f->V.p, z8, z64, f->ascratch.p, tvec, s);                // V^T z
+    do_allreduce(const_cast<nle_b200_filter*>(f), tvec, (size_t)k);
+    NLE_CUDA(cudaMemcpyAsync(gmul, g_host, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, s));
+    vec_mul(gvec, gmul, tvec, k, s);                                                 // diag(fS) (V^T z)
+    launch_recompose(f->nloc, k, f->V.p, gvec, out64, out8, s);
+}
+
+static std::vector<double> transform_eigenvalues(const double* S, int k, const double* w, int m) {
+    // filter.cpp:334-347
+    std::vector<double> fS(k);
+    for (int i = 0; i < k; ++i) {
+        double eig = S[i];
+        fS[i] = w[0];
+        for (int q = 1; q < m; ++q) fS[i] += (w[q] - w[q - 1]) * std::pow(eig, (double)q);
+    }
+    return fS;
+}
+
+template <typename F>
+static int guarded(F&& fn) {
+    try {
+        fn();
+        return NLE_B200_OK;
+    } catch (const InvalidArg& e) { set_error(e.msg); return NLE_B200_ERR_INVALID; }
+    catch (const Unsupported& e) { set_error(e.msg); return NLE_B200_ERR_UNSUPPORTED; }
+    catch (const NoConvergence& e) { set_error(e.msg); return NLE_B200_ERR_NOCONV; }
+    catch (const CudaError& e) {
+        set_error(std::string("CUDA error: ") + cudaGetErrorString(e.e) + " at " + e.file + ":" + std::to_string(e.line) + " (" + e.what + ")");
+        cudaGetLastError();
+        return NLE_B200_ERR_CUDA;
+    } catch (const std::exception& e) { set_error(e.what()); return NLE_B200_ERR_INVALID; }
+}
+
+static void require_device() {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n < 1) {
+        cudaGetLastError();
+        throw CudaError{e == cudaSuccess ? cudaErrorNoDevice : e, "no CUDA device: libnle_b200 has no CPU fallback", __FILE__, __LINE__};
+    }
+}
+
+// dense helper: eigen-decomposition of a host matrix
+static int eig_host(const double* M, int n, double eps, bool psd, double* U, double* D) {
+    cudaStream_t s = nullptr;
+    DevBuf<double> dM((size_t)n * n), dU((size_t)n * n), dD(n);
+    DevBuf<int> dr(1);
+    dM.upload(M, (size_t)n * n, s);
+    EigWorkspace ws;
+    sym_eig(dM.p, n, n, eps, psd, dU.p, dD.p, dr.p, ws, s);
+    int r = read_int(dr.p, s);
+    dU.download(U, (size_t)n * n, s);
+    dD.download(D, n, s);
+    NLE_CUDA(cudaStreamSynchronize(s));
+    return r;
+}
+
+}  // namespace nle
+
+// =============================================================================================
+extern "C" {
+
+const char* nle_b200_last_error(void) { return g_error.c_str(); }
+int nle_b200_version(void) { return 100; }
+int nle_b200_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+void nle_b200_set_keep_stages(int keep) { g_keep_stages = keep; }
+long long nle_b200_launch_count(int reset) {
+    long long v = g_launches;
+    if (reset) g_launches = 0;
+    return v;
+}
+
+int nle_b200_sample_count(int rows, int cols, int nRowSamples, int nColSamples, int* p_out) {
+    return guarded([&] {
+        Grid g = make_grid(rows, cols, nRowSamples, nColSamples);
+        if (p_out) *p_out = g.p;
+    });
+}
+
+int nle_b200_sample_indices(int rows, int cols, int nRowSamples, int nColSamples,
+                            int32_t* selected, int32_t* rest) {
+    return guarded([&] {
+        require_device();
+        Grid g = make_grid(rows, cols, nRowSamples, nColSamples);
+        cudaStream_t s = nullptr;
+        const long long N = (long long)rows * cols;
+        DevBuf<int> rowa(rows), colb(cols), rr(rows), cr(cols);
+        rowa.upload(g.rowa.data(), rows, s); colb.upload(g.colb.data(), cols, s);
+        rr.upload(g.rowrank.data(), rows, s); cr.upload(g.colrank.data(), cols, s);
+        DevBuf<int32_t> dsel(g.p), drest(rest ? (size_t)(N - g.p) : 0);
+        launch_sample_indices(rows, cols, rowa.p, colb.p, rr.p, cr.p, g.nC, dsel.p, rest ? drest.p : nullptr, s);
+        dsel.download(selected, g.p, s);
+        if (rest && N - g.p > 0) drest.download(rest, (size_t)(N - g.p), s);
+        NLE_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int nle_b200_eigen_decomposition(const double* M, int n, double eps, double* U, double* D, int* r_out) {
+    return guarded([&] {
+        require_device();
+        if (n < 0) throw InvalidArg{"n must be >= 0"};
+        int r = (n == 0) ? 0 : eig_host(M, n, eps, false, U, D);
+        if (r_out) *r_out = r;
+    });
+}
+
+int nle_b200_transform_eigenvalues(const double* eigvals, int k, const double* weights, int m, double* fS) {
+    return guarded([&] {
+        if (m < 1) throw InvalidArg{"at least one weight is required"};
+        auto v = transform_eigenvalues(eigvals, k, weights, m);
+        std::copy(v.begin(), v.end(), fS);
+    });
+}
+
+static void upload_checked_u8(const double* channel, long long n, DevBuf<uint8_t>& out, cudaStream_t s) {
+    DevBuf<double> tmp((size_t)n);
+    DevBuf<int> bad(1);
+    tmp.upload(channel, (size_t)n, s);
+    bad.zero(s);
+    out.alloc((size_t)n);
+    launch_u8_from_f64(tmp.p, n, out.p, bad.p, s);
+    if (read_int(bad.p, s))
+        throw Unsupported{"luminance channel must hold integer values in [0,255] (8-bit Lab L as produced by getLuminanceChannel, filter.cpp:460-469)"};
+}
+
+int nle_b200_compute_kernel(const double* channel, int rows, int cols, int nRowSamples, int nColSamples,
+                            double hx, double hy, int32_t* perm, double* Ka, double* Kab) {
+    return guarded([&] {
+        require_device();
+        Grid g = make_grid(rows, cols, nRowSamples, nColSamples);
+        cudaStream_t s = nullptr;
+        const long long N = (long long)rows * cols;
+        const int p = g.p;
+        DevBuf<uint8_t> lum;
+        upload_checked_u8(channel, N, lum, s);
+        std::vector<uint8_t> ys(p);
+        for (int a = 0; a < g.nR; ++a)
+            for (int b = 0; b < g.nC; ++b) ys[a * g.nC + b] = (uint8_t)channel[(size_t)g.sel_rows[a] * cols + g.sel_cols[b]];
+        DevBuf<uint8_t> Ysel(p);
+        Ysel.upload(ys.data(), p, s);
+        DevBuf<int> sr(g.nR), sc(g.nC);
+        sr.upload(g.sel_rows.data(), g.nR, s); sc.upload(g.sel_cols.data(), g.nC, s);
+        if (Ka) {
+            DevBuf<double> dKa((size_t)p * p);
+            launch_ka(p, g.nC, sr.p, sc.p, Ysel.p, hx, hy, dKa.p, s);
+            dKa.download(Ka, (size_t)p * p, s);
+            NLE_CUDA(cudaStreamSynchronize(s));
+        }
+        std::vector<int32_t> permv;
+        if (perm || Kab) {
+            permv.resize(N);
+            int32_t* sel = permv.data();
+            int32_t* rest = permv.data() + p;
+            long long ns = 0, nr = 0;
+            for (int r = 0; r < rows; ++r)
+                for (int c = 0; c < cols; ++c) {
+                    if (g.rowa[r] >= 0 && g.colb[c] >= 0) sel[ns++] = r * cols + c; else rest[nr++] = r * cols + c;
+                }
+            if (perm) std::copy(permv.begin(), permv.end(), perm);
+        }
+        if (Kab) {
+            // dense Kab only for small test inputs: evaluate columns through the extension kernel with Y = I_p
+            const long long nrest = N - p;
+            if ((double)p * (double)N * 8.0 > 2e9) throw Unsupported{"dense Kab requested for a large image; the product path never materialises it"};
+            DevBuf<int> rowa(rows), colb(cols);
+            rowa.upload(g.rowa.data(), rows, s); colb.upload(g.colb.data(), cols, s);
+            DevBuf<double> Er((size_t)rows * g.nR), Ec((size_t)cols * g.nC), EcT((size_t)cols * g.nC), Gt(256);
+            launch_tables(rows, cols, g.nR, g.nC, sr.p, sc.p, hx, hy, Er.p, Ec.p, EcT.p, Gt.p, s);
+            AffinityTables tb;
+            tb.rows = rows; tb.cols = cols; tb.row0 = 0; tb.nrows = rows; tb.nR = g.nR; tb.nC = g.nC; tb.p = p;
+            tb.lum = lum.p; tb.Er = Er.p; tb.Ec = Ec.p; tb.EcT = EcT.p; tb.Gt = Gt.p; tb.Ysel = Ysel.p;
+            tb.rowa = rowa.p; tb.colb = colb.p;
+            std::vector<double> eye((size_t)p * p, 0.0);
+            for (int i = 0; i < p; ++i) eye[i + (size_t)i * p] = 1.0;
+            DevBuf<double> Y((size_t)p * p), ones((size_t)N), Vd((size_t)N * p);
+            Y.upload(eye.data(), (size_t)p * p, s);
+            launch_fill(ones.p, N, 1.0, s);
+            Vd.zero(s);
+            launch_extension(tb, ones.p, Y.p, p, Vd.p, s);
+            std::vector<double> Vh((size_t)N * p);
+            Vd.download(Vh.data(), (size_t)N * p, s);
+            NLE_CUDA(cudaStreamSynchronize(s));
+            for (long long j = 0; j < nrest; ++j) {
+                const double* src = Vh.data() + (size_t)permv[p + j] * p;
+                for (int i = 0; i < p; ++i) Kab[i + (size_t)j * p] = src[i];
+            }
+        }
+    });
+}
+
+int nle_b200_nystrom_approximation(const double* Ka, int p, const double* Kab, int nrest,
+                                   double* eigvals, double* phi, int* r_out) {
+    return guarded([&] {
+        require_device();
+        if (p < 1 || nrest < 0) throw InvalidArg{"bad sizes"};
+        cudaStream_t s = nullptr;
+        const int n = p + nrest;
+        DevBuf<double> dKa((size_t)p * p), U((size_t)p * p), lam(p), inv(p);
+        DevBuf<int> dr(1);
+        dKa.upload(Ka, (size_t)p * p, s);
+        EigWorkspace ws;
+        sym_eig(dKa.p, p, p, kEps, false, U.p, lam.p, dr.p, ws, s);
+        int r = read_int(dr.p, s);
+        DevBuf<double> dphi((size_t)n * p);
+        dphi.zero(s);
+        // phi << U, Kab^T U Lam^-1   (filter.cpp:275)
+        NLE_CUDA(cudaMemcpy2DAsync(dphi.p, (size_t)n * 8, U.p, (size_t)p * 8, (size_t)p * 8, r, cudaMemcpyDeviceToDevice, s));
+        if (nrest > 0 && r > 0) {
+            DevBuf<double> dKab((size_t)p * nrest);
+            dKab.upload(Kab, (size_t)p * nrest, s);
+            copy_dd(inv.p, lam.p, p, s);
+            guarded_reciprocal(inv.p, r, kEps, s);
+            dgemm(true, false, nrest, r, p, 1.0, dKab.p, p, U.p, p, 0.0, dphi.p + p, n, s);
+            scale_rows_cols(nrest, r, dphi.p + p, n, nullptr, inv.p, dphi.p + p, n, s);
+            NLE_CUDA(cudaStreamSynchronize(s));
+        }
+        dphi.download(phi, (size_t)n * p, s);
+        lam.download(eigvals, p, s);
+        NLE_CUDA(cudaStreamSynchronize(s));
+        if (r_out) *r_out = r;
+    });
+}
+
+int nle_b200_sinkhorn(const double* phi, int n, int r, const double* eigvals, int maxIter,
+                      double* Wa, double* Wab) {
+    return guarded([&] {
+        require_device();
+        if (n < 1 || r < 1 || r > n || maxIter < 0) throw InvalidArg{"bad sizes"};
+        cudaStream_t s = nullptr;
+        DevBuf<double> P((size_t)n * r), lam(r), rv(n), cv(n), t(r);
+        P.upload(phi, (size_t)n * r, s);
+        lam.upload(eigvals, r, s);
+        launch_fill(rv.p, n, 1.0, s);
+        cv.zero(s);
+        for (int it = 0; it < maxIter; ++it) {                     // filter.cpp:238-245
+            dgemv_t(n, r, P.p, n, rv.p, t.p, s);
+            vec_mul(t.p, lam.p, t.p, r, s);
+            dgemv_n(n, r, P.p, n, t.p, cv.p, s);
+            guarded_reciprocal(cv.p, n, kEps, s);
+            dgemv_t(n, r, P.p, n, cv.p, t.p, s);
+            vec_mul(t.p, lam.p, t.p, r, s);
+            dgemv_n(n, r, P.p, n, t.p, rv.p, s);
+            guarded_reciprocal(rv.p, n, kEps, s);
+        }
+        // p = phi.cols() (:247);  Wa = (R phi_top D)(c_head o phi_top)^T, Wab = (R phi_top D)(c_tail o phi_bot)^T
+        DevBuf<double> L((size_t)r * r), CP((size_t)n * r), dWa((size_t)r * r), dWab((size_t)r * std::max(1, n - r));
+        scale_rows_cols(r, r, P.p, n, rv.p, lam.p, L.p, r, s);
+        scale_rows_cols(n, r, P.p, n, cv.p, nullptr, CP.p, n, s);
+        dgemm(false, true, r, r, r, 1.0, L.p, r, CP.p, n, 0.0, dWa.p, r, s);
+        dWa.download(Wa, (size_t)r * r, s);
+        if (n - r > 0) {
+            dgemm(false, true, r, n - r, r, 1.0, L.p, r, CP.p + r, n, 0.0, dWab.p, r, s);
+            if (Wab) dWab.download(Wab, (size_t)r * (n - r), s);
+        }
+        NLE_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int nle_b200_orthogonalize(const double* Wa, int p, const double* Wab, int nrest, int nEigVectors,
+                           double eps, double* V, double* S, int* k_out) {
+    return guarded([&] {
+        require_device();
+        if (p < 1 || nrest < 0 || nEigVectors < 1) throw InvalidArg{"bad sizes"};
+        cudaStream_t s = nullptr;
+        const int n = p + nrest;
+        DevBuf<double> dWa((size_t)p * p), dWab((size_t)p * std::max(1, nrest)), Ua((size_t)p * p), la(p), irl(p),
+            UaS((size_t)p * p), irw((size_t)p * p), G((size_t)p * p), T2((size_t)p * p), Q((size_t)p * p),
+            Vq((size_t)p * p), Sq(p);
+        DevBuf<int> dr(1);
+        dWa.upload(Wa, (size_t)p * p, s);
+        if (nrest > 0) dWab.upload(Wab, (size_t)p * nrest, s);
+        EigWorkspace ws;
+        sym_eig(dWa.p, p, p, kEps, false, Ua.p, la.p, dr.p, ws, s);    // default eps of eigenDecomposition (:287)
+        int r2 = read_int(dr.p, s);
+        irw.zero(s);
+        if (r2 > 0) {
+            guarded_inv_sqrt(la.p, irl.p, r2, kEps, s);
+            scale_rows_cols(p, r2, Ua.p, p, nullptr, irl.p, UaS.p, p, s);
+            dgemm(false, true, p, p, r2, 1.0, UaS.p, p, Ua.p, p, 0.0, irw.p, p, s);
+        }
+        G.zero(s);
+        if (nrest > 0) dgemm(false, true, p, p, nrest, 1.0, dWab.p, p, dWab.p, p, 0.0, G.p, p, s);
+        dgemm(false, false, p, p, p, 1.0, irw.p, p, G.p, p, 0.0, T2.p, p, s);
+        copy_dd(Q.p, dWa.p, (size_t)p * p, s);
+        dgemm(false, false, p, p, p, 1.0, T2.p, p, irw.p, p, 1.0, Q.p, p, s);
+        sym_eig(Q.p, p, p, kEps, false, Vq.p, Sq.p, dr.p, ws, s);
+        int nq = read_int(dr.p, s);
+        int k = std::min(nEigVectors, nq);
+        (void)eps;   // the reference only uses eps in a debug print (:299)
+        if (k_out) *k_out = k;
+        if (k > 0) {
+            DevBuf<double> irs(k), VqS((size_t)p * k), Mv((size_t)p * k), tmp((size_t)n * p), Vd((size_t)n * k);
+            guarded_inv_sqrt(Sq.p, irs.p, k, kEps, s);
+            scale_rows_cols(p, k, Vq.p, p, nullptr, irs.p, VqS.p, p, s);
+            dgemm(false, false, p, k, p, 1.0, irw.p, p, VqS.p, p, 0.0, Mv.p, p, s);
+            // tmp << Wa, Wab^T  (:324-325);  V = tmp * invRootWa * Vq * diag (:327)
+            dgemm(false, false, p, k, p, 1.0, dWa.p, p, Mv.p, p, 0.0, Vd.p, n, s);
+            if (nrest > 0) dgemm(true, false, nrest, k, p, 1.0, dWab.p, p, Mv.p, p, 0.0, Vd.p + p, n, s);
+            Vd.download(V, (size_t)n * k, s);
+            Sq.download(S, k, s);
+            NLE_CUDA(cudaStreamSynchronize(s));
+        }
+    });
+}
+
+// ---- training ---------------------------------------------------------------------------------
+static int train_host_u8(const uint8_t* lum, int rows, int cols, int row0, int row1, int nRS, int nCS,
+                         double hx, double hy, int T, int nEig, nle_b200_allreduce_fn ar, void* user,
+                         nle_b200_filter** out) {
+    return guarded([&] {
+        require_device();
+        if (!lum || !out) throw InvalidArg{"null pointer"};
+        *out = nullptr;
+        Grid g = make_grid(rows, cols, nRS, nCS);
+        if (row0 < 0 || row1 > rows || row0 >= row1) throw InvalidArg{"invalid row slab"};
+        std::vector<uint8_t> ys(g.p);
+        for (int a = 0; a < g.nR; ++a)
+            for (int b = 0; b < g.nC; ++b) ys[a * g.nC + b] = lum[(size_t)g.sel_rows[a] * cols + g.sel_cols[b]];
+        const size_t nloc = (size_t)(row1 - row0) * cols;
+        DevBuf<uint8_t> d(nloc);
+        d.upload(lum + (size_t)row0 * cols, nloc, nullptr);
+        auto f = train_core(d.p, rows, cols, row0, row1, ys.data(), nRS, nCS, hx, hy, T, nEig, ar, user);
+        *out = f.release();
+    });
+}
+
+int nle_b200_train_u8(const uint8_t* lum, int rows, int cols, int nRowSamples, int nColSamples,
+                      double hx, double hy, int nSinkhornIter, int nEigenVectors, nle_b200_filter** out) {
+    return train_host_u8(lum, rows, cols, 0, rows, nRowSamples, nColSamples, hx, hy, nSinkhornIter,
+                         nEigenVectors, nullptr, nullptr, out);
+}
+
+int nle_b200_train_u8_sharded(const uint8_t* lum, int rows, int cols, int row0, int row1,
+                              int nRowSamples, int nColSamples, double hx, double hy,
+                              int nSinkhornIter, int nEigenVectors, nle_b200_allreduce_fn allreduce,
+                              void* user, nle_b200_filter** out) {
+    return train_host_u8(lum, rows, cols, row0, row1, nRowSamples, nColSamples, hx, hy, nSinkhornIter,
+                         nEigenVectors, allreduce, user, out);
+}
+
+int nle_b200_train(const double* channel, int rows, int cols, int nRowSamples, int nColSamples,
+                   double hx, double hy, int nSinkhornIter, int nEigenVectors, nle_b200_filter** out) {
+    return guarded([&] {
+        require_device();
+        if (!channel || !out) throw InvalidArg{"null pointer"};
+        *out = nullptr;
+        Grid g = make_grid(rows, cols, nRowSamples, nColSamples);
+        const long long N = (long long)rows * cols;
+        DevBuf<uint8_t> lum;
+        upload_checked_u8(channel, N, lum, nullptr);
+        auto f = train_core(lum.p, rows, cols, 0, rows, nullptr, nRowSamples, nColSamples, hx, hy,
+                            nSinkhornIter, nEigenVectors, nullptr, nullptr);
+        *out = f.release();
+    });
+}
+
+int nle_b200_train_u8_dev(const uint8_t* lum_slab_dev, int rows, int cols, int row0, int row1,
+                          const uint8_t* sample_lum, int nRowSamples, int nColSamples, double hx,
+                          double hy, int nSinkhornIter, int nEigenVectors,
+                          nle_b200_allreduce_fn allreduce, void* user, nle_b200_filter** out) {
+    return guarded([&] {
+        require_device();
+        if (!lum_slab_dev || !out) throw InvalidArg{"null pointer"};
+        *out = nullptr;
+        auto f = train_core(lum_slab_dev, rows, cols, row0, row1, sample_lum, nRowSamples, nColSamples,
+                            hx, hy, nSinkhornIter, nEigenVectors, allreduce, user);
+        *out = f.release();
+    });
+}
+
+int nle_b200_filter_info(const nle_b200_filter* f, nle_b200_info* info) {
+    return guarded([&] {
+        if (!f || !info) throw InvalidArg{"null pointer"};
+        info->rows = f->rows; info->cols = f->cols; info->row0 = f->row0; info->row1 = f->row1;
+        info->p = f->p; info->r = f->r; info->r2 = f->r2; info->k = f->k;
+        info->n_row_samples_eff = f->nR; info->n_col_samples_eff = f->nC;
+        for (int i = 0; i < 3; ++i) info->eig_sweeps[i] = f->eig_sweeps[i];
+    });
+}
+
+int nle_b200_eigenvalues(const nle_b200_filter* f, double* S) {
+    return guarded([&] {
+        if (!f || !S) throw InvalidArg{"null pointer"};
+        std::copy(f->S.begin(), f->S.end(), S);
+    });
+}
+
+int nle_b200_eigenvectors(const nle_b200_filter* f, double* V) {
+    return guarded([&] {
+        if (!f || !V) throw InvalidArg{"null pointer"};
+        const size_t n = (size_t)f->nloc, k = (size_t)f->k;
+        std::vector<double> rowmajor(n * k);
+        f->V.download(rowmajor.data(), n * k, f->stream);
+        NLE_CUDA(cudaStreamSynchronize(f->stream));
+        for (size_t j = 0; j < n; ++j)
+            for (size_t v = 0; v < k; ++v) V[j + v * n] = rowmajor[j * k + v];
+    });
+}
+
+int nle_b200_apply(const nle_b200_filter* f, const double* channel, const double* fS, double* out) {
+    return guarded([&] {
+        if (!f || !channel || !fS || !out) throw InvalidArg{"null pointer"};
+        auto* ff = const_cast<nle_b200_filter*>(f);
+        const size_t n = (size_t)f->nloc;
+        if (ff->io64_in.n < n) { ff->io64_in.alloc(n); ff->io64_out.alloc(n); }
+        ff->io64_in.upload(channel, n, f->stream);
+        apply_core(f, nullptr, ff->io64_in.p, fS, ff->io64_out.p, nullptr);
+        ff->io64_out.download(out, n, f->stream);
+        NLE_CUDA(cudaStreamSynchronize(f->stream));
+    });
+}
+
+int nle_b200_enhance_luminance_u8_dev(const nle_b200_filter* f, const uint8_t* lum_slab_dev,
+                                      const double* weights, int m, uint8_t* out_slab_dev) {
+    return guarded([&] {
+        if (!f || !lum_slab_dev || !weights || !out_slab_dev) throw InvalidArg{"null pointer"};
+        if (m < 1) throw InvalidArg{"at least one weight is required"};
+        auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);             // filter.cpp:428
+        apply_core(f, lum_slab_dev, nullptr, fS.data(), nullptr, out_slab_dev);     // :431-436
+    });
+}
+
+int nle_b200_enhance_luminance_u8(const nle_b200_filter* f, const uint8_t* lum, const double* weights,
+                                  int m, uint8_t* out) {
+    return guarded([&] {
+        if (!f || !lum || !weights || !out) throw InvalidArg{"null pointer"};
+        if (m < 1) throw InvalidArg{"at least one weight is required"};
+        auto* ff = const_cast<nle_b200_filter*>(f);
+        const size_t n = (size_t)f->nloc;
+        if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
+        ff->io8_in.upload(lum, n, f->stream);
+        auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);
+        apply_core(f, ff->io8_in.p, nullptr, fS.data(), nullptr, ff->io8_out.p);
+        ff->io8_out.download(out, n, f->stream);
+        NLE_CUDA(cudaStreamSynchronize(f->stream));
+    });
+}
+
+int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, double kpow, uint8_t* out) {
+    return guarded([&] {
+        if (!f || !chan || !out) throw InvalidArg{"null pointer"};
+        auto* ff = const_cast<nle_b200_filter*>(f);
+        const size_t n = (size_t)f->nloc;
+        if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
+        ff->io8_in.upload(chan, n, f->stream);
+        std::vector<double> te(f->k);
+        for (int i = 0; i < f->k; ++i) te[i] = std::pow(std::min(f->S[i], 1.0), kpow);   // filter.cpp:378-385
+        apply_core(f, ff->io8_in.p, nullptr, te.data(), nullptr, ff->io8_out.p);
+        ff->io8_out.download(out, n, f->stream);
+        NLE_CUDA(cudaStreamSynchronize(f->stream));
+    });
+}
+
+int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t cap, size_t* size_out) {
+    return guarded([&] {
+        if (!f) throw InvalidArg{"null pointer"};
+        const DevBuf<double>* b = nullptr;
+        switch (which) {
+            case NLE_B200_STAGE_KA: b = &f->Ka; break;
+            case NLE_B200_STAGE_LAMBDA: b = &f->lam; break;
+            case NLE_B200_STAGE_RVEC_HEAD: b = &f->rvec_head; break;
+            case NLE_B200_STAGE_C: b = &f->c; break;
+            case NLE_B200_STAGE_WA: b = &f->Wa; break;
+            case NLE_B200_STAGE_Q: b = &f->Q; break;
+            case NLE_B200_STAGE_LA: b = &f->la; break;
+            case NLE_B200_STAGE_GRAM: b = &f->Gram; break;
+            case NLE_B200_STAGE_TIMES_MS: {
+                if (size_out) *size_out = 8;
+                if (out) for (size_t i = 0; i < std::min<size_t>(cap, 8); ++i) out[i] = f->times_ms[i];
+                return;
+            }
+            default: throw InvalidArg{"unknown stage"};
+        }
+        if (size_out) *size_out = b->n;
+        if (b->n == 0) throw InvalidArg{"stage not kept (nle_b200_set_keep_stages(0) was active)"};
+        if (out && cap) {
+            b->download(out, std::min(cap, b->n), f->stream);
+            NLE_CUDA(cudaStreamSynchronize(f->stream));
+        }
+    });
+}
+
+void nle_b200_free(nle_b200_filter* f) { delete f; }
+
+}  // extern "C"

@@ -1,0 +1,108 @@
+// Internal helpers shared by the translation units of libnle_b200.so (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+
+namespace nle {
+
+constexpr double kEps = 1e-10;  // nle::EPS, include/filter.hpp:14 of the reference
+
+void set_error(const std::string& msg);
+extern thread_local long long g_launches;  // kernels launched by this library on this thread
+
+struct CudaError {
+    cudaError_t e;
+    const char* what;
+    const char* file;
+    int line;
+};
+
+#define NLE_CUDA(call)                                                         \
+    do {                                                                       \
+        cudaError_t _e = (call);                                               \
+        if (_e != cudaSuccess) throw ::nle::CudaError{_e, #call, __FILE__, __LINE__}; \
+    } while (0)
+
+#define NLE_LAUNCH_CHECK()                                                     \
+    do {                                                                       \
+        ++::nle::g_launches;                                                   \
+        cudaError_t _e = cudaGetLastError();                                   \
+        if (_e != cudaSuccess) throw ::nle::CudaError{_e, "kernel launch", __FILE__, __LINE__}; \
+    } while (0)
+
+struct InvalidArg { std::string msg; };
+struct Unsupported { std::string msg; };
+struct NoConvergence { std::string msg; };
+
+// RAII device buffer (typed).
+template <typename T>
+struct DevBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    DevBuf() = default;
+    explicit DevBuf(size_t count) { alloc(count); }
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+    DevBuf(DevBuf&& o) noexcept : p(o.p), n(o.n) { o.p = nullptr; o.n = 0; }
+    DevBuf& operator=(DevBuf&& o) noexcept {
+        if (this != &o) { release(); p = o.p; n = o.n; o.p = nullptr; o.n = 0; }
+        return *this;
+    }
+    ~DevBuf() { release(); }
+    void alloc(size_t count) {
+        release();
+        n = count;
+        if (count) NLE_CUDA(cudaMalloc(&p, count * sizeof(T)));
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        n = 0;
+    }
+    void zero(cudaStream_t s) { if (n) NLE_CUDA(cudaMemsetAsync(p, 0, n * sizeof(T), s)); }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        NLE_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* h, size_t count, cudaStream_t s) const {
+        NLE_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
+inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+int sm_count();
+
+// ---- dense.cu : column-major FP64 building blocks ------------------------------------------
+// C(m x n) = alpha * op(A) * op(B) + beta * C
+void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const double* A, int lda,
+           const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t s);
+// y(m) = A(m x n) x        /  y(n) = A(m x n)^T x
+void dgemv_n(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s);
+void dgemv_t(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s);
+// out(i,j) = rowscale[i] * A(i,j) * colscale[j]   (either scale may be null)
+void scale_rows_cols(int m, int n, const double* A, int lda, const double* rowscale,
+                     const double* colscale, double* out, int ldo, cudaStream_t s);
+// v_i <- 1/v_i if |v_i| >= eps else 0        (inplaceReciprocal, filter.cpp:42-54)
+void guarded_reciprocal(double* v, int n, double eps, cudaStream_t s);
+// v_i <- 1/sqrt(v_i) if |v_i| >= eps else 0  (filter.cpp:289-291, 319-321)
+void guarded_inv_sqrt(const double* v, double* out, int n, double eps, cudaStream_t s);
+
+// ---- eig.cu : symmetric eigensolver (block one-sided Jacobi, FP64, no LAPACK) ---------------
+struct EigWorkspace {
+    DevBuf<double> W, As, T, lam_unsorted;
+    DevBuf<int> ctrl, order;
+    int cap = 0;
+    void reserve(int n);
+};
+// Eigen-decomposition of the symmetric matrix defined by the LOWER triangle of M (n x n, ld ldm).
+// U (n x n, ld n) receives eigenvectors sorted by descending eigenvalue, D (n) the eigenvalues;
+// d_r (device int) receives the length of the prefix with D >= eps.  `psd_hint` selects a small
+// spectral shift (inputs known to be positive semi-definite up to rounding).
+// Returns the number of Jacobi sweeps used.
+int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
+            int* d_r, EigWorkspace& ws, cudaStream_t s);
+
+}  // namespace nle

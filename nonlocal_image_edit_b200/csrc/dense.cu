@@ -1,0 +1,193 @@
+// Column-major FP64 building blocks for the small (p x p, r x r, r x k) algebra of the filter.
+// These replace the Eigen dense products of the reference (filter.cpp:239-250, 275, 292-296, 327).
+// They are deliberately plain CUDA-core kernels: the matrices are at most p x p (p <= a few
+// thousand) and FP64; B200 has no FP64 tcgen05 path, and the N-scaled work lives elsewhere.
+#include "common.cuh"
+
+namespace nle {
+
+thread_local long long g_launches = 0;
+
+int sm_count() {
+    static int n = 0;
+    if (!n) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------
+constexpr int GBM = 64, GBN = 64, GBK = 16;
+
+template <bool TA, bool TB>
+__global__ void __launch_bounds__(256)
+dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
+             const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc) {
+    __shared__ double As[GBK][GBM + 1];
+    __shared__ double Bs[GBK][GBN + 1];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int i0 = blockIdx.x * GBM, j0 = blockIdx.y * GBN;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
+
+    for (int k0 = 0; k0 < K; k0 += GBK) {
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            int idx = tid + l * 256;
+            int i, kk;
+            if (TA) { kk = idx & 15; i = idx >> 4; } else { i = idx & 63; kk = idx >> 6; }
+            int gi = i0 + i, gk = k0 + kk;
+            double v = 0.0;
+            if (gi < M && gk < K) v = TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda];
+            As[kk][i] = v;
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            int idx = tid + l * 256;
+            int j, kk;
+            if (TB) { j = idx & 63; kk = idx >> 6; } else { kk = idx & 15; j = idx >> 4; }
+            int gj = j0 + j, gk = k0 + kk;
+            double v = 0.0;
+            if (gj < N && gk < K) v = TB ? B[gj + (size_t)gk * ldb] : B[gk + (size_t)gj * ldb];
+            Bs[kk][j] = v;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GBK; ++kk) {
+            double a[4], b[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = As[kk][tx + 16 * u];
+#pragma unroll
+            for (int v = 0; v < 4; ++v) b[v] = Bs[kk][ty + 16 * v];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int v = 0; v < 4; ++v) {
+        int gj = j0 + ty + 16 * v;
+        if (gj >= N) continue;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            int gi = i0 + tx + 16 * u;
+            if (gi >= M) continue;
+            double* c = C + gi + (size_t)gj * ldc;
+            double r = alpha * acc[u][v];
+            if (beta != 0.0) r = fma(beta, *c, r);
+            *c = r;
+        }
+    }
+}
+
+void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const double* A, int lda,
+           const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    dim3 grid(cdiv(m, GBM), cdiv(n, GBN));
+    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else dgemm_kernel<true, true><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    NLE_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+// y = A x : one thread per row, rows coalesced; columns split over blockIdx.y would need atomics,
+// so each thread walks all n columns (m,n <= a few thousand).  Fixed summation order.
+__global__ void dgemv_n_kernel(int m, int n, const double* __restrict__ A, int lda,
+                               const double* __restrict__ x, double* __restrict__ y) {
+    extern __shared__ double xs[];
+    for (int j = threadIdx.x; j < n; j += blockDim.x) xs[j] = x[j];
+    __syncthreads();
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) acc = fma(A[i + (size_t)j * lda], xs[j], acc);
+    y[i] = acc;
+}
+
+// y = A^T x : one warp per column (coalesced along the column), fixed shuffle-tree order.
+__global__ void dgemv_t_kernel(int m, int n, const double* __restrict__ A, int lda,
+                               const double* __restrict__ x, double* __restrict__ y) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    int lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const double* col = A + (size_t)warp * lda;
+    double acc = 0.0;
+    for (int i = lane; i < m; i += 32) acc = fma(col[i], x[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) y[warp] = acc;
+}
+
+void dgemv_n(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s) {
+    if (m <= 0) return;
+    dgemv_n_kernel<<<cdiv(m, 64), 64, (size_t)n * sizeof(double), s>>>(m, n, A, lda, x, y);
+    NLE_LAUNCH_CHECK();
+}
+
+void dgemv_t(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s) {
+    if (n <= 0) return;
+    dgemv_t_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(m, n, A, lda, x, y);
+    NLE_LAUNCH_CHECK();
+}
+
+// ------------------------------------------------------------------------------------------
+__global__ void scale_rows_cols_kernel(int m, int n, const double* __restrict__ A, int lda,
+                                       const double* __restrict__ rs, const double* __restrict__ cs,
+                                       double* __restrict__ out, int ldo) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= m || j >= n) return;
+    double v = A[i + (size_t)j * lda];
+    if (rs) v *= rs[i];
+    if (cs) v *= cs[j];
+    out[i + (size_t)j * ldo] = v;
+}
+
+void scale_rows_cols(int m, int n, const double* A, int lda, const double* rowscale,
+                     const double* colscale, double* out, int ldo, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    dim3 grid(cdiv(m, 128), n);
+    scale_rows_cols_kernel<<<grid, 128, 0, s>>>(m, n, A, lda, rowscale, colscale, out, ldo);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void guarded_reciprocal_kernel(double* v, int n, double eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double x = v[i];
+        v[i] = (fabs(x) >= eps) ? 1.0 / x : 0.0;
+    }
+}
+
+__global__ void guarded_inv_sqrt_kernel(const double* v, double* out, int n, double eps) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) {
+        double x = v[i];
+        out[i] = (fabs(x) >= eps) ? sqrt(1.0 / x) : 0.0;   // reciprocal then cwiseSqrt, as the reference
+    }
+}
+
+void guarded_reciprocal(double* v, int n, double eps, cudaStream_t s) {
+    if (n <= 0) return;
+    guarded_reciprocal_kernel<<<cdiv(n, 256), 256, 0, s>>>(v, n, eps);
+    NLE_LAUNCH_CHECK();
+}
+
+void guarded_inv_sqrt(const double* v, double* out, int n, double eps, cudaStream_t s) {
+    if (n <= 0) return;
+    guarded_inv_sqrt_kernel<<<cdiv(n, 256), 256, 0, s>>>(v, out, n, eps);
+    NLE_LAUNCH_CHECK();
+}
+
+}  // namespace nle

@@ -1,0 +1,390 @@
+// Symmetric FP64 eigensolver for the three p x p / r x r eigen-decompositions of the filter
+// (reference: nle::eigenDecomposition, filter.cpp:204-228, which calls Eigen's
+// SelfAdjointEigenSolver; call sites filter.cpp:262, 287, 313).  No LAPACK / cuSOLVER.
+//
+// Method: block one-sided (Hestenes) Jacobi on the shifted matrix X = sym(M) + shift*I.
+//   * sym(M) mirrors the LOWER triangle (Eigen reads only the lower triangle).
+//   * shift makes X positive definite and well conditioned (Gershgorin bound), so that after
+//     convergence  X V = W  has orthogonal columns  w_i = (lambda_i + shift) v_i : the normalised
+//     columns of W ARE the eigenvectors and no separate V has to be accumulated.
+//   * eigenvalues are then taken as Rayleigh quotients v_i^T sym(M) v_i on the UNSHIFTED matrix
+//     (one DGEMM), which restores LAPACK-grade absolute accuracy (~eps*||M||) for the tiny
+//     eigenvalues that decide the 1e-10 rank cut.
+//   * one persistent cooperative kernel runs all sweeps: a round-robin tournament over column
+//     blocks, one CTA per block pair, panel (n x 2b) resident in shared memory, Gram matrix and
+//     panel update on the FP64 tensor pipe (mma.sync m8n8k4 DMMA), inner 2b x 2b problem by a
+//     parallel-order two-sided Jacobi in shared memory, one grid.sync per tournament step.
+#include <cooperative_groups.h>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nle {
+
+__device__ __forceinline__ void dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void eig_symmetrize_kernel(const double* __restrict__ M, int ldm, int n,
+                                      double* __restrict__ As, double* __restrict__ rowsum) {
+    // As(i,j) = M(max(i,j), min(i,j));  rowsum[i] = sum_j |As(i,j)|  (thread per row)
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) {
+        int hi = i > j ? i : j, lo = i > j ? j : i;
+        double v = M[hi + (size_t)lo * ldm];
+        As[i + (size_t)j * n] = v;
+        acc += fabs(v);
+    }
+    rowsum[i] = acc;
+}
+
+__global__ void eig_sigma_kernel(const double* __restrict__ rowsum, int n, double* __restrict__ sigma) {
+    __shared__ double red[256];
+    double m = 0.0;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmax(m, rowsum[i]);
+    red[threadIdx.x] = m;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] = fmax(red[threadIdx.x], red[threadIdx.x + o]);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) sigma[0] = (red[0] > 0.0 && isfinite(red[0])) ? red[0] : 1.0;
+}
+
+__global__ void eig_build_x_kernel(const double* __restrict__ As, int n, double* __restrict__ W,
+                                   int npad, const double* __restrict__ sigma, double shift_frac) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y;
+    if (i >= npad) return;
+    double sg = sigma[0];
+    double v = 0.0;
+    if (i < n && j < n) v = As[i + (size_t)j * n];
+    if (i == j) v = (i < n) ? v + shift_frac * sg : (shift_frac + 2.0) * sg;  // pad: isolated eigenvalue
+    W[i + (size_t)j * npad] = v;
+}
+
+// ---------------------------------------------------------------------------------------------
+template <int B2>
+__global__ void __launch_bounds__(256, 1)
+jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int max_sweeps,
+              int max_inner, int* __restrict__ ctrl) {
+    cg::grid_group grid = cg::this_grid();
+    constexpr int b = B2 / 2;
+    constexpr int NT = B2 / 8;   // 8-wide tiles per side
+    constexpr int KC = B2 / 4;   // k4 chunks across the panel columns
+    extern __shared__ double sm[];
+    double* P = sm;                     // [B2][ldp]   panel, column c at P + c*ldp
+    double* S0 = P + (size_t)B2 * ldp;  // [B2][B2]
+    double* S1 = S0 + B2 * B2;
+    double* R0 = S1 + B2 * B2;
+    double* R1 = R0 + B2 * B2;
+    double* cc = R1 + B2 * B2;          // [B2]  cos for index
+    double* ss = cc + B2;               // [B2]  signed sin for index
+    int* part = reinterpret_cast<int*>(ss + B2);  // [B2] partner index
+    __shared__ int s_rot;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, t = lane & 3;
+    const int half = npad >> 1;
+
+    int sweep = 0;
+    for (; sweep < max_sweeps; ++sweep) {
+        for (int step = 0; step < nb - 1; ++step) {
+            for (int pair = blockIdx.x; pair < nb / 2; pair += gridDim.x) {
+                int I, J;
+                if (pair == 0) { I = nb - 1; J = step % (nb - 1); }
+                else { I = (step + pair) % (nb - 1); J = (step - pair + (nb - 1)) % (nb - 1); }
+                // ---- load panel [W_I, W_J] -> shared
+                for (int idx = tid; idx < B2 * half; idx += 256) {
+                    int c = idx / half, k2 = idx - c * half;
+                    int col = (c < b) ? (I * b + c) : (J * b + (c - b));
+                    double2 v = *reinterpret_cast<const double2*>(W + (size_t)col * npad + 2 * k2);
+                    *reinterpret_cast<double2*>(P + (size_t)c * ldp + 2 * k2) = v;
+                }
+                for (int idx = tid; idx < B2 * B2; idx += 256) S0[idx] = 0.0;
+                __syncthreads();
+                // ---- Gram S = P^T P on the FP64 tensor pipe; warp w takes k4-steps w, w+8, ...
+                double d[NT][NT][2];
+#pragma unroll
+                for (int a = 0; a < NT; ++a)
+#pragma unroll
+                    for (int c2 = 0; c2 < NT; ++c2) d[a][c2][0] = d[a][c2][1] = 0.0;
+                for (int k0 = 4 * warp; k0 < npad; k0 += 32) {
+                    double f[NT];
+#pragma unroll
+                    for (int a = 0; a < NT; ++a) f[a] = P[(size_t)(a * 8 + g) * ldp + k0 + t];
+#pragma unroll
+                    for (int a = 0; a < NT; ++a)
+#pragma unroll
+                        for (int c2 = a; c2 < NT; ++c2) dmma(d[a][c2][0], d[a][c2][1], f[a], f[c2]);
+                }
+                // deterministic cross-warp sum (fixed warp order)
+                for (int w = 0; w < 8; ++w) {
+                    if (warp == w) {
+#pragma unroll
+                        for (int a = 0; a < NT; ++a)
+#pragma unroll
+                            for (int c2 = a; c2 < NT; ++c2) {
+                                S0[(a * 8 + g) * B2 + c2 * 8 + 2 * t + 0] += d[a][c2][0];
+                                S0[(a * 8 + g) * B2 + c2 * 8 + 2 * t + 1] += d[a][c2][1];
+                            }
+                    }
+                    __syncthreads();
+                }
+                // mirror to the lower triangle (tile (1,0) <- (0,1)^T, and inside diagonal tiles)
+                for (int idx = tid; idx < B2 * B2; idx += 256) {
+                    int i = idx / B2, j = idx - i * B2;
+                    if (i > j) S0[i * B2 + j] = S0[j * B2 + i];
+                }
+                __syncthreads();
+                // ---- does any pair exceed the threshold?
+                int need = 0;
+                for (int idx = tid; idx < B2 * B2; idx += 256) {
+                    int i = idx / B2, j = idx - i * B2;
+                    if (i < j) {
+                        double sij = S0[i * B2 + j];
+                        if (fabs(sij) > tol * sqrt(S0[i * B2 + i] * S0[j * B2 + j])) need = 1;
+                    }
+                }
+                need = __syncthreads_or(need);
+                if (!need) continue;   // uniform per CTA; panel untouched, nothing to store
+                if (tid == 0) atomicAdd(&ctrl[sweep], 1);
+                // ---- inner parallel-order two-sided Jacobi on S (B2 x B2), R accumulates rotations
+                for (int idx = tid; idx < B2 * B2; idx += 256) {
+                    int i = idx / B2, j = idx - i * B2;
+                    R0[idx] = (i == j) ? 1.0 : 0.0;
+                }
+                double* Sc = S0; double* Sn = S1; double* Rc = R0; double* Rn = R1;
+                __syncthreads();
+                for (int isw = 0; isw < max_inner; ++isw) {
+                    if (tid == 0) s_rot = 0;
+                    __syncthreads();
+                    for (int st = 0; st < B2 - 1; ++st) {
+                        if (tid < B2 / 2) {
+                            int p, q;
+                            if (tid == 0) { p = B2 - 1; q = st % (B2 - 1); }
+                            else { p = (st + tid) % (B2 - 1); q = (st - tid + (B2 - 1)) % (B2 - 1); }
+                            if (p > q) { int tmp = p; p = q; q = tmp; }
+                            double app = Sc[p * B2 + p], aqq = Sc[q * B2 + q], apq = Sc[p * B2 + q];
+                            double c = 1.0, s = 0.0;
+                            if (fabs(apq) > tol * sqrt(app * aqq)) {
+                                double theta = (aqq - app) / (2.0 * apq);
+                                double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                                c = 1.0 / sqrt(tt * tt + 1.0);
+                                s = tt * c;
+                                s_rot = 1;
+                            }
+                            cc[p] = c; ss[p] = -s; part[p] = q;
+                            cc[q] = c; ss[q] = s;  part[q] = p;
+                        }
+                        __syncthreads();
+                        for (int idx = tid; idx < B2 * B2; idx += 256) {
+                            int i = idx / B2, j = idx - i * B2;
+                            int pi = part[i], pj = part[j];
+                            double ci = cc[i], si = ss[i], cj = cc[j], sj = ss[j];
+                            double a = fma(sj, Sc[i * B2 + pj], cj * Sc[i * B2 + j]);
+                            double bb = fma(sj, Sc[pi * B2 + pj], cj * Sc[pi * B2 + j]);
+                            Sn[idx] = fma(si, bb, ci * a);
+                            Rn[idx] = fma(sj, Rc[i * B2 + pj], cj * Rc[idx]);
+                        }
+                        __syncthreads();
+                        double* tp = Sc; Sc = Sn; Sn = tp;
+                        tp = Rc; Rc = Rn; Rn = tp;
+                    }
+                    if (s_rot == 0) break;   // uniform: written before the last barrier of the sweep
+                    __syncthreads();
+                }
+                // ---- panel update P <- P * R  (DMMA); warp w takes 8-row tiles w, w+8, ...
+                {
+                    double bf[KC][NT];
+#pragma unroll
+                    for (int kc = 0; kc < KC; ++kc)
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) bf[kc][nt] = Rc[(4 * kc + t) * B2 + nt * 8 + g];
+                    for (int k0 = 8 * warp; k0 < npad; k0 += 64) {
+                        double af[KC];
+#pragma unroll
+                        for (int kc = 0; kc < KC; ++kc) af[kc] = P[(size_t)(4 * kc + t) * ldp + k0 + g];
+                        double o[NT][2];
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            o[nt][0] = o[nt][1] = 0.0;
+#pragma unroll
+                            for (int kc = 0; kc < KC; ++kc) dmma(o[nt][0], o[nt][1], af[kc], bf[kc][nt]);
+                        }
+                        __syncwarp();
+#pragma unroll
+                        for (int nt = 0; nt < NT; ++nt) {
+                            P[(size_t)(nt * 8 + 2 * t + 0) * ldp + k0 + g] = o[nt][0];
+                            P[(size_t)(nt * 8 + 2 * t + 1) * ldp + k0 + g] = o[nt][1];
+                        }
+                    }
+                }
+                __syncthreads();
+                // ---- store panel back
+                for (int idx = tid; idx < B2 * half; idx += 256) {
+                    int c = idx / half, k2 = idx - c * half;
+                    int col = (c < b) ? (I * b + c) : (J * b + (c - b));
+                    double2 v = *reinterpret_cast<const double2*>(P + (size_t)c * ldp + 2 * k2);
+                    *reinterpret_cast<double2*>(W + (size_t)col * npad + 2 * k2) = v;
+                }
+                __syncthreads();
+            }
+            grid.sync();
+        }
+        int rotated = *reinterpret_cast<volatile int*>(&ctrl[sweep]);
+        if (rotated == 0) { ++sweep; break; }
+    }
+    if (blockIdx.x == 0 && tid == 0) ctrl[63] = sweep;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void eig_normalize_kernel(double* __restrict__ W, int npad, int n) {
+    // one warp per column j < n : divide rows [0,n) by the full column norm
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    double* col = W + (size_t)warp * npad;
+    double acc = 0.0;
+    for (int i = lane; i < npad; i += 32) acc = fma(col[i], col[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    double inv = 1.0 / sqrt(acc);
+    for (int i = lane; i < n; i += 32) col[i] *= inv;
+}
+
+__global__ void eig_rayleigh_kernel(const double* __restrict__ V, int ldv, const double* __restrict__ T,
+                                    int ldt, int n, double* __restrict__ lam) {
+    int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const double* v = V + (size_t)warp * ldv;
+    const double* tt = T + (size_t)warp * ldt;
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) acc = fma(v[i], tt[i], acc);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) lam[warp] = acc;
+}
+
+__global__ void eig_rank_kernel(const double* __restrict__ lam, int n, int* __restrict__ order) {
+    int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    double lj = lam[j];
+    int rank = 0;
+    for (int l = 0; l < n; ++l) {
+        double ll = lam[l];
+        rank += (ll > lj) || (ll == lj && l < j);
+    }
+    order[j] = rank;
+}
+
+__global__ void eig_scatter_kernel(const double* __restrict__ V, int ldv, const double* __restrict__ lam,
+                                   const int* __restrict__ order, int n, double eps,
+                                   double* __restrict__ U, double* __restrict__ D, int* __restrict__ d_r) {
+    int j = blockIdx.y;
+    int dst = order[j];
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x)
+        U[i + (size_t)dst * n] = V[i + (size_t)j * ldv];
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        double l = lam[j];
+        D[dst] = l;
+        if (!(l >= eps)) atomicMin(d_r, dst);   // first index whose eigenvalue fails D >= eps
+    }
+}
+
+__global__ void set_int_kernel(int* p, int v) { *p = v; }
+
+void EigWorkspace::reserve(int n) {
+    if (n <= cap) return;
+    int npad = ((n + 15) / 16) * 16 + 16;
+    W.alloc((size_t)npad * npad);
+    As.alloc((size_t)n * n);
+    T.alloc((size_t)n * n);
+    lam_unsorted.alloc(n + 8);
+    ctrl.alloc(64);
+    order.alloc(n);
+    cap = n;
+}
+
+int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
+            int* d_r, EigWorkspace& ws, cudaStream_t s) {
+    if (n <= 0) {
+        set_int_kernel<<<1, 1, 0, s>>>(d_r, 0);
+        NLE_LAUNCH_CHECK();
+        return 0;
+    }
+    ws.reserve(n);
+    // block size: panel (n x 2b doubles) must fit in shared memory
+    int dev = 0, max_smem = 0;
+    NLE_CUDA(cudaGetDevice(&dev));
+    NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    auto geometry = [&](int B2, int& npad, int& nb, int& ldp, size_t& smem) {
+        int b = B2 / 2;
+        nb = (n + b - 1) / b;
+        if (nb & 1) ++nb;
+        if (nb < 2) nb = 2;
+        npad = nb * b;
+        ldp = npad + ((4 - (npad % 16)) + 16) % 16;
+        smem = (size_t)B2 * ldp * 8 + (size_t)4 * B2 * B2 * 8 + (size_t)2 * B2 * 8 + (size_t)B2 * 4 + 64;
+    };
+    int B2 = 16, npad, nb, ldp;
+    size_t smem;
+    geometry(16, npad, nb, ldp, smem);
+    if (smem > (size_t)max_smem) {
+        B2 = 8;
+        geometry(8, npad, nb, ldp, smem);
+        if (smem > (size_t)max_smem) throw Unsupported{"eigensolver: matrix too large for the shared-memory Jacobi panel (n=" + std::to_string(n) + ")"};
+    }
+    double* sigma = ws.lam_unsorted.p + n;   // scratch scalar after the n eigenvalues
+    eig_symmetrize_kernel<<<cdiv(n, 128), 128, 0, s>>>(M, ldm, n, ws.As.p, ws.lam_unsorted.p);
+    NLE_LAUNCH_CHECK();
+    eig_sigma_kernel<<<1, 256, 0, s>>>(ws.lam_unsorted.p, n, sigma);
+    NLE_LAUNCH_CHECK();
+    double shift_frac = psd_hint ? 0.125 : 1.25;
+    eig_build_x_kernel<<<dim3(cdiv(npad, 128), npad), 128, 0, s>>>(ws.As.p, n, ws.W.p, npad, sigma, shift_frac);
+    NLE_LAUNCH_CHECK();
+    NLE_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64 * sizeof(int), s));
+
+    double tol = (double)(npad < 16 ? 16 : npad) * 1.1102230246251565e-16;
+    int max_sweeps = 60, max_inner = 24;
+    void* kfn = (B2 == 16) ? (void*)jacobi_kernel<16> : (void*)jacobi_kernel<8>;
+    NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0;
+    NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 256, smem));
+    if (per_sm < 1) throw Unsupported{"eigensolver: Jacobi kernel does not fit on an SM"};
+    int grid = nb / 2;
+    int max_grid = per_sm * sm_count();
+    if (grid > max_grid) grid = max_grid;
+    double* Wp = ws.W.p;
+    int* ctrl = ws.ctrl.p;
+    void* args[] = {&Wp, &npad, &nb, &ldp, &tol, &max_sweeps, &max_inner, &ctrl};
+    NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, smem, s));
+    ++g_launches;
+
+    // eigenvectors = normalised columns; eigenvalues = Rayleigh quotients on sym(M)
+    eig_normalize_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(ws.W.p, npad, n);
+    NLE_LAUNCH_CHECK();
+    dgemm(false, false, n, n, n, 1.0, ws.As.p, n, ws.W.p, npad, 0.0, ws.T.p, n, s);
+    eig_rayleigh_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(ws.W.p, npad, ws.T.p, n, n, ws.lam_unsorted.p);
+    NLE_LAUNCH_CHECK();
+    eig_rank_kernel<<<cdiv(n, 128), 128, 0, s>>>(ws.lam_unsorted.p, n, ws.order.p);
+    NLE_LAUNCH_CHECK();
+    set_int_kernel<<<1, 1, 0, s>>>(d_r, n);
+    NLE_LAUNCH_CHECK();
+    eig_scatter_kernel<<<dim3(cdiv(n, 256) > 8 ? 8 : cdiv(n, 256), n), 256, 0, s>>>(
+        ws.W.p, npad, ws.lam_unsorted.p, ws.order.p, n, eps, U, D, d_r);
+    NLE_LAUNCH_CHECK();
+    int sweeps = 0;
+    NLE_CUDA(cudaMemcpyAsync(&sweeps, ws.ctrl.p + 63, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NLE_CUDA(cudaStreamSynchronize(s));
+    if (sweeps >= max_sweeps) throw NoConvergence{"eigensolver: Jacobi did not converge in " + std::to_string(max_sweeps) + " sweeps (n=" + std::to_string(n) + ")"};
+    return sweeps;
+}
+
+}  // namespace nle

@@ -1,0 +1,741 @@
+// N-scaled kernels of the Nystrom spectral filter (sm_100a).
+//
+// The reference materialises Kab (p x (N-p) doubles, filter.cpp:126,139-145), phi (N x r, :274-275)
+// and Wab (r x (N-r), :250).  Nothing of size O(p*N) exists here.  Every kernel below re-evaluates
+// the affinity on the fly from three small FP64 tables, using two structural facts of the
+// reference's own pipeline:
+//   (a) the Nystrom samples form a product grid rows_sel x cols_sel (filter.cpp:68-70 is separable),
+//   (b) the luminance is an 8-bit value (filter.cpp:463-466: 8-bit BGR2Lab, then convertTo CV_64F),
+// so that for sample i=(a,b) and pixel j=(row,col,l)
+//       K(i,j) = exp(-((row-Ra)^2+(col-Cb)^2)/hx^2 - (l-Yi)^2/hy^2) = Er[row][a]*Ec[col][b]*Gt[|l-Yi|].
+// The Sinkhorn half-passes use this to contract over the photometric axis through a per-image-row
+// table of 256 x nC entries (a "bilateral grid" in luminance), which removes the p*N exponentials
+// AND most of the p*N multiply-adds; the Gram and extension kernels use it to generate FP64 operand
+// tiles in shared memory with three table look-ups per element.
+#include "kernels.cuh"
+
+namespace nle {
+
+// =============================================================================================
+// (1) sample selection  -- filter.cpp:56-80, 156-164
+__global__ void sample_indices_kernel(int rows, int cols, const int* __restrict__ rowa,
+                                      const int* __restrict__ colb, const int* __restrict__ rowrank,
+                                      const int* __restrict__ colrank, int nC,
+                                      int32_t* __restrict__ selected, int32_t* __restrict__ rest) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= (long long)rows * cols) return;
+    int row = (int)(idx / cols), col = (int)(idx - (long long)row * cols);
+    int a = rowa[row], b = colb[col];
+    // number of selected pixels strictly before (row,col) in raster order
+    long long before = (long long)rowrank[row] * nC + (a >= 0 ? colrank[col] : 0);
+    if (a >= 0 && b >= 0) selected[a * nC + b] = (int32_t)idx;       // to1DIndex, utils.hpp:11-14
+    else if (rest) rest[idx - before] = (int32_t)idx;
+}
+
+void launch_sample_indices(int rows, int cols, const int* rowa, const int* colb,
+                           const int* rowrank, const int* colrank, int nC,
+                           int32_t* selected, int32_t* rest, cudaStream_t s) {
+    long long n = (long long)rows * cols;
+    sample_indices_kernel<<<cdiv(n, 256), 256, 0, s>>>(rows, cols, rowa, colb, rowrank, colrank, nC, selected, rest);
+    NLE_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// tables
+__global__ void tables_kernel(int rows, int cols, int nR, int nC, const int* __restrict__ sel_rows,
+                              const int* __restrict__ sel_cols, double sw, double pw,
+                              double* __restrict__ Er, double* __restrict__ Ec,
+                              double* __restrict__ EcT, double* __restrict__ Gt) {
+    long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    long long nEr = (long long)rows * nR, nEc = (long long)cols * nC;
+    if (idx < nEr) {
+        int row = (int)(idx / nR), a = (int)(idx - (long long)row * nR);
+        int d = row - sel_rows[a];
+        Er[idx] = exp(-sw * (double)(d * d));
+    } else if (idx < nEr + nEc) {
+        long long e = idx - nEr;
+        int col = (int)(e / nC), b = (int)(e - (long long)col * nC);
+        int d = col - sel_cols[b];
+        double v = exp(-sw * (double)(d * d));
+        Ec[e] = v;
+        EcT[(size_t)b * cols + col] = v;
+    } else if (idx < nEr + nEc + 256) {
+        int d = (int)(idx - nEr - nEc);
+        Gt[d] = exp(-pw * (double)(d * d));
+    }
+}
+
+void launch_tables(int rows, int cols, int nR, int nC, const int* sel_rows, const int* sel_cols,
+                   double hx, double hy, double* Er, double* Ec, double* EcT, double* Gt,
+                   cudaStream_t s) {
+    double pw = 1.0 / (hy * hy), sw = 1.0 / (hx * hx);   // filter.cpp:128-129
+    long long n = (long long)rows * nR + (long long)cols * nC + 256;
+    tables_kernel<<<cdiv(n, 256), 256, 0, s>>>(rows, cols, nR, nC, sel_rows, sel_cols, sw, pw, Er, Ec, EcT, Gt);
+    NLE_LAUNCH_CHECK();
+}
+
+// Ka with the reference's single exponential of the summed argument (filter.cpp:109-111,134-136,144)
+__global__ void ka_kernel(int p, int nC, const int* __restrict__ sel_rows, const int* __restrict__ sel_cols,
+                          const uint8_t* __restrict__ Ysel, double sw, double pw, double* __restrict__ Ka) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= p) return;
+    int ai = i / nC, bi = i - ai * nC, aj = j / nC, bj = j - aj * nC;
+    int dr = sel_rows[ai] - sel_rows[aj], dc = sel_cols[bi] - sel_cols[bj];
+    double d2 = (double)(dr * dr + dc * dc);
+    double dy = (double)Ysel[i] - (double)Ysel[j];
+    Ka[i + (size_t)j * p] = exp(-sw * d2 - pw * (dy * dy));
+}
+
+void launch_ka(int p, int nC, const int* sel_rows, const int* sel_cols, const uint8_t* Ysel,
+               double hx, double hy, double* Ka, cudaStream_t s) {
+    double pw = 1.0 / (hy * hy), sw = 1.0 / (hx * hx);
+    ka_kernel<<<dim3(cdiv(p, 128), p), 128, 0, s>>>(p, nC, sel_rows, sel_cols, Ysel, sw, pw, Ka);
+    NLE_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// Per-row level list: which of the 256 luminance levels occur in this image row.
+// Requires blockDim.x == 256.  levidx[l] = compact index or -1; lev[li] = level; returns nlev.
+__device__ __forceinline__ int build_levels(const uint8_t* __restrict__ Lrow, int W, int* flags,
+                                            int* levidx, int* lev, int* wcount) {
+    const int tid = threadIdx.x;
+    flags[tid] = 0;
+    __syncthreads();
+    for (int c = tid; c < W; c += 256) flags[Lrow[c]] = 1;
+    __syncthreads();
+    unsigned m = __ballot_sync(0xffffffffu, flags[tid] != 0);
+    if ((tid & 31) == 0) wcount[tid >> 5] = __popc(m);
+    __syncthreads();
+    int base = 0;
+    for (int w = 0; w < (tid >> 5); ++w) base += wcount[w];
+    int my = base + __popc(m & ((1u << (tid & 31)) - 1u));
+    if (flags[tid]) { levidx[tid] = my; lev[my] = tid; } else levidx[tid] = -1;
+    int total = 0;
+    for (int w = 0; w < 8; ++w) total += wcount[w];
+    __syncthreads();
+    return total;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sinkhorn "dot" half-pass, one CTA per image row (SURVEY App. A.4:  (K~x)_j = k_j^T w).
+//   wp[a][b]   = Er[row][a] * w[a][b]
+//   F[li][b]   = sum_a wp[a][b] * Gt[|lev[li] - Y[a][b]|]          (nlev*p multiply-adds per row)
+//   y_col      = sum_b Ec[col][b] * F[li(col)][b]                   (W*nC per row)
+//   x_col      = |y| >= eps ? 1/y : 0   (inplaceReciprocal, filter.cpp:42-54); 0 at sample pixels
+__global__ void __launch_bounds__(256)
+pass_dot_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ x, int lev_cap) {
+    extern __shared__ double smd[];
+    const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
+    double* wp = smd;                       // p
+    double* Gs = wp + p;                    // 256
+    double* F = Gs + 256;                   // lev_cap * nC
+    int* flags = reinterpret_cast<int*>(F + (size_t)lev_cap * nC);  // 256
+    int* levidx = flags + 256;              // 256
+    int* lev = levidx + 256;                // 256
+    int* wcount = lev + 256;                // 8
+    uint8_t* Ys = reinterpret_cast<uint8_t*>(wcount + 8);  // p
+    uint8_t* Lrow = Ys + ((p + 15) / 16) * 16;             // W
+    const int tid = threadIdx.x;
+    for (int i = tid; i < p; i += 256) Ys[i] = t.Ysel[i];
+    Gs[tid] = t.Gt[tid];
+    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
+        const int row = t.row0 + rl;
+        const uint8_t* Lg = t.lum + (size_t)rl * W;
+        __syncthreads();
+        for (int c = tid; c < W; c += 256) Lrow[c] = Lg[c];
+        const double* er = t.Er + (size_t)row * nR;
+        for (int i = tid; i < p; i += 256) wp[i] = er[i / nC] * w[i];
+        __syncthreads();
+        int nlev = build_levels(Lrow, W, flags, levidx, lev, wcount);
+        for (int e = tid; e < nlev * nC; e += 256) {
+            int li = e / nC, b = e - li * nC;
+            int lvl = lev[li];
+            double acc = 0.0;
+            for (int a = 0; a < nR; ++a) {
+                int i = a * nC + b;
+                int d = lvl - (int)Ys[i];
+                acc = fma(wp[i], Gs[d < 0 ? -d : d], acc);
+            }
+            F[e] = acc;
+        }
+        __syncthreads();
+        const int a_row = t.rowa[row];
+        double* xo = x + (size_t)rl * W;
+        for (int c = tid; c < W; c += 256) {
+            double r = 0.0;
+            if (!(a_row >= 0 && t.colb[c] >= 0)) {
+                const double* f = F + (size_t)levidx[Lrow[c]] * nC;
+                double acc = 0.0;
+                for (int b = 0; b < nC; ++b) acc = fma(t.EcT[(size_t)b * W + c], f[b], acc);
+                r = (fabs(acc) >= kEps) ? 1.0 / acc : 0.0;
+            }
+            xo[c] = r;
+        }
+    }
+}
+
+static size_t pass_smem_bytes(const AffinityTables& t, bool reduce) {
+    size_t b = 0;
+    if (!reduce) b += (size_t)t.p * 8;                 // wp
+    b += 256 * 8;                                      // Gs
+    b += (size_t)256 * t.nC * 8;                       // F / Hh
+    b += (256 * 3 + 8) * 4;                            // flags, levidx, lev, wcount
+    b += ((t.p + 15) / 16) * 16;                       // Ys
+    b += ((t.cols + 15) / 16) * 16;                    // Lrow
+    if (reduce) b += (size_t)t.cols * 8 + ((t.cols + 15) / 16) * 16;   // xrow, lirow
+    return b + 64;
+}
+
+void launch_pass_dot(const AffinityTables& t, const double* w, double* x, cudaStream_t s) {
+    size_t smem = pass_smem_bytes(t, false);
+    if (smem > 227 * 1024) throw Unsupported{"pass_dot: sample grid too wide for the per-row table (nC=" + std::to_string(t.nC) + ", p=" + std::to_string(t.p) + ")"};
+    static size_t configured = 0;
+    if (smem > configured) {
+        NLE_CUDA(cudaFuncSetAttribute(pass_dot_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    int grid = t.nrows;
+    pass_dot_kernel<<<grid, 256, smem, s>>>(t, w, x, 256);
+    NLE_LAUNCH_CHECK();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Sinkhorn "reduce" half-pass, one CTA per image row (s = Kab x_rest).
+//   Hh[li][b]  = sum_{col : level(col)=lev[li]} Ec[col][b] * x_col     (W*nC multiply-adds per row)
+//   s_row[a,b] = Er[row][a] * sum_li Gt[|lev[li]-Y[a][b]|] * Hh[li][b] (nlev*p per row)
+// Deterministic: each (li,b) bin is owned by one lane and filled in ascending column order.
+__global__ void __launch_bounds__(256)
+pass_reduce_kernel(AffinityTables t, const double* __restrict__ x, double* __restrict__ spart) {
+    extern __shared__ double smd[];
+    const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
+    double* Gs = smd;                        // 256
+    double* Hh = Gs + 256;                   // 256 * nC
+    double* xrow = Hh + (size_t)256 * nC;    // W
+    int* flags = reinterpret_cast<int*>(xrow + W);
+    int* levidx = flags + 256;
+    int* lev = levidx + 256;
+    int* wcount = lev + 256;
+    uint8_t* Ys = reinterpret_cast<uint8_t*>(wcount + 8);
+    uint8_t* Lrow = Ys + ((p + 15) / 16) * 16;
+    uint8_t* lirow = Lrow + ((W + 15) / 16) * 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < p; i += 256) Ys[i] = t.Ysel[i];
+    Gs[tid] = t.Gt[tid];
+    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
+        const int row = t.row0 + rl;
+        const uint8_t* Lg = t.lum + (size_t)rl * W;
+        const double* xg = x + (size_t)rl * W;
+        __syncthreads();
+        for (int c = tid; c < W; c += 256) { Lrow[c] = Lg[c]; xrow[c] = xg[c]; }
+        __syncthreads();
+        int nlev = build_levels(Lrow, W, flags, levidx, lev, wcount);
+        for (int c = tid; c < W; c += 256) lirow[c] = (uint8_t)levidx[Lrow[c]];
+        for (int e = tid; e < nlev * nC; e += 256) Hh[e] = 0.0;
+        __syncthreads();
+        // warp `warp` owns the levels with (li & 7) == warp; lanes own b
+        for (int c0 = 0; c0 < W; c0 += 32) {
+            int c = c0 + lane;
+            int li_l = (c < W) ? (int)lirow[c] : 0;
+            bool mine = (c < W) && ((li_l & 7) == warp) && (xrow[c] != 0.0);
+            unsigned m = __ballot_sync(0xffffffffu, mine);
+            while (m) {
+                int j = __ffs(m) - 1;
+                m &= m - 1;
+                int col = c0 + j;
+                int li = __shfl_sync(0xffffffffu, li_l, j);
+                double xv = xrow[col];
+                const double* ec = t.Ec + (size_t)col * nC;
+                double* h = Hh + (size_t)li * nC;
+                for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+            }
+        }
+        __syncthreads();
+        const double* er = t.Er + (size_t)row * nR;
+        double* so = spart + (size_t)rl * p;
+        for (int i = tid; i < p; i += 256) {
+            int a = i / nC, b = i - a * nC;
+            int yi = (int)Ys[i];
+            double acc = 0.0;
+            for (int li = 0; li < nlev; ++li) {
+                int d = lev[li] - yi;
+                acc = fma(Gs[d < 0 ? -d : d], Hh[(size_t)li * nC + b], acc);
+            }
+            so[i] = er[a] * acc;
+        }
+    }
+}
+
+// s[i] = sum over rows of spart[row][i]; two deterministic stages (row chunks, then chunks).
+__global__ void colsum_stage_kernel(const double* __restrict__ in, int nrows, int p, int rows_per,
+                                    double* __restrict__ out) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int chunk = blockIdx.y;
+    if (i >= p) return;
+    int r0 = chunk * rows_per, r1 = min(nrows, r0 + rows_per);
+    double acc = 0.0;
+    for (int r = r0; r < r1; ++r) acc += in[(size_t)r * p + i];
+    out[(size_t)chunk * p + i] = acc;
+}
+
+void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart, double* s_out,
+                        cudaStream_t s) {
+    size_t smem = pass_smem_bytes(t, true);
+    if (smem > 227 * 1024) throw Unsupported{"pass_reduce: sample grid / image too wide for the per-row table (nC=" + std::to_string(t.nC) + ", cols=" + std::to_string(t.cols) + ")"};
+    static size_t configured = 0;
+    if (smem > configured) {
+        NLE_CUDA(cudaFuncSetAttribute(pass_reduce_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    pass_reduce_kernel<<<t.nrows, 256, smem, s>>>(t, x, spart);
+    NLE_LAUNCH_CHECK();
+    // stage 1: chunks of 32 rows written back into the head of spart's own rows is unsafe; use the
+    // tail-free trick: chunk c's result goes to row c (c <= first row of the chunk, already consumed
+    // by this same thread order) -- done in two separate launches to stay race-free.
+    int rows_per = 32;
+    int nchunks = cdiv(t.nrows, rows_per);
+    double* stage = spart + (size_t)t.nrows * t.p;   // scratch tail: nchunks * p doubles
+    colsum_stage_kernel<<<dim3(cdiv(t.p, 128), nchunks), 128, 0, s>>>(spart, t.nrows, t.p, rows_per, stage);
+    NLE_LAUNCH_CHECK();
+    colsum_stage_kernel<<<dim3(cdiv(t.p, 128), 1), 128, 0, s>>>(stage, nchunks, t.p, nchunks, s_out);
+    NLE_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// Weighted Gram  G = sum_j c_j^2 k_j k_j^T   (the "Wab Wab^T" of filter.cpp:296 in factor form,
+// SURVEY App. A.5).  FP64 SYRK whose K dimension is the pixel axis; the operand tiles
+// a_ij = c_j K(i,j) are generated in shared memory and never touch HBM.
+// CTA = 128x128 output tile (upper-triangular tile pairs only) x one contiguous range of image rows.
+constexpr int GT = 128;   // tile edge (samples)
+constexpr int GKC = 16;   // pixels per chunk
+
+__global__ void __launch_bounds__(256, 1)
+gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int nsplit,
+            double* __restrict__ part) {
+    extern __shared__ double gsm[];
+    double (*As)[GKC][GT] = reinterpret_cast<double (*)[GKC][GT]>(gsm);                      // [2][GKC][GT]
+    double (*Bs)[GKC][GT] = reinterpret_cast<double (*)[GKC][GT]>(gsm + 2 * GKC * GT);       // [2][GKC][GT]
+    double* Gs = gsm + 4 * GKC * GT;                                                         // [256]
+    double (*pc)[GKC] = reinterpret_cast<double (*)[GKC]>(Gs + 256);                         // [2][GKC]
+    int (*pcol)[GKC] = reinterpret_cast<int (*)[GKC]>(Gs + 256 + 2 * GKC);                   // [2][GKC]
+    int (*plev)[GKC] = pcol + 2;                                                             // [2][GKC]
+
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
+    // tile pair from linear upper-triangular index
+    int tp = blockIdx.x, ti = 0;
+    {
+        int rem = tp;
+        while (rem >= ntile - ti) { rem -= ntile - ti; ++ti; }
+        tp = rem;
+    }
+    const int tj = ti + tp;
+    const bool diag = (ti == tj);
+    const int split = blockIdx.y;
+    const int rb = (int)(((long long)t.nrows * split) / nsplit);
+    const int re = (int)(((long long)t.nrows * (split + 1)) / nsplit);
+
+    Gs[tid] = t.Gt[tid];
+    // generation role: sample sIdx of each tile, pixel half gh (8 pixels of the 16-pixel chunk)
+    const int sIdx = tid & 127, gh = tid >> 7;
+    const int iA = ti * GT + sIdx, iB = tj * GT + sIdx;
+    const bool vA = iA < p, vB = iB < p;
+    const int aA = vA ? iA / nC : 0, bA = vA ? iA - aA * nC : 0;
+    const int aB = vB ? iB / nC : 0, bB = vB ? iB - aB * nC : 0;
+    const int yA = vA ? (int)t.Ysel[iA] : 0, yB = vB ? (int)t.Ysel[iB] : 0;
+
+    double acc[8][8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) acc[u][v] = 0.0;
+
+    const int chunks_per_row = (W + GKC - 1) / GKC;
+    const long long nchunks = (long long)(re - rb) * chunks_per_row;
+    double regA[8], regB[8];
+    double erA = 0.0, erB = 0.0;
+    int cur_row = -1;
+
+    auto load_meta = [&](long long ch, int buf) {
+        if (tid < GKC) {
+            int rl = rb + (int)(ch / chunks_per_row);
+            int c = (int)(ch % chunks_per_row) * GKC + tid;
+            bool ok = c < W;
+            int cc = ok ? c : W - 1;
+            pcol[buf][tid] = cc;
+            plev[buf][tid] = (int)t.lum[(size_t)rl * W + cc];
+            pc[buf][tid] = ok ? cvec[(size_t)rl * W + cc] : 0.0;
+        }
+    };
+    auto generate = [&](long long ch, int buf) {
+        int rl = rb + (int)(ch / chunks_per_row);
+        if (rl != cur_row) {
+            cur_row = rl;
+            const double* er = t.Er + (size_t)(t.row0 + rl) * nR;
+            erA = vA ? er[aA] : 0.0;
+            erB = vB ? er[aB] : 0.0;
+        }
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            int kk = gh * 8 + q;
+            int col = pcol[buf][kk], lv = plev[buf][kk];
+            double cj = pc[buf][kk];
+            int dA = lv - yA, dB = lv - yB;
+            regA[q] = erA * cj * t.Ec[(size_t)col * nC + bA] * Gs[dA < 0 ? -dA : dA];
+            if (!diag) regB[q] = erB * cj * t.Ec[(size_t)col * nC + bB] * Gs[dB < 0 ? -dB : dB];
+        }
+    };
+    auto stash = [&](int buf) {
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+            As[buf][gh * 8 + q][sIdx] = regA[q];
+            if (!diag) Bs[buf][gh * 8 + q][sIdx] = regB[q];
+        }
+    };
+
+    if (nchunks > 0) {
+        load_meta(0, 0);
+        __syncthreads();
+        generate(0, 0);
+        stash(0);
+        if (nchunks > 1) load_meta(1, 1);
+        __syncthreads();
+        for (long long ch = 0; ch < nchunks; ++ch) {
+            const int buf = (int)(ch & 1);
+            const bool more = ch + 1 < nchunks;
+            if (more) generate(ch + 1, buf ^ 1);          // table loads in flight during the FMA block
+            // meta slot `buf` (chunk ch) was last read before the previous barrier -> refill for ch+2
+            if (ch + 2 < nchunks) load_meta(ch + 2, buf);
+            const double (*Ap)[GT] = As[buf];
+            const double (*Bp)[GT] = diag ? As[buf] : Bs[buf];
+#pragma unroll 4
+            for (int kk = 0; kk < GKC; ++kk) {
+                double a[8], b[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = Ap[kk][ty + 16 * u];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) b[v] = Bp[kk][tx + 16 * v];
+#pragma unroll
+                for (int u = 0; u < 8; ++u)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+            }
+            if (more) stash(buf ^ 1);                      // tiles of buf^1 were consumed at ch-1
+            __syncthreads();
+        }
+    }
+    double* out = part + ((size_t)split * gridDim.x + blockIdx.x) * (GT * GT);
+#pragma unroll
+    for (int u = 0; u < 8; ++u)
+#pragma unroll
+        for (int v = 0; v < 8; ++v) out[(ty + 16 * u) * GT + tx + 16 * v] = acc[u][v];
+}
+
+__global__ void gram_reduce_kernel(const double* __restrict__ part, int p, int ntile, int ntp,
+                                   int nsplit, double* __restrict__ G) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= p) return;
+    int ti = i / GT, tj = j / GT;
+    int r = i % GT, c = j % GT;
+    if (ti > tj) { int tmp = ti; ti = tj; tj = tmp; tmp = r; r = c; c = tmp; }
+    // linear index of (ti,tj), ti<=tj : sum_{q<ti} (ntile-q) + (tj-ti)
+    int tp = ti * ntile - (ti * (ti - 1)) / 2 + (tj - ti);
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) acc += part[((size_t)s * ntp + tp) * (GT * GT) + r * GT + c];
+    G[i + (size_t)j * p] = acc;
+}
+
+static void gram_geometry(const AffinityTables& t, int& ntile, int& ntp, int& nsplit) {
+    ntile = cdiv(t.p, GT);
+    ntp = ntile * (ntile + 1) / 2;
+    nsplit = (8 * sm_count()) / ntp;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > t.nrows) nsplit = t.nrows;
+    if (nsplit < 1) nsplit = 1;
+}
+
+size_t gram_scratch_doubles(const AffinityTables& t) {
+    int ntile, ntp, nsplit;
+    gram_geometry(t, ntile, ntp, nsplit);
+    return (size_t)ntp * nsplit * GT * GT;
+}
+
+void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
+    int ntile, ntp, nsplit;
+    gram_geometry(t, ntile, ntp, nsplit);
+    const size_t smem = (size_t)(4 * GKC * GT + 256 + 2 * GKC) * sizeof(double) + 4 * GKC * sizeof(int);
+    static bool configured = false;
+    if (!configured) {
+        NLE_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = true;
+    }
+    gram_kernel<<<dim3(ntp, nsplit), 256, smem, s>>>(t, c, ntile, nsplit, scratch);
+    NLE_LAUNCH_CHECK();
+    gram_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(scratch, t.p, ntile, ntp, nsplit, G);
+    NLE_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// Eigenvector extension for the non-sample pixels (filter.cpp:324-327 in factor form, App. A.6):
+//   V_j = c_j * sum_i K(i,j) Y[i][:]
+constexpr int EV = 32;    // eigenvector columns per CTA
+constexpr int EI = 128;   // samples per shared-memory chunk
+constexpr int EPX = 2;    // pixels per thread (register blocking over the broadcast Y loads)
+
+__global__ void __launch_bounds__(256)
+extension_kernel(AffinityTables t, const double* __restrict__ cvec, const double* __restrict__ Y,
+                 int k, double* __restrict__ V) {
+    __shared__ double2 Ys[EI][EV / 2 + 1];
+    __shared__ double Gs[256];
+    __shared__ int sa[EI], sb[EI], sy[EI];
+    const int tid = threadIdx.x;
+    const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
+    const long long nloc = (long long)t.nrows * W;
+    const int v0 = blockIdx.y * EV;
+    const int nv = min(EV, k - v0);
+    long long jj[EPX];
+    bool live[EPX];
+    int lv[EPX];
+    double cj[EPX];
+    const double* er[EPX];
+    const double* ec[EPX];
+    bool any = false;
+#pragma unroll
+    for (int q = 0; q < EPX; ++q) {
+        jj[q] = ((long long)blockIdx.x * EPX + q) * 256 + tid;
+        live[q] = jj[q] < nloc;
+        int rl = 0, col = 0;
+        lv[q] = 0; cj[q] = 0.0;
+        if (live[q]) {
+            rl = (int)(jj[q] / W); col = (int)(jj[q] - (long long)rl * W);
+            lv[q] = (int)t.lum[jj[q]];
+            cj[q] = cvec[jj[q]];
+            if (t.rowa[t.row0 + rl] >= 0 && t.colb[col] >= 0) live[q] = false;   // sample pixel: scattered separately
+        }
+        er[q] = t.Er + (size_t)(t.row0 + rl) * nR;
+        ec[q] = t.Ec + (size_t)col * nC;
+        any = any || (live[q] && cj[q] != 0.0);
+    }
+    Gs[tid] = t.Gt[tid];
+    double acc[EPX][EV];
+#pragma unroll
+    for (int q = 0; q < EPX; ++q)
+#pragma unroll
+        for (int v = 0; v < EV; ++v) acc[q][v] = 0.0;
+    double* Ysd = reinterpret_cast<double*>(&Ys[0][0]);
+    constexpr int YLD = 2 * (EV / 2 + 1);
+    for (int i0 = 0; i0 < p; i0 += EI) {
+        __syncthreads();
+        for (int e = tid; e < EI * EV; e += 256) {
+            int sI = e & (EI - 1), v = e >> 7;          // EI == 128
+            int i = i0 + sI;
+            Ysd[sI * YLD + v] = (i < p && v < nv) ? Y[i + (size_t)(v0 + v) * p] : 0.0;
+        }
+        if (tid < EI) {
+            int i = i0 + tid;
+            if (i < p) { sa[tid] = i / nC; sb[tid] = i % nC; sy[tid] = (int)t.Ysel[i]; }
+            else { sa[tid] = 0; sb[tid] = 0; sy[tid] = 0; }
+        }
+        __syncthreads();
+        const int ni = min(EI, p - i0);
+        if (any) {
+            for (int sI = 0; sI < ni; ++sI) {
+                double kv[EPX];
+#pragma unroll
+                for (int q = 0; q < EPX; ++q) {
+                    int d = lv[q] - sy[sI];
+                    kv[q] = er[q][sa[sI]] * ec[q][sb[sI]] * Gs[d < 0 ? -d : d];
+                }
+#pragma unroll
+                for (int v2 = 0; v2 < EV / 2; ++v2) {
+                    double2 y2 = Ys[sI][v2];
+#pragma unroll
+                    for (int q = 0; q < EPX; ++q) {
+                        acc[q][2 * v2] = fma(kv[q], y2.x, acc[q][2 * v2]);
+                        acc[q][2 * v2 + 1] = fma(kv[q], y2.y, acc[q][2 * v2 + 1]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < EPX; ++q) {
+        if (!live[q]) continue;
+        double* vo = V + (size_t)jj[q] * k + v0;
+#pragma unroll
+        for (int v = 0; v < EV; ++v)
+            if (v < nv) vo[v] = cj[q] * acc[q][v];
+    }
+}
+
+void launch_extension(const AffinityTables& t, const double* c, const double* Y, int k, double* V,
+                      cudaStream_t s) {
+    long long nloc = (long long)t.nrows * t.cols;
+    if (k <= 0 || nloc <= 0) return;
+    extension_kernel<<<dim3(cdiv(nloc, 256 * EPX), cdiv(k, EV)), 256, 0, s>>>(t, c, Y, k, V);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void scatter_rows_kernel(AffinityTables t, const int32_t* __restrict__ sel, int i0, int n,
+                                    const double* __restrict__ src, int ld, int k, double* __restrict__ V) {
+    int i = blockIdx.x;          // sample within [0,n)
+    long long pix = sel[i0 + i];
+    int row = (int)(pix / t.cols);
+    if (row < t.row0 || row >= t.row0 + t.nrows) return;
+    long long loc = pix - (long long)t.row0 * t.cols;
+    for (int v = threadIdx.x; v < k; v += blockDim.x) V[(size_t)loc * k + v] = src[i + (size_t)v * ld];
+}
+
+void launch_scatter_rows(const AffinityTables& t, const int32_t* sel, int i0, int n, const double* src,
+                         int ld, int k, double* V, cudaStream_t s) {
+    if (n <= 0 || k <= 0) return;
+    scatter_rows_kernel<<<n, 64, 0, s>>>(t, sel, i0, n, src, ld, k, V);
+    NLE_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+// apply (filter.cpp:445-458):  out = V (g o (V^T z)),  V row-major (N x k).
+constexpr int AP_PIX = 1024;   // pixels per CTA in the V^T z pass
+
+int apply_blocks(long long nloc) { return cdiv(nloc, AP_PIX); }
+
+__global__ void __launch_bounds__(256)
+vtz_kernel(long long nloc, int k, const double* __restrict__ V, const uint8_t* __restrict__ z8,
+           const double* __restrict__ z64, double* __restrict__ partial) {
+    // thread v-lane layout: 256 threads = 8 pixel-lanes x 32 v-lanes; each reads V rows coalesced.
+    extern __shared__ double red[];   // 8 * kpad
+    const int vl = threadIdx.x & 31, pl = threadIdx.x >> 5;
+    const long long base = (long long)blockIdx.x * AP_PIX;
+    const int kpad = ((k + 31) / 32) * 32;
+    for (int vb = 0; vb < k; vb += 32) {
+        int v = vb + vl;
+        double acc = 0.0;
+        if (v < k) {
+            for (int q = pl; q < AP_PIX; q += 8) {
+                long long j = base + q;
+                if (j >= nloc) break;
+                double z = z8 ? (double)z8[j] : z64[j];
+                acc = fma(V[(size_t)j * k + v], z, acc);
+            }
+        }
+        red[pl * kpad + vb + vl] = acc;
+    }
+    __syncthreads();
+    for (int v = threadIdx.x; v < k; v += 256) {
+        double s = 0.0;
+        for (int q = 0; q < 8; ++q) s += red[q * kpad + v];
+        partial[(size_t)blockIdx.x * k + v] = s;
+    }
+}
+
+__global__ void vtz_final_kernel(const double* __restrict__ partial, int nblocks, int k,
+                                 double* __restrict__ tout) {
+    int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= k) return;
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * k + v];
+    tout[v] = s;
+}
+
+void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, const double* z_f64,
+                double* scratch, double* t_out, cudaStream_t s) {
+    int nb = apply_blocks(nloc);
+    int kpad = ((k + 31) / 32) * 32;
+    vtz_kernel<<<nb, 256, (size_t)8 * kpad * sizeof(double), s>>>(nloc, k, V, z_u8, z_f64, scratch);
+    NLE_LAUNCH_CHECK();
+    vtz_final_kernel<<<cdiv(k, 64), 64, 0, s>>>(scratch, nb, k, t_out);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256)
+recompose_kernel(long long nloc, int k, const double* __restrict__ V, const double* __restrict__ g,
+                 double* __restrict__ out64, uint8_t* __restrict__ out8) {
+    // one warp per group of pixels; lanes stride over k so V rows are read coalesced
+    extern __shared__ double gs[];
+    for (int v = threadIdx.x; v < k; v += 256) gs[v] = g[v];
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
+    long long nwarps = ((long long)gridDim.x * 256) >> 5;
+    for (long long j = warp; j < nloc; j += nwarps) {
+        const double* vr = V + (size_t)j * k;
+        double acc = 0.0;
+        for (int v = lane; v < k; v += 32) acc = fma(vr[v], gs[v], acc);
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) {
+            if (out64) out64[j] = acc;
+            if (out8) {
+                // cv::max(.,0), cv::min(.,255), convertTo(CV_8U) = cvRound = round half to even
+                double c = fmin(fmax(acc, 0.0), 255.0);
+                out8[j] = (uint8_t)__double2int_rn(c);
+            }
+        }
+    }
+}
+
+void launch_recompose(long long nloc, int k, const double* V, const double* g, double* out_f64,
+                      uint8_t* out_u8, cudaStream_t s) {
+    if (nloc <= 0) return;
+    long long warps_needed = nloc;
+    int grid = (int)std::min<long long>((warps_needed + 7) / 8, (long long)sm_count() * 16);
+    if (grid < 1) grid = 1;
+    recompose_kernel<<<grid, 256, (size_t)(k > 0 ? k : 1) * sizeof(double), s>>>(nloc, k, V, g, out_f64, out_u8);
+    NLE_LAUNCH_CHECK();
+}
+
+// =============================================================================================
+__global__ void fill_kernel(double* p, long long n, double v) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] = v;
+}
+void launch_fill(double* p, long long n, double v, cudaStream_t s) {
+    if (n <= 0) return;
+    fill_kernel<<<cdiv(n, 256), 256, 0, s>>>(p, n, v);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void mask_samples_kernel(AffinityTables t, double* x) {
+    long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= (long long)t.nrows * t.cols) return;
+    int rl = (int)(j / t.cols), col = (int)(j - (long long)rl * t.cols);
+    if (t.rowa[t.row0 + rl] >= 0 && t.colb[col] >= 0) x[j] = 0.0;
+}
+void launch_mask_samples(const AffinityTables& t, double* x, cudaStream_t s) {
+    long long n = (long long)t.nrows * t.cols;
+    if (n <= 0) return;
+    mask_samples_kernel<<<cdiv(n, 256), 256, 0, s>>>(t, x);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void u8_from_f64_kernel(const double* __restrict__ in, long long n, uint8_t* __restrict__ out,
+                                   int* __restrict__ bad) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    double v = in[i];
+    double r = rint(v);
+    if (!(v >= 0.0 && v <= 255.0) || r != v) atomicExch(bad, 1);
+    out[i] = (uint8_t)(int)fmin(fmax(r, 0.0), 255.0);
+}
+void launch_u8_from_f64(const double* in, long long n, uint8_t* out, int* bad_flag, cudaStream_t s) {
+    if (n <= 0) return;
+    u8_from_f64_kernel<<<cdiv(n, 256), 256, 0, s>>>(in, n, out, bad_flag);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void gather_c_sel_kernel(AffinityTables t, const int32_t* __restrict__ sel,
+                                    const double* __restrict__ c_sel, double* __restrict__ c_full) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= t.p) return;
+    long long pix = sel[i];
+    int row = (int)(pix / t.cols);
+    if (row < t.row0 || row >= t.row0 + t.nrows) return;
+    c_full[pix - (long long)t.row0 * t.cols] = c_sel[i];
+}
+void launch_gather_c_sel(const AffinityTables& t, const int32_t* sel, const double* c_sel, double* c_full,
+                         cudaStream_t s) {
+    gather_c_sel_kernel<<<cdiv(t.p, 128), 128, 0, s>>>(t, sel, c_sel, c_full);
+    NLE_LAUNCH_CHECK();
+}
+
+}  // namespace nle

@@ -1,0 +1,68 @@
+// Launchers of the N-scaled kernels (filter_kernels.cu).  All device pointers.
+#pragma once
+#include "common.cuh"
+
+namespace nle {
+
+// Everything the N-scaled kernels need to evaluate K(i,j) for sample i=(a,b) and pixel j=(row,col,l):
+//   K = Er[row][a] * Ec[col][b] * Gt[|l - Ysel[i]|]      (filter.cpp:104-112,128-129,144-145)
+// exact because samples form a product grid (filter.cpp:68-70) and L is 8-bit (filter.cpp:463-466).
+struct AffinityTables {
+    int rows, cols;          // full image
+    int row0, nrows;         // slab owned by this rank: image rows [row0, row0+nrows)
+    int nR, nC, p;           // sample grid and p = nR*nC
+    const uint8_t* lum;      // slab luminance, nrows x cols
+    const double* Er;        // rows x nR   (row-major)
+    const double* Ec;        // cols x nC   (row-major)
+    const double* EcT;       // nC x cols
+    const double* Gt;        // 256
+    const uint8_t* Ysel;     // p   luminance of sample i (raster order: i = a*nC + b)
+    const int* rowa;         // rows : a if the image row is a sample row else -1
+    const int* colb;         // cols : b or -1
+};
+
+void launch_sample_indices(int rows, int cols, const int* rowa, const int* colb,
+                           const int* rowrank, const int* colrank, int nC,
+                           int32_t* selected, int32_t* rest, cudaStream_t s);
+void launch_tables(int rows, int cols, int nR, int nC, const int* sel_rows, const int* sel_cols,
+                   double hx, double hy, double* Er, double* Ec, double* EcT, double* Gt,
+                   cudaStream_t s);
+void launch_ka(int p, int nC, const int* sel_rows, const int* sel_cols, const uint8_t* Ysel,
+               double hx, double hy, double* Ka, cudaStream_t s);
+
+// Sinkhorn pass, "dot" half:   x_j = recip( k_j^T w )  for every slab pixel (0 at sample pixels).
+void launch_pass_dot(const AffinityTables& t, const double* w, double* x, cudaStream_t s);
+// Sinkhorn pass, "reduce" half: s_i = sum_j K(i,j) x_j  over the slab (x is 0 at sample pixels).
+// spart: nrows x p scratch.  s_out: p.
+void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart, double* s_out,
+                        cudaStream_t s);
+
+// Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab.
+size_t gram_scratch_doubles(const AffinityTables& t);
+void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G,
+                 cudaStream_t s);
+
+// Extension  V_j = c_j * k_j^T Y   for non-sample slab pixels.  Y: p x k (column-major),
+// V: (nrows*cols) x k ROW-major (k fastest).
+void launch_extension(const AffinityTables& t, const double* c, const double* Y, int k, double* V,
+                      cudaStream_t s);
+// V[pixel(sel[i0+i]) - slab offset][:] = src(i, :)  for samples that fall in the slab.  src: n x k col-major (ld).
+void launch_scatter_rows(const AffinityTables& t, const int32_t* sel, int i0, int n, const double* src,
+                         int ld, int k, double* V, cudaStream_t s);
+
+// apply:  tpart/t = V^T z ; out = V (g)   with optional clamp+round to u8.
+// z_u8 or z_f64 (exactly one non-null).  t_out: k.  scratch: nblocks*k doubles.
+int apply_blocks(long long nloc);
+void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, const double* z_f64,
+                double* scratch, double* t_out, cudaStream_t s);
+void launch_recompose(long long nloc, int k, const double* V, const double* g, double* out_f64,
+                      uint8_t* out_u8, cudaStream_t s);
+
+// misc elementwise
+void launch_fill(double* p, long long n, double v, cudaStream_t s);
+void launch_mask_samples(const AffinityTables& t, double* x, cudaStream_t s);  // x=0 at sample pixels
+void launch_u8_from_f64(const double* in, long long n, uint8_t* out, int* bad_flag, cudaStream_t s);
+void launch_gather_c_sel(const AffinityTables& t, const int32_t* sel, const double* c_sel, double* c_full,
+                         cudaStream_t s);
+
+}  // namespace nle
