@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200-native Nystrom spectral filter.
+
+Metric (BASELINE.json): enhance MP/s (p=1600, k=50).  A "step" = train + enhance of ONE image
+(NLEFilter::trainFilter + enhance on the L channel, filter.cpp:480-502 and 426-436).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+N=1 workload = BASELINE.json configs[2]: synthetic 1024x1024 8-bit luminance, 40x40=1600 samples,
+hx=500 hy=30, 20 Sinkhorn iterations, k=50, weights 2 3 4 1 (SURVEY.md 8d "S-gray-1024").
+N>1 = weak scaling: the image grows to (1024*N) x 1024 and is sharded by image rows, one slab per
+rank; NCCL carries the p-vector Sinkhorn sums, one p x p Gram and the k-vector V^T z.
+
+value : MP/s with the luminance slab already resident in HBM (nle_b200_train_u8_dev +
+        nle_b200_enhance_luminance_u8_dev), timed with CUDA events, max over ranks.
+e2e   : MP/s through the host-pointer C ABI (nle_b200_train_u8_sharded + enhance_luminance_u8)
+        from pinned host memory, H2D and D2H inside the timed region.
+--impl reference : the CPU restatement of the reference (oracle/nle_oracle.py, NumPy/SciPy FP64,
+        all host threads) on a bounded crop of the same workload.  The reference binary itself
+        needs Eigen + OpenCV C++ which this image does not have.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# ---- workload -----------------------------------------------------------------------------------
+BASE_ROWS, COLS = 1024, 1024
+GRID = (40, 40)
+HX, HY = 500.0, 30.0
+T_SINK, K_EIG = 20, 50
+WEIGHTS = [2.0, 3.0, 4.0, 1.0]
+CPU_CROP = 256            # cpu_baseline / reference arm: CPU_CROP x CPU_CROP crop, same grid/k/T
+
+
+def synth_luminance(rows, cols, seed=1234):
+    """SURVEY.md 8(d) S-gray generator: smooth periodic structure + 5x5-box-smoothed noise, 8-bit."""
+    rng = np.random.default_rng(seed)
+    y, x = np.mgrid[0:rows, 0:cols].astype(np.float64)
+    noise = rng.standard_normal((rows + 4, cols + 4))
+    cs = np.cumsum(np.cumsum(np.pad(noise, ((1, 0), (1, 0))), axis=0), axis=1)
+    box = (cs[5:, 5:] - cs[:-5, 5:] - cs[5:, :-5] + cs[:-5, :-5]) / 25.0
+    img = 128.0 + 60.0 * np.sin(2 * np.pi * x / 97.0) * np.cos(2 * np.pi * y / 61.0) + 25.0 * 5.0 * box
+    return np.clip(np.rint(img), 0, 255).astype(np.uint8)
+
+
+def nproc_used():
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+# ---- clocks sampler -----------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(smax)), "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---- reference / CPU arm ------------------------------------------------------------------------
+def cpu_step(lum_crop):
+    from oracle import nle_oracle as O
+    flt = O.train_dense(lum_crop.astype(np.float64), GRID[0], GRID[1], HX, HY, T_SINK, K_EIG)
+    out = O.enhance_luminance(flt, lum_crop, WEIGHTS)
+    return out
+
+
+def cpu_sample_desc():
+    return (f"{CPU_CROP}x{CPU_CROP} top-left crop of the {BASE_ROWS}x{COLS} workload, same 40x40 grid "
+            f"(p=1600), T={T_SINK}, k={K_EIG}; dense FP64 NumPy/SciPy restatement of filter.cpp "
+            f"(oracle/nle_oracle.py), OpenBLAS threads = all host cores; full image needs ~80 GB dense")
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    lum = synth_luminance(BASE_ROWS, COLS)[:CPU_CROP, :CPU_CROP].copy()
+    for _ in range(args.warmup):
+        cpu_step(lum)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_step(lum)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    mp = CPU_CROP * CPU_CROP / 1e6
+    val = mp / dt
+    line = {
+        "impl": "reference", "metric": "enhance MP/s (p=1600,k=50)", "value": val, "unit": "MP/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args.gpus),
+        "cpu_baseline": {"value": val, "unit": "MP/s", "cores": nproc_used(), "kind": "port", "sample": cpu_sample_desc()},
+        "e2e": {"value": val, "unit": "MP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(n):
+    return {"workload": f"synthetic {BASE_ROWS * n}x{COLS} 8-bit luminance (S-gray generator, seed 1234), "
+                        f"{GRID[0]}x{GRID[1]}=1600 Nystrom samples, hx={HX:g} hy={HY:g}, T={T_SINK} Sinkhorn iters, "
+                        f"k={K_EIG}, weights {WEIGHTS}",
+            "baseline_config": "BASELINE.json configs[2]",
+            "rows": BASE_ROWS * n, "cols": COLS, "p": 1600, "k": K_EIG, "sinkhorn_iters": T_SINK,
+            "parallelism": f"row-sharded x{n}" if n > 1 else "single GPU",
+            "l2_policy": "each step streams >500 MB of scratch (Gram partial tiles, V) through the 126 MB L2; "
+                         "inputs are re-uploaded / re-read every step",
+            "lab_conversion": "L channel fed directly to the C ABI; BGR<->Lab stays in host OpenCV as in the reference"}
+
+
+# ---- B200 arm -----------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from nonlocal_image_edit_b200 import _lib
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    lib = _lib.load()
+    lib.nle_b200_set_keep_stages(0)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    rows = BASE_ROWS * world
+    lum = synth_luminance(rows, COLS)
+    row0, row1 = rank * BASE_ROWS, (rank + 1) * BASE_ROWS
+    nloc = (row1 - row0) * COLS
+    weights = (C.c_double * len(WEIGHTS))(*WEIGHTS)
+
+    # sample luminances (p bytes, host) -- needed by every rank
+    p = C.c_int(0)
+    _lib.check(lib.nle_b200_sample_count(rows, COLS, GRID[0], GRID[1], C.byref(p)))
+
+    def axis(n, k):
+        step = n // k
+        off = (step - 1 + (n - step * k)) // 2
+        r = np.arange(n)
+        return r[(r >= off) & (r <= n - off) & ((r - off) % step == 0)]
+    ys = np.ascontiguousarray(lum[np.ix_(axis(rows, GRID[0]), axis(COLS, GRID[1]))].ravel())
+    assert ys.size == p.value
+
+    class _Arr:   # zero-copy view of a raw device pointer for torch
+        def __init__(self, ptr, n):
+            self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f8", "data": (ptr, False), "version": 3}
+
+    def allreduce(buf, count, stream, user):
+        try:
+            t = torch.as_tensor(_Arr(buf, count), device=dev)
+            dist.all_reduce(t)
+            return 0
+        except Exception:
+            import traceback
+            traceback.print_exc()
+            return 1
+    cb = _lib.ALLREDUCE_FN(allreduce) if world > 1 else C.cast(None, _lib.ALLREDUCE_FN)
+
+    pinned_in = torch.from_numpy(lum).pin_memory()
+    pinned_out = torch.empty(nloc, dtype=torch.uint8).pin_memory()
+    d_slab = torch.from_numpy(lum[row0:row1].copy()).to(dev)
+    d_out = torch.empty(nloc, dtype=torch.uint8, device=dev)
+
+    def step_dev():
+        h = C.c_void_p()
+        _lib.check(lib.nle_b200_train_u8_dev(C.c_void_p(d_slab.data_ptr()), rows, COLS, row0, row1,
+                                             ys.ctypes.data_as(C.c_void_p), GRID[0], GRID[1], HX, HY, T_SINK, K_EIG,
+                                             cb, None, C.byref(h)))
+        _lib.check(lib.nle_b200_enhance_luminance_u8_dev(h, C.c_void_p(d_slab.data_ptr()), weights, len(WEIGHTS),
+                                                         C.c_void_p(d_out.data_ptr())))
+        return h
+
+    def step_host():
+        h = C.c_void_p()
+        _lib.check(lib.nle_b200_train_u8_sharded(C.c_void_p(pinned_in.data_ptr()), rows, COLS, row0, row1, GRID[0], GRID[1],
+                                                 HX, HY, T_SINK, K_EIG, cb, None, C.byref(h)))
+        _lib.check(lib.nle_b200_enhance_luminance_u8(h, C.c_void_p(pinned_in.data_ptr() + row0 * COLS), weights,
+                                                     len(WEIGHTS), C.c_void_p(pinned_out.data_ptr())))
+        return h
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, collect=None):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            h = fn()
+            if collect is not None:
+                collect(h)
+            lib.nle_b200_free(h)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    for _ in range(max(3, args.warmup)):
+        lib.nle_b200_free(step_dev())
+    for _ in range(2):
+        lib.nle_b200_free(step_host())
+
+    stage_ms = []
+    infos = []
+
+    def collect(h):
+        out = (C.c_double * 8)()
+        size = C.c_size_t(0)
+        lib.nle_b200_get_stage(h, 8, out, 8, C.byref(size))
+        stage_ms.append(list(out))
+        inf = _lib.Info()
+        lib.nle_b200_filter_info(h, C.byref(inf))
+        infos.append(inf)
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    lib.nle_b200_launch_count(1)
+    ms_dev = timed(step_dev, args.steps, collect)
+    launches = int(lib.nle_b200_launch_count(0))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_host = timed(step_host, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    total_mp = rows * COLS / 1e6
+    ms_step = ms_dev / args.steps
+    value = total_mp / (ms_step * 1e-3)
+    e2e_val = total_mp / (ms_host / args.steps * 1e-3)
+    st = np.median(np.array(stage_ms), axis=0)
+    inf = infos[-1]
+
+    # roofline of the dominant kernel: the fused affinity+Gram kernel (FP64 FMA bound).
+    # algorithmic work per launch = one fused multiply-add per (pixel, sample pair i<=j): N*p*(p+1)/2 FMAs
+    # = N*p*(p+1) flops on this rank's slab (symmetric form).
+    pp = inf.p
+    gram_flops = float(nloc) * pp * (pp + 1)
+    peak = lib.nle_b200_fp64_fma_peak_tflops()
+    achieved = gram_flops / (st[7] * 1e-3) * 1e-12 if st[7] > 0 else None
+    roofline = {"kernel": "gram_kernel (fused affinity tile generation + FP64 SYRK over pixels)",
+                "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                "launch_ms": float(st[7]),
+                "peak_source": "measured in this run by nle_b200_fp64_fma_peak_tflops (register-resident DFMA "
+                               "microbenchmark); MEASURED_PEAKS.json has no FP64 figure",
+                "algorithmic_flops_per_launch": gram_flops}
+
+    # CPU baseline on a bounded crop (rank 0, N=1 only)
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        crop = lum[:CPU_CROP, :CPU_CROP].copy()
+        t0 = time.perf_counter()
+        cpu_step(crop)
+        dt = time.perf_counter() - t0
+        cpu = {"value": CPU_CROP * CPU_CROP / 1e6 / dt, "unit": "MP/s", "cores": nproc_used(), "kind": "port",
+               "sample": cpu_sample_desc(), "seconds": dt}
+
+    line = {
+        "metric": "enhance MP/s (p=1600,k=50)", "value": value, "unit": "MP/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(world),
+        "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(nloc + ys.size) * world,
+                "d2h_bytes_per_step": int(nloc) * world, "ms_per_step": ms_host / args.steps},
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "stage_ms": {"setup_tables_Ka": float(st[0]), "eig_Ka": float(st[1]), "sinkhorn_passes": float(st[2]),
+                     "gram": float(st[3]), "small_algebra_2eigs": float(st[4]), "extension": float(st[5]),
+                     "train_total": float(st[6]), "gram_kernel_only": float(st[7])},
+        "filter": {"p": inf.p, "r": inf.r, "r2": inf.r2, "k": inf.k, "eig_sweeps": list(inf.eig_sweeps)},
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

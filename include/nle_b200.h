@@ -163,6 +163,10 @@ void nle_b200_set_keep_stages(int keep);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 long long nle_b200_launch_count(int reset);
 
+/* FP64 FMA throughput of this GPU measured by a register-resident microbenchmark (TFLOP/s); the
+ * roofline denominator bench.py uses for the DFMA-bound Gram kernel. */
+double nle_b200_fp64_fma_peak_tflops(void);
+
 void nle_b200_free(nle_b200_filter* f);
 
 #ifdef __cplusplus

@@ -52,6 +52,7 @@ SYMBOLS = {
     "nle_b200_set_keep_stages": (None, [C.c_int]),
     "nle_b200_launch_count": (C.c_longlong, [C.c_int]),
     "nle_b200_free": (None, [_P]),
+    "nle_b200_fp64_fma_peak_tflops": (C.c_double, []),
 }
 
 _lib = None

@@ -5,6 +5,7 @@
 // arithmetic that reaches the output is FP64, as in the reference (filter.hpp:10-14).
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 
@@ -106,6 +107,36 @@ static int read_int(const int* d, cudaStream_t s) {
 
 static void copy_dd(double* dst, const double* src, size_t n, cudaStream_t s) {
     if (n) NLE_CUDA(cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToDevice, s));
+}
+
+// FP64 FMA microbenchmark: the roofline denominator of the DFMA-bound kernels (MEASURED_PEAKS.json
+// only carries HBM and bf16-tensor peaks).  8 independent FMA chains per thread, 1024 threads/SM.
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+            x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+            x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+        }
+    }
+    double r = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (r == 123.456) out[0] = r;
+}
+double measure_fp64_peak_tflops() {
+    cudaStream_t s = nullptr;
+    DevBuf<double> d(1);
+    const int iters = 4096, blocks = sm_count() * 4;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        Timer t(s);
+        fp64_peak_kernel<<<blocks, 256, 0, s>>>(d.p, iters, 0.999999, 1e-9);
+        NLE_LAUNCH_CHECK();
+        double ms = t.stop();
+        double flops = 2.0 * 64.0 * iters * 256.0 * blocks;
+        best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    return best;
 }
 
 // small vector helpers used by the Sinkhorn loop
@@ -250,7 +281,9 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     DevBuf<double> Gp((size_t)p * p);
     {
         DevBuf<double> gscratch(gram_scratch_doubles(tb));
+        Timer t_gk(s);
         launch_gram(tb, cfull.p, gscratch.p, Gp.p, s);
+        f->times_ms[7] = t_gk.stop();                       // gram_kernel + its partial-tile reduce only
         do_allreduce(f.get(), Gp.p, (size_t)p * p);
         NLE_CUDA(cudaStreamSynchronize(s));
     }
@@ -407,7 +440,13 @@ static int eig_host(const double* M, int n, double eps, bool psd, double* U, dou
     DevBuf<int> dr(1);
     dM.upload(M, (size_t)n * n, s);
     EigWorkspace ws;
-    sym_eig(dM.p, n, n, eps, psd, dU.p, dD.p, dr.p, ws, s);
+    if (const char* e = getenv("NLE_B200_EIG_INNER")) ws.max_inner = atoi(e);
+    int sweeps = sym_eig(dM.p, n, n, eps, psd, dU.p, dD.p, dr.p, ws, s);
+    if (getenv("NLE_B200_EIG_PROF")) {
+        const long long* q = ws.prof_host;
+        fprintf(stderr, "[eig n=%d] sweeps=%d steps=%lld pairs(block0)=%lld cycles: load=%lld gram=%lld inner=%lld update=%lld store=%lld gridsync=%lld\n",
+                n, sweeps, q[6], q[7], q[0], q[1], q[2], q[3], q[4], q[5]);
+    }
     int r = read_int(dr.p, s);
     dU.download(U, (size_t)n * n, s);
     dD.download(D, n, s);
@@ -845,5 +884,14 @@ int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t 
 }
 
 void nle_b200_free(nle_b200_filter* f) { delete f; }
+
+double nle_b200_fp64_fma_peak_tflops(void) {
+    double out = 0.0;
+    guarded([&] {
+        require_device();
+        out = nle::measure_fp64_peak_tflops();
+    });
+    return out;
+}
 
 }  // extern "C"

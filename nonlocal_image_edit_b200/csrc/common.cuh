@@ -94,6 +94,9 @@ void guarded_inv_sqrt(const double* v, double* out, int n, double eps, cudaStrea
 struct EigWorkspace {
     DevBuf<double> W, As, T, lam_unsorted;
     DevBuf<int> ctrl, order;
+    DevBuf<long long> prof;
+    long long prof_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // block-0 cycle counts: load, gram, inner, update, store, gridsync, steps, pairs
+    int max_inner = 2;                                  // inner Jacobi sweeps per block-pair visit
     int cap = 0;
     void reserve(int n);
 };

@@ -58,23 +58,31 @@ __global__ void eig_sigma_kernel(const double* __restrict__ rowsum, int n, doubl
 }
 
 __global__ void eig_build_x_kernel(const double* __restrict__ As, int n, double* __restrict__ W,
-                                   int npad, const double* __restrict__ sigma, double shift_frac) {
+                                   int npad, const double* __restrict__ sigma, double shift_frac, double pad_frac) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y;
     if (i >= npad) return;
     double sg = sigma[0];
     double v = 0.0;
     if (i < n && j < n) v = As[i + (size_t)j * n];
-    if (i == j) v = (i < n) ? v + shift_frac * sg : (shift_frac + 2.0) * sg;  // pad: isolated eigenvalue
+    if (i == j) v = (i < n) ? v + shift_frac * sg : pad_frac * sg;  // pad: isolated, SMALLEST eigenvalue (stays last under sorting)
     W[i + (size_t)j * npad] = v;
 }
+
+// Columns are kept sorted by descending norm (de Rijk ordering), but only where the norms differ by
+// more than this relative slack -- equal norms (the numerically-null cluster) are left alone.
+constexpr double kSortSlack = 1.0 + 1e-9;
 
 // ---------------------------------------------------------------------------------------------
 template <int B2>
 __global__ void __launch_bounds__(256, 1)
 jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int max_sweeps,
-              int max_inner, int* __restrict__ ctrl) {
+              int max_inner, int* __restrict__ ctrl, long long* __restrict__ prof) {
     cg::grid_group grid = cg::this_grid();
+    long long pr[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const bool profiler = (blockIdx.x == 0 && threadIdx.x == 0 && prof != nullptr);
+    long long tmark = clock64();
+#define NLE_PROF(slot) do { if (profiler) { long long now_ = clock64(); pr[slot] += now_ - tmark; tmark = now_; } } while (0)
     constexpr int b = B2 / 2;
     constexpr int NT = B2 / 8;   // 8-wide tiles per side
     constexpr int KC = B2 / 4;   // k4 chunks across the panel columns
@@ -93,6 +101,7 @@ jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int
     const int warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, t = lane & 3;
     const int half = npad >> 1;
+    const double tol2 = tol * tol;
 
     int sweep = 0;
     for (; sweep < max_sweeps; ++sweep) {
@@ -101,15 +110,18 @@ jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int
                 int I, J;
                 if (pair == 0) { I = nb - 1; J = step % (nb - 1); }
                 else { I = (step + pair) % (nb - 1); J = (step - pair + (nb - 1)) % (nb - 1); }
+                if (I > J) { int tmp = I; I = J; J = tmp; }   // larger norms migrate to lower column indices
                 // ---- load panel [W_I, W_J] -> shared
-                for (int idx = tid; idx < B2 * half; idx += 256) {
-                    int c = idx / half, k2 = idx - c * half;
-                    int col = (c < b) ? (I * b + c) : (J * b + (c - b));
-                    double2 v = *reinterpret_cast<const double2*>(W + (size_t)col * npad + 2 * k2);
-                    *reinterpret_cast<double2*>(P + (size_t)c * ldp + 2 * k2) = v;
+#pragma unroll 4
+                for (int c = 0; c < B2; ++c) {
+                    const int col = (c < b) ? (I * b + c) : (J * b + (c - b));
+                    const double2* src = reinterpret_cast<const double2*>(W + (size_t)col * npad);
+                    double2* dst = reinterpret_cast<double2*>(P + (size_t)c * ldp);
+                    for (int k2 = tid; k2 < half; k2 += 256) dst[k2] = src[k2];
                 }
                 for (int idx = tid; idx < B2 * B2; idx += 256) S0[idx] = 0.0;
                 __syncthreads();
+                NLE_PROF(0);
                 // ---- Gram S = P^T P on the FP64 tensor pipe; warp w takes k4-steps w, w+8, ...
                 double d[NT][NT][2];
 #pragma unroll
@@ -149,11 +161,12 @@ jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int
                 for (int idx = tid; idx < B2 * B2; idx += 256) {
                     int i = idx / B2, j = idx - i * B2;
                     if (i < j) {
-                        double sij = S0[i * B2 + j];
-                        if (fabs(sij) > tol * sqrt(S0[i * B2 + i] * S0[j * B2 + j])) need = 1;
+                        double sij = S0[i * B2 + j], sii = S0[i * B2 + i], sjj = S0[j * B2 + j];
+                        if (sij * sij > tol2 * sii * sjj || sjj > sii * kSortSlack) need = 1;
                     }
                 }
                 need = __syncthreads_or(need);
+                NLE_PROF(1);
                 if (!need) continue;   // uniform per CTA; panel untouched, nothing to store
                 if (tid == 0) atomicAdd(&ctrl[sweep], 1);
                 // ---- inner parallel-order two-sided Jacobi on S (B2 x B2), R accumulates rotations
@@ -173,16 +186,32 @@ jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int
                             else { p = (st + tid) % (B2 - 1); q = (st - tid + (B2 - 1)) % (B2 - 1); }
                             if (p > q) { int tmp = p; p = q; q = tmp; }
                             double app = Sc[p * B2 + p], aqq = Sc[q * B2 + q], apq = Sc[p * B2 + q];
-                            double c = 1.0, s = 0.0;
-                            if (fabs(apq) > tol * sqrt(app * aqq)) {
-                                double theta = (aqq - app) / (2.0 * apq);
-                                double tt = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                                c = 1.0 / sqrt(tt * tt + 1.0);
+                            double c = 1.0, s = 0.0, napp = app, naqq = aqq;
+                            if (apq * apq > tol2 * app * aqq) {
+                                // the rotation ANGLE only needs a few digits (Jacobi is self-correcting), the
+                                // rotation itself must be orthogonal to FP64: t in FP32, c = rsqrt(1+t^2) in FP64.
+                                float th = __fdividef((float)(aqq - app), 2.0f * (float)apq);
+                                float tf = copysignf(1.0f, th) / (fabsf(th) + sqrtf(fmaf(th, th, 1.0f)));
+                                if (!isfinite(th)) tf = 0.0f;
+                                double tt = (double)tf;
+                                c = rsqrt(fma(tt, tt, 1.0));
                                 s = tt * c;
+                                // rotated diagonal for this (approximate) angle
+                                napp = c * c * app - 2.0 * c * s * apq + s * s * aqq;
+                                naqq = s * s * app + 2.0 * c * s * apq + c * c * aqq;
                                 s_rot = 1;
                             }
-                            cc[p] = c; ss[p] = -s; part[p] = q;
-                            cc[q] = c; ss[q] = s;  part[q] = p;
+                            // new column j = own[j]*col_j + oth[j]*col_partner(j).  Plain rotation:
+                            // p:(c,-s) q:(c,s).  If the rotated diagonal would be ascending, compose with
+                            // a signed swap so that norms end up sorted descending (de Rijk ordering):
+                            // p:(-s,-c) q:(-s,c).
+                            if (naqq > napp * kSortSlack) {
+                                cc[p] = -s; ss[p] = -c; cc[q] = -s; ss[q] = c;
+                                s_rot = 1;
+                            } else {
+                                cc[p] = c; ss[p] = -s; cc[q] = c; ss[q] = s;
+                            }
+                            part[p] = q; part[q] = p;
                         }
                         __syncthreads();
                         for (int idx = tid; idx < B2 * B2; idx += 256) {
@@ -201,6 +230,8 @@ jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int
                     if (s_rot == 0) break;   // uniform: written before the last barrier of the sweep
                     __syncthreads();
                 }
+                NLE_PROF(2);
+                if (profiler) pr[7] += 1;
                 // ---- panel update P <- P * R  (DMMA); warp w takes 8-row tiles w, w+8, ...
                 {
                     double bf[KC][NT];
@@ -228,21 +259,28 @@ jacobi_kernel(double* __restrict__ W, int npad, int nb, int ldp, double tol, int
                     }
                 }
                 __syncthreads();
+                NLE_PROF(3);
                 // ---- store panel back
-                for (int idx = tid; idx < B2 * half; idx += 256) {
-                    int c = idx / half, k2 = idx - c * half;
-                    int col = (c < b) ? (I * b + c) : (J * b + (c - b));
-                    double2 v = *reinterpret_cast<const double2*>(P + (size_t)c * ldp + 2 * k2);
-                    *reinterpret_cast<double2*>(W + (size_t)col * npad + 2 * k2) = v;
+#pragma unroll 4
+                for (int c = 0; c < B2; ++c) {
+                    const int col = (c < b) ? (I * b + c) : (J * b + (c - b));
+                    double2* dst = reinterpret_cast<double2*>(W + (size_t)col * npad);
+                    const double2* src = reinterpret_cast<const double2*>(P + (size_t)c * ldp);
+                    for (int k2 = tid; k2 < half; k2 += 256) dst[k2] = src[k2];
                 }
                 __syncthreads();
+                NLE_PROF(4);
             }
             grid.sync();
+            NLE_PROF(5);
+            if (profiler) pr[6] += 1;
         }
         int rotated = *reinterpret_cast<volatile int*>(&ctrl[sweep]);
         if (rotated == 0) { ++sweep; break; }
     }
     if (blockIdx.x == 0 && tid == 0) ctrl[63] = sweep;
+    if (profiler) for (int i = 0; i < 8; ++i) prof[i] = pr[i];
+#undef NLE_PROF
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -308,12 +346,14 @@ void EigWorkspace::reserve(int n) {
     T.alloc((size_t)n * n);
     lam_unsorted.alloc(n + 8);
     ctrl.alloc(64);
+    prof.alloc(8);
     order.alloc(n);
     cap = n;
 }
 
-int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
-            int* d_r, EigWorkspace& ws, cudaStream_t s) {
+static int sym_eig_once(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
+                        int* d_r, EigWorkspace& ws, cudaStream_t s, bool* shift_ok) {
+    *shift_ok = true;
     if (n <= 0) {
         set_int_kernel<<<1, 1, 0, s>>>(d_r, 0);
         NLE_LAUNCH_CHECK();
@@ -346,13 +386,15 @@ int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* 
     NLE_LAUNCH_CHECK();
     eig_sigma_kernel<<<1, 256, 0, s>>>(ws.lam_unsorted.p, n, sigma);
     NLE_LAUNCH_CHECK();
-    double shift_frac = psd_hint ? 0.125 : 1.25;
-    eig_build_x_kernel<<<dim3(cdiv(npad, 128), npad), 128, 0, s>>>(ws.As.p, n, ws.W.p, npad, sigma, shift_frac);
+    // resolution of close eigenvalues is ~tol*shift/2: keep the shift small when the input is
+    // positive semi-definite up to rounding so that the 1e-10 rank cut matches LAPACK's count.
+    double shift_frac = psd_hint ? 1.0 / 1024.0 : 1.25;
+    eig_build_x_kernel<<<dim3(cdiv(npad, 128), npad), 128, 0, s>>>(ws.As.p, n, ws.W.p, npad, sigma, shift_frac, psd_hint ? 0.5 * shift_frac : 0.1 * shift_frac);
     NLE_LAUNCH_CHECK();
     NLE_CUDA(cudaMemsetAsync(ws.ctrl.p, 0, 64 * sizeof(int), s));
 
     double tol = (double)(npad < 16 ? 16 : npad) * 1.1102230246251565e-16;
-    int max_sweeps = 60, max_inner = 24;
+    int max_sweeps = 60, max_inner = ws.max_inner;
     void* kfn = (B2 == 16) ? (void*)jacobi_kernel<16> : (void*)jacobi_kernel<8>;
     NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0;
@@ -363,7 +405,8 @@ int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* 
     if (grid > max_grid) grid = max_grid;
     double* Wp = ws.W.p;
     int* ctrl = ws.ctrl.p;
-    void* args[] = {&Wp, &npad, &nb, &ldp, &tol, &max_sweeps, &max_inner, &ctrl};
+    long long* prof = ws.prof.p;
+    void* args[] = {&Wp, &npad, &nb, &ldp, &tol, &max_sweeps, &max_inner, &ctrl, &prof};
     NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(256), args, smem, s));
     ++g_launches;
 
@@ -381,9 +424,27 @@ int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* 
         ws.W.p, npad, ws.lam_unsorted.p, ws.order.p, n, eps, U, D, d_r);
     NLE_LAUNCH_CHECK();
     int sweeps = 0;
+    double dmin = 0.0, sg = 0.0;
+    NLE_CUDA(cudaMemcpyAsync(ws.prof_host, ws.prof.p, 8 * sizeof(long long), cudaMemcpyDeviceToHost, s));
     NLE_CUDA(cudaMemcpyAsync(&sweeps, ws.ctrl.p + 63, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NLE_CUDA(cudaMemcpyAsync(&dmin, D + (n - 1), sizeof(double), cudaMemcpyDeviceToHost, s));
+    NLE_CUDA(cudaMemcpyAsync(&sg, sigma, sizeof(double), cudaMemcpyDeviceToHost, s));
     NLE_CUDA(cudaStreamSynchronize(s));
+    // the small shift is only valid if X = sym(M) + shift*I stayed positive definite with margin
+    if (psd_hint && !(dmin > -0.5 * shift_frac * sg)) *shift_ok = false;
     if (sweeps >= max_sweeps) throw NoConvergence{"eigensolver: Jacobi did not converge in " + std::to_string(max_sweeps) + " sweeps (n=" + std::to_string(n) + ")"};
+    return sweeps;
+}
+
+// Tries the small (accurate) shift first -- valid whenever sym(M) is positive semi-definite up to
+// rounding, which holds for Ka, Wa and Q of the filter -- and falls back to the Gershgorin shift for
+// genuinely indefinite input (only the reference's unit tests feed such matrices).
+int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
+            int* d_r, EigWorkspace& ws, cudaStream_t s) {
+    (void)psd_hint;
+    bool ok = true;
+    int sweeps = sym_eig_once(M, ldm, n, eps, true, U, D, d_r, ws, s, &ok);
+    if (!ok) sweeps += sym_eig_once(M, ldm, n, eps, false, U, D, d_r, ws, s, &ok);
     return sweeps;
 }
 
