@@ -1,0 +1,47 @@
+"""Row sharding of one image across ranks (one process per GPU) and the small all-reduce adapter.
+
+The N-scaled work of the filter is a map over pixels followed by small reductions, so rank g owns a
+contiguous slab of image rows and only p-vectors (Sinkhorn sums), one p x p Gram matrix and the
+k-vector V^T z ever cross NVLink.  The C ABI takes the reduction as a callback
+(nle_b200_allreduce_fn); this module builds it from torch.distributed."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+
+def row_slab(rows: int, rank: int, world: int):
+    """Contiguous, balanced row range [row0, row1) of rank `rank` out of `world`."""
+    if not (0 <= rank < world):
+        raise ValueError("rank out of range")
+    if world > rows:
+        raise ValueError("more ranks than image rows")
+    base, rem = divmod(rows, world)
+    row0 = rank * base + min(rank, rem)
+    return row0, row0 + base + (1 if rank < rem else 0)
+
+
+class _DevArray:
+    """Zero-copy view of `count` doubles at a raw CUDA device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, count):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": "<f8", "data": (int(ptr), False), "version": 3}
+
+
+def torch_allreduce(device=None, group=None):
+    """Returns f(ptr, count, stream) that sums `count` doubles in place across the process group.
+
+    device=None -> the buffer is HOST memory (gloo, used by the CPU tests of the sharding logic);
+    otherwise a torch.device for NCCL over NVLink."""
+    import torch
+    import torch.distributed as dist
+
+    def _fn(ptr, count, stream=None):
+        if device is None:
+            arr = np.ctypeslib.as_array(C.cast(C.c_void_p(int(ptr)), C.POINTER(C.c_double)), shape=(count,))
+            t = torch.from_numpy(arr)
+        else:
+            t = torch.as_tensor(_DevArray(ptr, count), device=device)
+        dist.all_reduce(t, group=group)
+    return _fn

@@ -287,13 +287,21 @@ def _tiles(n, tile):
 
 def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx: float, hy: float,
                     n_sinkhorn_iter: int = 10, n_eigen_vectors: int = 5,
-                    tile: int = 16384) -> TrainedFilter:
+                    tile: int = 16384, slab=None, allreduce=None) -> TrainedFilter:
+    """slab=(row0,row1) restricts every pixel sum to the image rows owned by one rank and
+    `allreduce(np.ndarray)` (in-place sum over ranks) completes them: the CPU model of the row-sharded
+    multi-GPU path.  The returned eigvecs then cover only the slab's pixels."""
     lum = np.asarray(lum, dtype=np.float64)
     nrows, ncols = lum.shape
     if n_row_samples > nrows or n_col_samples > ncols:
         raise RuntimeError("Number of samples per row and col must be <= that of image.")
     z = lum.ravel()
     sel, rest = sample_pixels(nrows, ncols, n_row_samples, n_col_samples)
+    if slab is not None:
+        rest = rest[(rest >= slab[0] * ncols) & (rest < slab[1] * ncols)]
+    if allreduce is None:
+        def allreduce(a):
+            return a
     perm = np.concatenate([sel, rest])
     p, nrest = sel.size, rest.size
     T = n_sinkhorn_iter
@@ -323,11 +331,13 @@ def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx:
             xr, _ = inplace_reciprocal(K.T @ w)
             x_rest[s:e] = xr
             s_vec += K @ xr
+        allreduce(s_vec)
         return x_sel, x_rest, s_vec
 
     s0 = np.zeros(p)
     for s, e in _tiles(nrest, tile):
         s0 += kb(s, e).sum(axis=1)                        # Kab * 1
+    allreduce(s0)
     t = phiT_x(np.ones(p), s0)
     c_sel = c_rest = r_sel = None
     if T < 1:
@@ -348,6 +358,7 @@ def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx:
     for s, e in _tiles(nrest, tile):
         K = kb(s, e) * c_rest[None, s:e]
         Gp += K @ K.T
+    allreduce(Gp)
     UL = U * inv_lam[None, :]                             # p x r : U Lam^-1
     G = UL.T @ Gp @ UL
     demoted = U[r:p] * c_sel[r:p, None]                   # samples r..p-1 are "rest" for Wab
@@ -366,13 +377,16 @@ def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx:
     # --- extension (A.6): V_pi = [Wa ; Wab^T] Mv
     Z_rest = L.T @ Mv                                     # r x k'
     Y = UL @ Z_rest                                       # p x k'
-    V = np.empty((nrows * ncols, k))
+    V = np.zeros((nrows * ncols, k))
     V[perm[:r]] = Wa @ Mv                                 # top block: rows of Wa
     V[perm[r:p]] = c_sel[r:p, None] * (U[r:p] @ Z_rest)   # demoted samples: c_j phi_j Z_rest
     for s, e in _tiles(nrest, tile):
         K = kb(s, e)
         V[rest[s:e]] = c_rest[s:e, None] * (K.T @ Y)
     c_full = np.concatenate([c_sel, c_rest])
+    if slab is not None:
+        lo, hi = slab[0] * ncols, slab[1] * ncols
+        V = V[lo:hi]
     stages = dict(perm=perm, p=p, r=r, r2=int(la.size), Ka=Ka, lam=lam, Wa=Wa,
                   rvec_head=r_sel[:r].copy(), c=c_full, la=la, Q=Q, Sq=Sq, G=G)
     return TrainedFilter(nrows, ncols, V, Sq, stages)

@@ -1,0 +1,142 @@
+"""CPU tests (-m "not gpu"): the FP64 oracle against the reference's own pins.
+
+G1  README rows + committed outputs data/*-filtered.png  (README.md:74-83)
+G2  3x3 known-answer eigen-decomposition                  (test/test_filter.cpp:42-68)
+G3  identity Sinkhorn                                     (test/test_filter.cpp:70-94)
+G4  balanced random matrix / orthogonalize properties     (test/test_filter.cpp:96-153), fixed seeds
+"""
+import os
+
+import numpy as np
+import pytest
+
+from nle_testlib import load_case, manifest, synth_lum, train_args
+from oracle import nle_oracle as O
+
+TOL = 1e-10  # test_filter.cpp:8
+
+
+def is_approx(a, b, tol):
+    """Eigen's isApprox: ||a-b||_F <= tol * min(||a||_F, ||b||_F)."""
+    return np.linalg.norm(a - b) <= tol * min(np.linalg.norm(a), np.linalg.norm(b))
+
+
+# ---- sampling (filter.cpp:56-80) -----------------------------------------------------------------
+@pytest.mark.parametrize("shape", [(736, 491, 20, 10), (100, 100, 40, 40), (7, 5, 7, 5), (33, 17, 4, 3),
+                                   (267, 400, 10, 20), (50, 64, 1, 1), (9, 9, 9, 1)])
+def test_sample_pixels_matches_literal_loop(shape):
+    sel, rest = O.sample_pixels(*shape)
+    sel2, rest2 = O.sample_pixels_loop(*shape)
+    assert np.array_equal(sel, sel2) and np.array_equal(rest, rest2)
+    assert sel.size + rest.size == shape[0] * shape[1]
+
+
+def test_sample_count_can_exceed_request():
+    sel, _ = O.sample_pixels(100, 100, 40, 40)       # n=100,k=40 -> 41 per axis
+    assert sel.size == 41 * 41
+
+
+def test_survey_grid_offsets():
+    # C1 rows step 36 off 25, cols step 49 off 24; C3 step 25 offset 24
+    assert O.sample_axis(736, 20)[0] == 25 and O.sample_axis(736, 20)[1] - O.sample_axis(736, 20)[0] == 36
+    assert O.sample_axis(491, 10)[0] == 24
+    ax = O.sample_axis(1024, 40)
+    assert ax[0] == 24 and ax[-1] == 999 and ax.size == 40
+
+
+# ---- G2 ------------------------------------------------------------------------------------------
+def test_eigen_decomposition_known_answer():
+    R = np.array([[2., -1, 0], [-1, 2, -1], [0, -1, 2]])
+    U, D = O.eigen_decomposition(R, TOL)
+    assert is_approx(D, np.array([3.41421356, 2., 0.58578644]), 1e-5)
+    assert is_approx((U * D) @ U.T, R, TOL)
+    assert is_approx(np.eye(3), U.T @ U, TOL)
+
+
+def test_eigen_decomposition_reads_lower_triangle_and_truncates():
+    M = np.array([[2., 99.], [1., 2.]])              # upper entry must be ignored
+    U, D = O.eigen_decomposition(M)
+    assert np.allclose(D, [3., 1.])
+    U, D = O.eigen_decomposition(np.diag([1., 1e-11, -3.]))
+    assert D.size == 1 and U.shape == (3, 1)         # 1e-11 < EPS and negatives are dropped
+
+
+# ---- G3 / G4 ---------------------------------------------------------------------------------------
+def test_sinkhorn_identity():
+    Wa, Wab, _, _ = O.sinkhorn(np.eye(2), np.ones(2), 10)
+    assert Wab.shape == (2, 0)
+    assert is_approx(Wa, Wa.T, 1e-12)
+    assert is_approx(Wa.sum(axis=1), np.ones(2), TOL) and is_approx(Wa.sum(axis=0), np.ones(2), TOL)
+
+
+def test_sinkhorn_balanced_random():
+    rng = np.random.default_rng(3)
+    R = rng.uniform(0, 1, (5, 5))
+    U, D = O.eigen_decomposition(R, TOL)
+    Wa, Wab, _, _ = O.sinkhorn(U, D, 60)             # the reference uses 20 its with an unseeded draw
+    W = np.hstack([Wa, Wab])
+    assert is_approx(W.sum(axis=1), np.ones(Wa.shape[0]), 1e-8)
+    assert is_approx(np.vstack([Wa, Wab.T]).sum(axis=0), np.ones(Wa.shape[1]), 1e-8)
+
+
+def test_orthogonalize_properties():
+    rng = np.random.default_rng(11)
+    p, n, k = 10, 100, 5
+    Wa = rng.uniform(0, 1, (p, p)); Wa = (Wa + Wa.T) / 2
+    Wab = rng.uniform(0, 1, (p, n - p))
+    V, S, _ = O.orthogonalize(Wa, Wab, k)
+    assert S.size == V.shape[1] > 0
+    assert is_approx(V.T @ V, np.eye(V.shape[1]), 1e-8)
+
+
+def test_inplace_reciprocal_zeroes_small_entries():
+    v, nnz = O.inplace_reciprocal(np.array([2.0, 1e-11, -4.0, 0.0]))
+    assert nnz == 2 and np.array_equal(v, [0.5, 0.0, -0.25, 0.0])
+
+
+def test_transform_eigenvalues_polynomial():
+    S = np.array([1.0, 0.5, 0.1])
+    w = [2.0, 3.0, 4.0, 1.0]
+    expect = w[0] + (w[1] - w[0]) * S + (w[2] - w[1]) * S**2 + (w[3] - w[2]) * S**3
+    assert np.allclose(O.transform_eigenvalues(S, w), expect)
+    assert np.allclose(O.transform_eigenvalues(S, [1.0]), 1.0)
+
+
+def test_compute_kernel_errors_and_shapes():
+    L = synth_lum(20, 30).astype(float)
+    with pytest.raises(RuntimeError, match="Number of samples per row and col must be <= that of image."):
+        O.compute_kernel(L, 21, 3, 10.0, 10.0)
+    perm, Ka, Kab = O.compute_kernel(L, 4, 5, 10.0, 10.0)
+    assert Ka.shape == (20, 20) and Kab.shape == (20, 580) and np.array_equal(np.sort(perm), np.arange(600))
+    assert np.allclose(np.diag(Ka), 1.0) and np.allclose(Ka, Ka.T)
+
+
+# ---- streaming (factor form) == dense (literal) --------------------------------------------------
+@pytest.mark.parametrize("case", [(48, 64, 6, 8, 20.0, 25.0, 5, 6), (40, 56, 5, 7, 300.0, 12.0, 8, 40)])
+def test_streaming_equals_dense(case):
+    rows, cols, *a = case
+    L = synth_lum(rows, cols).astype(float)
+    fd = O.train_dense(L, *a)
+    fs = O.train_streaming(L, *a, tile=500)
+    assert fd.stages["r"] == fs.stages["r"] and fd.stages["r2"] == fs.stages["r2"]
+    assert fd.eigvals.size == fs.eigvals.size
+    assert np.allclose(fd.eigvals, fs.eigvals, rtol=1e-7, atol=1e-12)
+    assert np.abs(fd.stages["Wa"] - fs.stages["Wa"]).max() < 1e-12
+    z = L.ravel()
+    fS = O.transform_eigenvalues(fd.eigvals, [2, 3, 4, 1])
+    assert np.allclose(O.apply(fd, L, fS), O.apply(fs, L, O.transform_eigenvalues(fs.eigvals, [2, 3, 4, 1])), atol=1e-6)
+    assert z.size == fd.eigvecs.shape[0]
+
+
+# ---- G1: README goldens ------------------------------------------------------------------------------
+_CPU_CASES = [m["name"] for m in manifest() if m["name"] != "rock2" or os.environ.get("NLE_FULL")]
+
+
+@pytest.mark.parametrize("name", _CPU_CASES)
+def test_oracle_reproduces_readme_golden(name):
+    m, img, gold = load_case(name)
+    flt = O.train_for_enhancement(img, *train_args(m))
+    out = O.enhance(flt, img, m["weights"])
+    d = np.abs(out.astype(int) - gold.astype(int))
+    assert d.max() <= 2, d.max()
+    assert (d <= 1).mean() >= 0.999
