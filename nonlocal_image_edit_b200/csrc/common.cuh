@@ -90,9 +90,16 @@ void guarded_reciprocal(double* v, int n, double eps, cudaStream_t s);
 // v_i <- 1/sqrt(v_i) if |v_i| >= eps else 0  (filter.cpp:289-291, 319-321)
 void guarded_inv_sqrt(const double* v, double* out, int n, double eps, cudaStream_t s);
 
-// ---- eig.cu : symmetric eigensolver (block one-sided Jacobi, FP64, no LAPACK) ---------------
+// ---- eig_dc.cu / eig.cu : symmetric eigensolver (FP64, no LAPACK) ----------------------------
+// Default: Householder tridiagonalisation + divide & conquer + back-transformation (eig_dc.cu).
+// Fallback (NLE_B200_EIG=jacobi, or if the direct solver's device-side sanity check fails): block
+// one-sided Jacobi (eig.cu).
 struct EigWorkspace {
     DevBuf<double> W, As, T, lam_unsorted;
+    DevBuf<double> Qa, Qb, Sb, dcd;                     // divide & conquer buffers (eig_dc.cu)
+    DevBuf<int> dci;
+    int dc_cap = 0;
+    void reserve_dc(int n);
     DevBuf<int> ctrl, order;
     DevBuf<long long> prof;
     long long prof_host[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // block-0 cycle counts: load, gram, inner, update, store, gridsync, steps, pairs
@@ -104,7 +111,8 @@ struct EigWorkspace {
 // U (n x n, ld n) receives eigenvectors sorted by descending eigenvalue, D (n) the eigenvalues;
 // d_r (device int) receives the length of the prefix with D >= eps.  `psd_hint` selects a small
 // spectral shift (inputs known to be positive semi-definite up to rounding).
-// Returns the number of Jacobi sweeps used.
+// Returns the number of Jacobi sweeps used (0 when the direct solver was used).
+bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double** lam_out, double** vec_out);
 int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
             int* d_r, EigWorkspace& ws, cudaStream_t s);
 

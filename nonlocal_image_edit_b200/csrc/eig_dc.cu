@@ -1,0 +1,761 @@
+// Symmetric FP64 eigensolver, direct method: Householder tridiagonalisation + Cuppen divide & conquer
+// + reflector back-transformation, all on the device (no LAPACK / cuSOLVER).
+//
+// Replaces the Eigen SelfAdjointEigenSolver calls of the reference (nle::eigenDecomposition,
+// filter.cpp:204-228; call sites filter.cpp:262, 287, 313).  The block-Jacobi solver of eig.cu needs
+// 30-50 sweeps on the Gaussian kernel matrices of this filter (measured) -- ~8 n^3
+// flops per sweep -- whereas this path costs ~(4/3) n^3 for the reduction plus a D&C phase that
+// deflates almost completely on such spectra (top merge k = 362 of 1600 for the bench Ka).
+//
+//   tridiag_kernel        persistent cooperative kernel; ONE pass over the trailing matrix and ONE
+//                         grid.sync per Householder step: the rank-2 update of step j is fused with
+//                         the symmetric matrix-vector product of step j+1 (the next reflector is
+//                         derived redundantly by every CTA from the updated column j+1).
+//   dc_leaf_kernel        implicit-shift QL on leaves of <= 32 rows, one warp per leaf.
+//   dc_setup_kernel       per merge: z vector, rank sort, LAPACK dlaed2-style deflation.
+//   dc_rotate_kernel      applies the deflation Givens rotations to the eigenvector columns.
+//   dc_secular_kernel     one warp per root; bisection on the BIT PATTERN of the offset from the
+//                         nearer pole (<= 62 steps, converges to the last ulp, no safeguards needed).
+//   dc_zhat_kernel        Gu-Eisenstat recomputed z (keeps eigenvectors orthogonal to rounding).
+//   dc_smat_kernel        normalised eigenvectors of the rank-one-updated diagonal problem.
+//   dc_gemm_kernel        Q_new = Q[:, non-deflated] * S  (gathered columns), all merges of a level.
+//   backtransform_kernel  U = H_0 ... H_{n-3} Z, one warp per column (column resident in shared memory).
+//
+// scripts/proto_eig_dc.py is the NumPy prototype of exactly this structure (checked against LAPACK).
+#include <cooperative_groups.h>
+
+#include <cstdlib>
+
+#include "common.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace nle {
+
+namespace {
+
+constexpr double kUnitRoundoff = 1.1102230246251565e-16;
+constexpr int kLeaf = 32;
+constexpr int kTrdThreads = 512;
+constexpr int kTrdWarps = kTrdThreads / 32;
+
+__device__ __forceinline__ int node_start(int n, int depth, int i) { return (int)(((long long)i * n) >> depth); }
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_prod(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v *= __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+
+// deterministic block-wide sum for kTrdThreads threads; every thread returns the same value.
+__device__ __forceinline__ double block_sum(double v, double* red /*>= 2*kTrdWarps doubles*/, int& phase) {
+    v = warp_sum(v);
+    double* slot = red + (phase & 1) * kTrdWarps;
+    if ((threadIdx.x & 31) == 0) slot[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double s = 0.0;
+#pragma unroll
+    for (int w = 0; w < kTrdWarps; ++w) s += slot[w];
+    ++phase;   // alternate slots so the next reduction cannot overwrite values still being read
+    return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Householder tridiagonalisation A = Q T Q^T of a symmetric matrix held in FULL storage (both
+// triangles, column-major).  On exit: d (n), e (n-1), tau (n-1); reflector j (H_j = I - tau_j v v^T,
+// v[j+1] = 1) is stored in A(j+1:n, j) including the explicit 1.
+__global__ void __launch_bounds__(kTrdThreads, 1)
+tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
+               double* __restrict__ tau, double* __restrict__ pbuf) {
+    cg::grid_group grid = cg::this_grid();
+    extern __shared__ double sm[];
+    double* v = sm;            // current reflector, global row indexing
+    double* w = sm + n;
+    double* cn = sm + 2 * (size_t)n;   // updated next column -> next reflector
+    double* red = sm + 3 * (size_t)n;  // 2*kTrdWarps
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    int phase = 0;
+
+    if (n < 3) {
+        if (b == 0 && tid == 0) {
+            d[0] = A[0];
+            if (n == 2) { e[0] = A[1]; d[1] = A[1 + (size_t)lda]; tau[0] = 0.0; }
+        }
+        return;
+    }
+
+    // make a reflector from cn[j0+1 .. n-1] in place (x -> v, v[j0+1] = 1); returns beta, sets tau_out.
+    // cn[j0] (the diagonal) is left untouched.  All threads get the same result.
+    auto make_reflector = [&](int j0, double& tau_out) -> double {
+        const double alpha = cn[j0 + 1];
+        double part = 0.0;
+        for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
+        const double xn2 = block_sum(part, red, phase);
+        double beta;
+        if (xn2 == 0.0) {
+            tau_out = 0.0;
+            beta = alpha;
+            __syncthreads();
+            if (tid == 0) cn[j0 + 1] = 1.0;
+        } else {
+            beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+            tau_out = (beta - alpha) / beta;
+            const double scal = 1.0 / (alpha - beta);
+            __syncthreads();
+            for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) cn[i] *= scal;
+            if (tid == 0) cn[j0 + 1] = 1.0;
+        }
+        __syncthreads();
+        return beta;
+    };
+
+    // symv for owned columns c >= c0: pout[c] = sum_{i >= c0} A[i,c] * vec[i]   (no update)
+    // (used once, for the first reflector)
+    double tau_j, beta_j, diag_j;
+    {
+        for (int i = tid; i < n; i += kTrdThreads) cn[i] = A[i];
+        __syncthreads();
+        diag_j = cn[0];
+        beta_j = make_reflector(0, tau_j);
+        // v <- cn
+        double* t = v; v = cn; cn = t;
+        for (int q = warp; ; q += kTrdWarps) {
+            const int c = b + G * q;
+            if (c >= n) break;
+            if (c < 1) continue;
+            const double* col = A + (size_t)c * lda;
+            double acc = 0.0;
+            for (int i = 1 + lane; i < n; i += 32) acc = fma(col[i], v[i], acc);
+            acc = warp_sum(acc);
+            if (lane == 0) pbuf[c] = acc;
+        }
+        __threadfence();
+        grid.sync();
+    }
+
+    for (int j = 0; j <= n - 3; ++j) {
+        const double* p = pbuf + (size_t)(j & 1) * n;
+        double* pn = pbuf + (size_t)((j + 1) & 1) * n;
+        // (0) publish reflector j (column j of A is no longer read by anybody in this kernel)
+        if (b == 0) {
+            double* col = A + (size_t)j * lda;
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) col[i] = v[i];
+            if (tid == 0) { d[j] = diag_j; e[j] = beta_j; tau[j] = tau_j; }
+        }
+        // (1) w = tau*p - (tau^2/2)(p.v) v
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) {
+            const double pi = __ldcg(p + i);
+            w[i] = pi;
+            part = fma(pi, v[i], part);
+        }
+        const double dot = block_sum(part, red, phase);
+        const double kappa = 0.5 * tau_j * tau_j * dot;
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
+        __syncthreads();
+        // (2) updated column j+1 (rows j+1..n-1) -> next diagonal and next reflector
+        {
+            const double* col = A + (size_t)(j + 1) * lda;
+            const double wj1 = w[j + 1];   // v[j+1] == 1
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = __ldcg(col + i) - v[i] * wj1 - w[i];
+            __syncthreads();
+        }
+        const double diag_next = cn[j + 1];
+        double tau_next = 0.0, beta_next;
+        if (j + 1 <= n - 3) {
+            beta_next = make_reflector(j + 1, tau_next);
+        } else {
+            beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
+        }
+        // (3) rank-2 update of the owned columns c >= j+2 fused with the next symv
+        const bool has_next = (j + 1 <= n - 3);
+        for (int q = warp; ; q += kTrdWarps) {
+            const int c = b + G * q;
+            if (c >= n) break;
+            if (c < j + 2) continue;
+            double* col = A + (size_t)c * lda;
+            const double wc = w[c], vc = v[c];
+            double acc = 0.0;
+            int i = j + 2 + lane;
+            // batches of 8 independent loads to cover the L2 latency
+            for (; i + 7 * 32 < n; i += 8 * 32) {
+                double a[8];
+#pragma unroll
+                for (int u = 0; u < 8; ++u) a[u] = __ldcg(col + i + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 8; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = fma(-w[ii], vc, fma(-v[ii], wc, a[u]));
+                    acc = fma(a[u], cn[ii], acc);
+                    __stcg(col + ii, a[u]);
+                }
+            }
+            for (; i < n; i += 32) {
+                double a = __ldcg(col + i);
+                a = fma(-w[i], vc, fma(-v[i], wc, a));
+                acc = fma(a, cn[i], acc);
+                __stcg(col + i, a);
+            }
+            if (has_next) {
+                acc = warp_sum(acc);
+                if (lane == 0) pn[c] = acc;
+            }
+        }
+        // rotate state
+        diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
+        { double* t = v; v = cn; cn = t; }
+        __threadfence();
+        grid.sync();
+    }
+    // epilogue: j = n-2 entries and the last diagonal
+    if (b == 0 && tid == 0) {
+        d[n - 2] = diag_j;
+        e[n - 2] = beta_j;
+        tau[n - 2] = 0.0;
+        d[n - 1] = __ldcg(A + (size_t)(n - 1) * lda + (n - 1));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Leaves: symmetric tridiagonal QL with implicit Wilkinson shift (EISPACK tql2 lineage), one warp
+// per leaf; lane = row of the eigenvector matrix.  The scalar recurrence is executed redundantly by
+// all lanes on a shared copy of (d, e) -- every lane writes identical values.
+__global__ void __launch_bounds__(32)
+dc_leaf_kernel(const double* __restrict__ d_in, const double* __restrict__ e_in, int n, int depth,
+               double* __restrict__ d_out, double* __restrict__ Q, int ldq, int* __restrict__ fail) {
+    const int leaf = blockIdx.x, lane = threadIdx.x;
+    const int s0 = node_start(n, depth, leaf), s1 = node_start(n, depth, leaf + 1);
+    const int m = s1 - s0;
+    __shared__ double Zs[kLeaf][kLeaf + 1];
+    __shared__ double ds[kLeaf + 1], es[kLeaf + 1];
+    if (lane < m) {
+        double val = d_in[s0 + lane];
+        if (lane == 0 && s0 > 0) val -= fabs(e_in[s0 - 1]);          // rank-one tear on the left boundary
+        if (lane == m - 1 && s1 < n) val -= fabs(e_in[s1 - 1]);      // ... and on the right boundary
+        ds[lane] = val;
+        es[lane] = (lane < m - 1) ? e_in[s0 + lane] : 0.0;
+    }
+    for (int i = 0; i < kLeaf; ++i) Zs[lane][i] = (i == lane) ? 1.0 : 0.0;
+    __syncwarp();
+    bool failed = false;
+    for (int l = 0; l < m; ++l) {
+        int iter = 0;
+        while (true) {
+            int mm = l;
+            while (mm < m - 1) {
+                const double dd = fabs(ds[mm]) + fabs(ds[mm + 1]);
+                if (fabs(es[mm]) <= kUnitRoundoff * dd) break;
+                ++mm;
+            }
+            if (mm == l) break;
+            if (++iter > 80) { failed = true; break; }
+            double g = (ds[l + 1] - ds[l]) / (2.0 * es[l]);
+            double r = hypot(g, 1.0);
+            g = ds[mm] - ds[l] + es[l] / (g + copysign(r, g));
+            double s = 1.0, c = 1.0, p = 0.0;
+            bool broke = false;
+            for (int i = mm - 1; i >= l; --i) {
+                double f = s * es[i];
+                const double bb = c * es[i];
+                r = hypot(f, g);
+                es[i + 1] = r;
+                if (r == 0.0) {
+                    ds[i + 1] -= p;
+                    es[mm] = 0.0;
+                    broke = true;
+                    break;
+                }
+                s = f / r;
+                c = g / r;
+                g = ds[i + 1] - p;
+                r = (ds[i] - g) * s + 2.0 * c * bb;
+                p = s * r;
+                ds[i + 1] = g + p;
+                g = c * r - bb;
+                const double z1 = Zs[lane][i + 1], z0 = Zs[lane][i];
+                Zs[lane][i + 1] = s * z0 + c * z1;
+                Zs[lane][i] = c * z0 - s * z1;
+            }
+            if (broke) continue;
+            ds[l] -= p;
+            es[l] = g;
+            es[mm] = 0.0;
+        }
+        if (failed) break;
+    }
+    __syncwarp();
+    if (failed && lane == 0) atomicExch(fail, 1);
+    if (lane < m) d_out[s0 + lane] = ds[lane];
+    for (int i = 0; i < m; ++i)
+        if (lane < m) Q[(size_t)(s0 + lane) + (size_t)(s0 + i) * ldq] = Zs[lane][i];
+}
+
+// ---------------------------------------------------------------------------------------------
+struct DcArrays {
+    double* dk;      // n  non-deflated poles (ascending) at [off, off+k)
+    double* zk;      // n  their z components
+    int* colmap;     // n  source column of output column off+j (non-deflated first, then deflated)
+    int* rotA; int* rotB; double* rotC; double* rotS;   // n  deflation rotations at [off, off+nrot)
+    int* org;        // n  origin pole of root j
+    double* mu;      // n  offset of root j from its origin
+    double* zh;      // n  Gu-Eisenstat z-hat
+    int* kArr; int* nrotArr; double* rhoArr;            // per merge
+};
+
+// One CTA per merge.  Dynamic shared memory: 3*nm doubles + 2*nm ints.
+__global__ void __launch_bounds__(1024)
+dc_setup_kernel(int n, int depth, const double* __restrict__ e, const double* __restrict__ dcur,
+                const double* __restrict__ Q, int ldq, double* __restrict__ dnew, DcArrays a) {
+    const int node = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    const int off = node_start(n, depth, node), end = node_start(n, depth, node + 1);
+    const int split = node_start(n, depth + 1, 2 * node + 1);
+    const int nm = end - off, n1 = split - off;
+    extern __shared__ double smd[];
+    double* draw = smd;                 // unsorted d; later: deflated values
+    double* dsrt = smd + nm;
+    double* zsrt = smd + 2 * (size_t)nm;
+    int* csrt = reinterpret_cast<int*>(smd + 3 * (size_t)nm);
+    int* cdef = csrt + nm;
+    __shared__ double redm[64];
+    __shared__ int s_k, s_ndef, s_nrot;
+
+    const double beta = e[split - 1];
+    const double sgn = (beta >= 0.0) ? 1.0 : -1.0;
+    const double rho = 2.0 * fabs(beta);
+    for (int c = tid; c < nm; c += nt) draw[c] = dcur[off + c];
+    __syncthreads();
+    double dmax = 0.0, zmax = 0.0;
+    for (int c = tid; c < nm; c += nt) {
+        const double dc = draw[c];
+        int rank = 0;
+        for (int o = 0; o < nm; ++o) {
+            const double dv = draw[o];
+            rank += (dv < dc) || (dv == dc && o < c);
+        }
+        double z = (c < n1) ? Q[(size_t)(split - 1) + (size_t)(off + c) * ldq]
+                            : sgn * Q[(size_t)split + (size_t)(off + c) * ldq];
+        z *= 0.70710678118654752440;
+        dsrt[rank] = dc;
+        zsrt[rank] = z;
+        csrt[rank] = off + c;
+        dmax = fmax(dmax, fabs(dc));
+        zmax = fmax(zmax, fabs(z));
+    }
+    dmax = warp_max(dmax);
+    zmax = warp_max(zmax);
+    if ((tid & 31) == 0) { redm[tid >> 5] = dmax; redm[32 + (tid >> 5)] = zmax; }
+    __syncthreads();
+    dmax = 0.0; zmax = 0.0;
+    for (int wv = 0; wv < (nt >> 5); ++wv) { dmax = fmax(dmax, redm[wv]); zmax = fmax(zmax, redm[32 + wv]); }
+    const double tol = 8.0 * kUnitRoundoff * fmax(dmax, zmax);
+    __syncthreads();   // everyone has read draw[] before it is reused for the deflated list
+
+    if (tid == 0) {
+        int k = 0, ndef = 0, nrot = 0;
+        if (rho * zmax <= tol) {
+            for (int i = 0; i < nm; ++i) { draw[ndef] = dsrt[i]; cdef[ndef] = csrt[i]; ++ndef; }
+        } else {
+            int prev = -1;
+            for (int i = 0; i < nm; ++i) {
+                if (rho * fabs(zsrt[i]) <= tol) {
+                    draw[ndef] = dsrt[i]; cdef[ndef] = csrt[i]; ++ndef;
+                    continue;
+                }
+                if (prev >= 0) {
+                    double sv = -zsrt[prev], cv = zsrt[i];
+                    const double tt = hypot(cv, sv);
+                    const double t = dsrt[i] - dsrt[prev];
+                    cv /= tt; sv /= tt;
+                    if (fabs(t * cv * sv) <= tol) {
+                        // rotate (prev, i): z_prev -> 0 (deflated), z_i -> tt
+                        zsrt[i] = tt;
+                        a.rotA[off + nrot] = csrt[prev]; a.rotB[off + nrot] = csrt[i];
+                        a.rotC[off + nrot] = cv; a.rotS[off + nrot] = sv;
+                        ++nrot;
+                        const double dp = dsrt[prev] * cv * cv + dsrt[i] * sv * sv;
+                        dsrt[i] = dsrt[prev] * sv * sv + dsrt[i] * cv * cv;
+                        draw[ndef] = dp; cdef[ndef] = csrt[prev]; ++ndef;
+                    } else {
+                        a.dk[off + k] = dsrt[prev]; a.zk[off + k] = zsrt[prev]; a.colmap[off + k] = csrt[prev];
+                        ++k;
+                    }
+                }
+                prev = i;
+            }
+            if (prev >= 0) {
+                a.dk[off + k] = dsrt[prev]; a.zk[off + k] = zsrt[prev]; a.colmap[off + k] = csrt[prev];
+                ++k;
+            }
+        }
+        s_k = k; s_ndef = ndef; s_nrot = nrot;
+        a.kArr[node] = k; a.nrotArr[node] = nrot; a.rhoArr[node] = rho;
+    }
+    __syncthreads();
+    const int k = s_k, ndef = s_ndef;
+    for (int t = tid; t < ndef; t += nt) {
+        dnew[off + k + t] = draw[t];
+        a.colmap[off + k + t] = cdef[t];
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dc_rotate_kernel(int n, int depth, double* __restrict__ Q, int ldq, DcArrays a) {
+    const int node = blockIdx.y;
+    const int off = node_start(n, depth, node), end = node_start(n, depth, node + 1);
+    const int row = off + blockIdx.x * 256 + threadIdx.x;
+    if (row >= end) return;
+    const int nrot = a.nrotArr[node];
+    for (int t = 0; t < nrot; ++t) {
+        const int ca = a.rotA[off + t], cb = a.rotB[off + t];
+        const double c = a.rotC[off + t], s = a.rotS[off + t];
+        const double qa = Q[(size_t)row + (size_t)ca * ldq], qb = Q[(size_t)row + (size_t)cb * ldq];
+        Q[(size_t)row + (size_t)ca * ldq] = c * qa + s * qb;
+        Q[(size_t)row + (size_t)cb * ldq] = -s * qa + c * qb;
+    }
+}
+
+// secular function  f(mu) = 1 + rho * sum_i z_i^2 / ((d_i - d_org) - mu), evaluated by one warp
+__device__ __forceinline__ double secular_f(const double* __restrict__ dk, const double* __restrict__ zk, int k,
+                                            double rho, double dorg, double mu, int lane) {
+    double s = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        const double z = zk[i];
+        s += (z * z) / ((dk[i] - dorg) - mu);
+    }
+    s = warp_sum(s);
+    return fma(rho, s, 1.0);
+}
+
+__global__ void __launch_bounds__(256)
+dc_secular_kernel(int n, int depth, double* __restrict__ dnew, DcArrays a) {
+    const int node = blockIdx.y, lane = threadIdx.x & 31;
+    const int off = node_start(n, depth, node);
+    const int k = a.kArr[node];
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= k) return;
+    const double rho = a.rhoArr[node];
+    const double* dk = a.dk + off;
+    const double* zk = a.zk + off;
+    int org;
+    double sign, hi;
+    if (j < k - 1) {
+        const double half = 0.5 * (dk[j + 1] - dk[j]);
+        const double fmid = secular_f(dk, zk, k, rho, dk[j], half, lane);
+        if (fmid > 0.0) { org = j; sign = 1.0; } else { org = j + 1; sign = -1.0; }
+        hi = half;
+    } else {
+        double s = 0.0;
+        for (int i = lane; i < k; i += 32) s = fma(zk[i], zk[i], s);
+        s = warp_sum(s);
+        org = k - 1; sign = 1.0;
+        hi = rho * s * (1.0 + 16.0 * kUnitRoundoff) + 1e-300;
+    }
+    const double dorg = dk[org];
+    long long lo_i = 0, hi_i = __double_as_longlong(hi);
+    while (hi_i - lo_i > 1) {
+        const long long mid_i = lo_i + ((hi_i - lo_i) >> 1);   // no overflow: patterns of |mu| >= 2 exceed 2^62
+        const double aa = __longlong_as_double(mid_i);
+        const double val = sign * secular_f(dk, zk, k, rho, dorg, sign * aa, lane);
+        if (val < 0.0) lo_i = mid_i; else hi_i = mid_i;
+    }
+    const double mu = sign * __longlong_as_double(hi_i);
+    if (lane == 0) {
+        a.org[off + j] = org;
+        a.mu[off + j] = mu;
+        dnew[off + j] = dorg + mu;
+    }
+}
+
+__global__ void __launch_bounds__(256)
+dc_zhat_kernel(int n, int depth, DcArrays a) {
+    const int node = blockIdx.y, lane = threadIdx.x & 31;
+    const int off = node_start(n, depth, node);
+    const int k = a.kArr[node];
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (i >= k) return;
+    const double* dk = a.dk + off;
+    const double* mu = a.mu + off;
+    const int* org = a.org + off;
+    const double di = dk[i];
+    double prod = 1.0;
+    for (int j = lane; j < k; j += 32) {
+        const double num = (dk[org[j]] - di) + mu[j];     // lambda_j - d_i
+        prod *= (j == i) ? num : num / (dk[j] - di);
+    }
+    prod = warp_prod(prod);
+    if (lane == 0) a.zh[off + i] = copysign(sqrt(fabs(prod) / a.rhoArr[node]), a.zk[off + i]);
+}
+
+__global__ void __launch_bounds__(256)
+dc_smat_kernel(int n, int depth, double* __restrict__ S, int lds, DcArrays a) {
+    const int node = blockIdx.y, lane = threadIdx.x & 31;
+    const int off = node_start(n, depth, node);
+    const int k = a.kArr[node];
+    const int j = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (j >= k) return;
+    const double* dk = a.dk + off;
+    const double* zh = a.zh + off;
+    const double dorg = dk[a.org[off + j]], mu = a.mu[off + j];
+    double* col = S + (size_t)off + (size_t)(off + j) * lds;
+    double nrm = 0.0;
+    for (int i = lane; i < k; i += 32) {
+        const double val = zh[i] / ((dk[i] - dorg) - mu);     // zh_i / (d_i - lambda_j)
+        col[i] = val;
+        nrm = fma(val, val, nrm);
+    }
+    nrm = warp_sum(nrm);
+    const double inv = 1.0 / sqrt(nrm);
+    for (int i = lane; i < k; i += 32) col[i] *= inv;
+}
+
+// Qn[off+row, off+j] = sum_{i<k} Q[off+row, colmap[off+i]] * S[off+i, off+j]   (row < nm, j < k)
+constexpr int DBM = 64, DBN = 64, DBK = 16;
+__global__ void __launch_bounds__(256)
+dc_gemm_kernel(int n, int depth, const double* __restrict__ Q, int ldq, const double* __restrict__ S, int lds,
+               double* __restrict__ Qn, DcArrays a) {
+    const int node = blockIdx.z;
+    const int off = node_start(n, depth, node), end = node_start(n, depth, node + 1);
+    const int nm = end - off;
+    const int k = a.kArr[node];
+    const int i0 = blockIdx.x * DBM, j0 = blockIdx.y * DBN;
+    if (i0 >= nm || j0 >= k) return;
+    __shared__ double As[DBK][DBM + 1];
+    __shared__ double Bs[DBK][DBN + 1];
+    __shared__ int cols[DBK];
+    const int tid = threadIdx.x;
+    const int tx = tid & 15, ty = tid >> 4;
+    double acc[4][4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int vv = 0; vv < 4; ++vv) acc[u][vv] = 0.0;
+    for (int k0 = 0; k0 < k; k0 += DBK) {
+        if (tid < DBK) cols[tid] = (k0 + tid < k) ? a.colmap[off + k0 + tid] : -1;
+        __syncthreads();
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int idx = tid + l * 256;
+            const int i = idx & 63, kk = idx >> 6;
+            const int gi = i0 + i, c = cols[kk];
+            As[kk][i] = (gi < nm && c >= 0) ? Q[(size_t)(off + gi) + (size_t)c * ldq] : 0.0;
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+            const int idx = tid + l * 256;
+            const int kk = idx & 15, j = idx >> 4;
+            const int gj = j0 + j, gk = k0 + kk;
+            Bs[kk][j] = (gj < k && gk < k) ? S[(size_t)(off + gk) + (size_t)(off + gj) * lds] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < DBK; ++kk) {
+            double av[4], bv[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) av[u] = As[kk][tx + 16 * u];
+#pragma unroll
+            for (int vv = 0; vv < 4; ++vv) bv[vv] = Bs[kk][ty + 16 * vv];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int vv = 0; vv < 4; ++vv) acc[u][vv] = fma(av[u], bv[vv], acc[u][vv]);
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int vv = 0; vv < 4; ++vv) {
+        const int gj = j0 + ty + 16 * vv;
+        if (gj >= k) continue;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int gi = i0 + tx + 16 * u;
+            if (gi >= nm) continue;
+            Qn[(size_t)(off + gi) + (size_t)(off + gj) * ldq] = acc[u][vv];
+        }
+    }
+}
+
+// deflated columns are copied through: Qn[:, off+t] = Q[:, colmap[off+t]] for t in [k, nm)
+__global__ void __launch_bounds__(128)
+dc_copy_deflated_kernel(int n, int depth, const double* __restrict__ Q, int ldq, double* __restrict__ Qn, DcArrays a) {
+    const int node = blockIdx.z;
+    const int off = node_start(n, depth, node), end = node_start(n, depth, node + 1);
+    const int nm = end - off;
+    const int k = a.kArr[node];
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    if (row >= nm) return;
+    for (int t = k + blockIdx.y; t < nm; t += gridDim.y) {
+        const int c = a.colmap[off + t];
+        Qn[(size_t)(off + row) + (size_t)(off + t) * ldq] = Q[(size_t)(off + row) + (size_t)c * ldq];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// U = H_0 H_1 ... H_{n-3} Z in place; one warp per column, the column lives in shared memory.
+__global__ void backtransform_kernel(const double* __restrict__ A, int lda, const double* __restrict__ tau, int n,
+                                     double* __restrict__ Z, int ldz, int ncols) {
+    extern __shared__ double zsm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int wpb = blockDim.x >> 5;
+    const int col = blockIdx.x * wpb + warp;
+    if (col >= ncols) return;
+    double* z = zsm + (size_t)warp * n;
+    double* zc = Z + (size_t)col * ldz;
+    for (int i = lane; i < n; i += 32) z[i] = zc[i];
+    __syncwarp();
+    for (int j = n - 3; j >= 0; --j) {
+        const double t = tau[j];
+        if (t == 0.0) continue;
+        const double* v = A + (size_t)j * lda;
+        double dot = 0.0;
+        for (int i = j + 1 + lane; i < n; i += 32) dot = fma(v[i], z[i], dot);
+        dot = warp_sum(dot) * t;
+        for (int i = j + 1 + lane; i < n; i += 32) z[i] = fma(-dot, v[i], z[i]);
+        __syncwarp();
+    }
+    for (int i = lane; i < n; i += 32) zc[i] = z[i];
+}
+
+__global__ void dc_check_kernel(const double* __restrict__ U, int ldu, int n, int* __restrict__ fail) {
+    // column norms must be 1 to ~1e-8 and finite (cheap sanity check of the whole pipeline)
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const double* c = U + (size_t)warp * ldu;
+    double acc = 0.0;
+    for (int i = lane; i < n; i += 32) acc = fma(c[i], c[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0 && !(fabs(acc - 1.0) < 1e-8)) atomicExch(fail, 2);
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+void EigWorkspace::reserve_dc(int n) {
+    if (n <= dc_cap) return;
+    const size_t nn = (size_t)n * n;
+    Qa.alloc(nn);
+    Qb.alloc(nn);
+    Sb.alloc(nn);
+    dcd.alloc(16 * (size_t)n + 64);
+    dci.alloc(8 * (size_t)n + 64);
+    dc_cap = n;
+}
+
+// Eigen-decomposition of the symmetric matrix As (n x n, ld n, full storage; DESTROYED).
+// Results: eigenvalues (unsorted) in *lam_out, eigenvectors in the columns of *vec_out (ld n).
+// Returns false if a device-side sanity check failed (caller falls back to Jacobi).
+bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double** lam_out, double** vec_out) {
+    ws.reserve_dc(n);
+    double* dd = ws.dcd.p;
+    double* d0 = dd;                 // tridiagonal diagonal
+    double* e0 = dd + n;             // off-diagonal
+    double* tau = dd + 2 * (size_t)n;
+    double* pbuf = dd + 3 * (size_t)n;   // 2n
+    double* dA = dd + 5 * (size_t)n;     // eigenvalue ping
+    double* dB = dd + 6 * (size_t)n;     // eigenvalue pong
+    DcArrays a;
+    a.dk = dd + 7 * (size_t)n;
+    a.zk = dd + 8 * (size_t)n;
+    a.rotC = dd + 9 * (size_t)n;
+    a.rotS = dd + 10 * (size_t)n;
+    a.mu = dd + 11 * (size_t)n;
+    a.zh = dd + 12 * (size_t)n;
+    a.rhoArr = dd + 13 * (size_t)n;
+    int* di = ws.dci.p;
+    a.colmap = di;
+    a.rotA = di + n;
+    a.rotB = di + 2 * (size_t)n;
+    a.org = di + 3 * (size_t)n;
+    a.kArr = di + 4 * (size_t)n;
+    a.nrotArr = di + 5 * (size_t)n;
+    int* fail = di + 6 * (size_t)n;
+    NLE_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
+
+    // ---- 1. tridiagonalisation
+    {
+        size_t smem = (3 * (size_t)n + 2 * kTrdWarps) * sizeof(double);
+        NLE_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int per_sm = 0;
+        NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_kernel, kTrdThreads, smem));
+        if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(n) + ")"};
+        int grid = sm_count();
+        if (grid > n) grid = n;
+        int lda = n;
+        void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf};
+        NLE_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(grid), dim3(kTrdThreads), args, smem, s));
+        ++g_launches;
+    }
+    // ---- 2. divide & conquer on (d0, e0)
+    int depth = 0;
+    while (((n + (1 << depth) - 1) >> depth) > kLeaf) ++depth;
+    const size_t nn = (size_t)n * n;
+    NLE_CUDA(cudaMemsetAsync(ws.Qa.p, 0, nn * sizeof(double), s));
+    NLE_CUDA(cudaMemsetAsync(ws.Qb.p, 0, nn * sizeof(double), s));
+    double* Qc = ws.Qa.p;
+    double* Qn = ws.Qb.p;
+    double* dc = dA;
+    double* dn = dB;
+    dc_leaf_kernel<<<1 << depth, 32, 0, s>>>(d0, e0, n, depth, dc, Qc, n, fail);
+    NLE_LAUNCH_CHECK();
+    for (int t = depth - 1; t >= 0; --t) {
+        const int nmerge = 1 << t;
+        const int nm_max = (n + nmerge - 1) / nmerge;
+        const size_t smem = (size_t)nm_max * (3 * sizeof(double) + 2 * sizeof(int));
+        NLE_CUDA(cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int threads = nm_max >= 1024 ? 1024 : (nm_max >= 256 ? 256 : 64);
+        dc_setup_kernel<<<nmerge, threads, smem, s>>>(n, t, e0, dc, Qc, n, dn, a);
+        NLE_LAUNCH_CHECK();
+        dc_rotate_kernel<<<dim3(cdiv(nm_max, 256), nmerge), 256, 0, s>>>(n, t, Qc, n, a);
+        NLE_LAUNCH_CHECK();
+        dc_secular_kernel<<<dim3(cdiv(nm_max, 8), nmerge), 256, 0, s>>>(n, t, dn, a);
+        NLE_LAUNCH_CHECK();
+        dc_zhat_kernel<<<dim3(cdiv(nm_max, 8), nmerge), 256, 0, s>>>(n, t, a);
+        NLE_LAUNCH_CHECK();
+        dc_smat_kernel<<<dim3(cdiv(nm_max, 8), nmerge), 256, 0, s>>>(n, t, ws.Sb.p, n, a);
+        NLE_LAUNCH_CHECK();
+        dc_gemm_kernel<<<dim3(cdiv(nm_max, DBM), cdiv(nm_max, DBN), nmerge), 256, 0, s>>>(n, t, Qc, n, ws.Sb.p, n, Qn, a);
+        NLE_LAUNCH_CHECK();
+        int ycopies = nm_max < 64 ? nm_max : 64;
+        dc_copy_deflated_kernel<<<dim3(cdiv(nm_max, 128), ycopies, nmerge), 128, 0, s>>>(n, t, Qc, n, Qn, a);
+        NLE_LAUNCH_CHECK();
+        std::swap(Qc, Qn);
+        std::swap(dc, dn);
+    }
+    // ---- 3. back-transformation (in place in Qc)
+    {
+        int dev = 0, max_smem = 0;
+        NLE_CUDA(cudaGetDevice(&dev));
+        NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        int wpb = (int)((size_t)(max_smem - 1024) / ((size_t)n * sizeof(double)));
+        if (wpb > 8) wpb = 8;
+        if (wpb < 1) throw Unsupported{"eigensolver: back-transformation column does not fit in shared memory (n=" + std::to_string(n) + ")"};
+        const size_t smem = (size_t)wpb * n * sizeof(double);
+        NLE_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        backtransform_kernel<<<cdiv(n, wpb), wpb * 32, smem, s>>>(As, n, tau, n, Qc, n, n);
+        NLE_LAUNCH_CHECK();
+    }
+    dc_check_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(Qc, n, n, fail);
+    NLE_LAUNCH_CHECK();
+    int fail_h = 0;
+    NLE_CUDA(cudaMemcpyAsync(&fail_h, fail, sizeof(int), cudaMemcpyDeviceToHost, s));
+    NLE_CUDA(cudaStreamSynchronize(s));
+    *lam_out = dc;
+    *vec_out = Qc;
+    if (fail_h != 0 && getenv("NLE_B200_EIG_DEBUG")) {
+        fprintf(stderr, "[eig_dc n=%d] sanity check failed, code %d (1 = leaf QL, 2 = column norm)\n", n, fail_h);
+        if (getenv("NLE_B200_EIG_NOCHECK")) return true;
+    }
+    return fail_h == 0;
+}
+
+}  // namespace nle
