@@ -10,6 +10,8 @@
 #include <memory>
 
 #include "../../include/nle_b200.h"
+#include <chrono>
+
 #include "kernels.cuh"
 
 namespace nle {
@@ -59,6 +61,21 @@ static Grid make_grid(int rows, int cols, int nRowSamples, int nColSamples) {
     for (int c = 0; c < cols; ++c) { g.colrank[c] = cnt; if (g.colb[c] >= 0) ++cnt; }
     return g;
 }
+
+// Developer trace (NLE_B200_TRACE=1): host wall-clock between labelled points, stream drained at each.
+struct Trace {
+    bool on;
+    cudaStream_t s;
+    std::chrono::steady_clock::time_point t0;
+    explicit Trace(cudaStream_t st) : on(getenv("NLE_B200_TRACE") != nullptr), s(st), t0(std::chrono::steady_clock::now()) {}
+    void operator()(const char* label) {
+        if (!on) return;
+        cudaStreamSynchronize(s);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[trace] %-28s %9.3f ms\n", label, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = std::chrono::steady_clock::now();
+    }
+};
 
 struct Timer {
     cudaEvent_t a, b;
@@ -184,6 +201,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     const long long nloc = f->nloc;
     const int nrows = row1 - row0;
 
+    Trace tr(s);
     Timer t_total(s);
     Timer t_setup(s);
     // ---- tables and sample data
@@ -225,11 +243,13 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     DevBuf<int> d_cnt(4);
     launch_ka(p, nC, d_selrows.p, d_selcols.p, Ysel.p, hx, hy, Ka.p, s);
     f->times_ms[0] = t_setup.stop();
+    tr("setup tables Ka");
     Timer t_eig1(s);
     EigWorkspace ws;
     f->eig_sweeps[0] = sym_eig(Ka.p, p, p, kEps, /*psd_hint=*/true, U.p, lam.p, d_cnt.p, ws, s);
     const int r = read_int(d_cnt.p, s);
     f->times_ms[1] = t_eig1.stop();
+    tr("eig Ka");
     f->r = r;
     if (r < 1) throw Unsupported{"Ka has no eigenvalue >= 1e-10"};
 
@@ -275,6 +295,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         if (!last) phiT_x(rsel.p, svec.p);                 // the final r is only used on perm[0:r]
     }
     f->times_ms[2] = t_sink.stop();
+    tr("sinkhorn");
 
     // ---- Gram of the rest pixels (filter.cpp:296 "Wab * Wab^T" in factor form, App. A.5)
     Timer t_gram(s);
@@ -288,6 +309,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         NLE_CUDA(cudaStreamSynchronize(s));
     }
     f->times_ms[3] = t_gram.stop();
+    tr("gram");
 
     // ---- small algebra: Wa, Wab Wab^T, orthogonalisation (filter.cpp:247-250, 282-327)
     Timer t_small(s);
@@ -311,10 +333,12 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         dgemm(false, false, r, r, r, 1.0, Lm.p, r, D2.p, r, 0.0, T3.p, r, s);
         dgemm(false, true, r, r, r, 1.0, T3.p, r, Lm.p, r, 1.0, WW.p, r, s);
     }
+    tr("small: Wa, WW");
     // eig(Wa) -> Wa^-1/2 (pseudo-inverse root on lambda >= 1e-10, filter.cpp:287-292)
     DevBuf<double> Ua((size_t)r * r), la(r), irl(r), UaS((size_t)r * r), irw((size_t)r * r);
     f->eig_sweeps[1] = sym_eig(Wa.p, r, r, kEps, /*psd_hint=*/false, Ua.p, la.p, d_cnt.p, ws, s);
     const int r2 = read_int(d_cnt.p, s);
+    tr("small: eig Wa");
     f->r2 = r2;
     if (r2 < 1) throw Unsupported{"Wa has no eigenvalue >= 1e-10"};
     guarded_inv_sqrt(la.p, irl.p, r2, kEps, s);
@@ -325,9 +349,11 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     dgemm(false, false, r, r, r, 1.0, irw.p, r, WW.p, r, 0.0, T2.p, r, s);
     copy_dd(Q.p, Wa.p, (size_t)r * r, s);
     dgemm(false, false, r, r, r, 1.0, T2.p, r, irw.p, r, 1.0, Q.p, r, s);
+    tr("small: invroot, Q");
     DevBuf<double> Vq((size_t)r * r), Sq(r);
     f->eig_sweeps[2] = sym_eig(Q.p, r, r, kEps, /*psd_hint=*/false, Vq.p, Sq.p, d_cnt.p, ws, s);
     const int nq = read_int(d_cnt.p, s);
+    tr("small: eig Q");
     const int k = std::min(nEig, nq);                                                // :314
     f->k = k;
     if (k < 1) throw Unsupported{"Q has no eigenvalue >= 1e-10"};
@@ -339,6 +365,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     scale_rows_cols(r, k, Vq.p, r, nullptr, irs.p, VqS.p, r, s);
     dgemm(false, false, r, k, r, 1.0, irw.p, r, VqS.p, r, 0.0, Mv.p, r, s);
     f->times_ms[4] = t_small.stop();
+    tr("small: Mv");
 
     // ---- extension V = [Wa ; Wab^T] invRootWa Vq Sq^-1/2 (:324-327) and un-permute (:502)
     Timer t_ext(s);
@@ -363,6 +390,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     launch_extension(tb, cfull.p, Y.p, k, f->V.p, s);
     NLE_CUDA(cudaStreamSynchronize(s));
     f->times_ms[5] = t_ext.stop();
+    tr("extension");
     f->times_ms[6] = t_total.stop();
 
     f->ascratch.alloc((size_t)apply_blocks(nloc) * k + 16);

@@ -37,6 +37,12 @@ struct InvalidArg { std::string msg; };
 struct Unsupported { std::string msg; };
 struct NoConvergence { std::string msg; };
 
+// Device memory comes from the CUDA stream-ordered pool (cudaMallocAsync on the legacy stream, release
+// threshold = unlimited, set once in dense.cu): after the first image every allocation of the
+// training pipeline is a pool hit (microseconds) instead of a cudaMalloc/cudaFree pair.
+void* pool_alloc(size_t bytes);
+void pool_free(void* p);
+
 // RAII device buffer (typed).
 template <typename T>
 struct DevBuf {
@@ -55,10 +61,10 @@ struct DevBuf {
     void alloc(size_t count) {
         release();
         n = count;
-        if (count) NLE_CUDA(cudaMalloc(&p, count * sizeof(T)));
+        if (count) p = static_cast<T*>(pool_alloc(count * sizeof(T)));
     }
     void release() {
-        if (p) cudaFree(p);
+        if (p) pool_free(p);
         p = nullptr;
         n = 0;
     }

@@ -8,6 +8,30 @@ namespace nle {
 
 thread_local long long g_launches = 0;
 
+static void pool_init_once() {
+    static thread_local int inited_dev = -1;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    if (inited_dev == dev) return;
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+        unsigned long long thr = ~0ULL;   // keep freed blocks cached in the pool across synchronisations
+        cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+    }
+    inited_dev = dev;
+}
+
+void* pool_alloc(size_t bytes) {
+    pool_init_once();
+    void* p = nullptr;
+    NLE_CUDA(cudaMallocAsync(&p, bytes, (cudaStream_t) nullptr));
+    return p;
+}
+
+void pool_free(void* p) {
+    if (p) cudaFreeAsync(p, (cudaStream_t) nullptr);
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) {
