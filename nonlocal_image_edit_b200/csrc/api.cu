@@ -161,6 +161,10 @@ __global__ void vec_axpy_kernel(double* y, const double* x, const double* scale,
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) y[i] = fma(scale[i], x[i], y[i]);
 }
+__global__ void add_diag_kernel(double* M, int n, const double* d) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) M[i + (size_t)i * n] += d[i];
+}
 __global__ void vec_mul_kernel(double* out, const double* a, const double* b, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) out[i] = a[i] * b[i];
@@ -168,6 +172,11 @@ __global__ void vec_mul_kernel(double* out, const double* a, const double* b, in
 void vec_axpy(double* y, const double* x, const double* scale, int n, cudaStream_t s) {
     if (n <= 0) return;
     vec_axpy_kernel<<<cdiv(n, 256), 256, 0, s>>>(y, x, scale, n);
+    NLE_LAUNCH_CHECK();
+}
+void add_diag(double* M, int n, const double* d, cudaStream_t s) {
+    if (n <= 0) return;
+    add_diag_kernel<<<cdiv(n, 256), 256, 0, s>>>(M, n, d);
     NLE_LAUNCH_CHECK();
 }
 void vec_mul(double* out, const double* a, const double* b, int n, cudaStream_t s) {
@@ -201,23 +210,28 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     const long long nloc = f->nloc;
     const int nrows = row1 - row0;
 
+    thread_arena().reset();     // all temporaries below are TmpBuf views of the thread's arena
     Trace tr(s);
     Timer t_total(s);
     Timer t_setup(s);
+    // V is the one large, long-lived buffer (nloc x k doubles, k <= nEig).  Take it from the pool BEFORE the
+    // temporaries so that the block a previous filter released is reused for it instead of being carved up
+    // (a fresh 400 MB mapping costs ~1 s on this driver).
+    f->V.alloc((size_t)nloc * std::min(nEig, p));
     // ---- tables and sample data
-    DevBuf<int> d_selrows(nR), d_selcols(nC), d_rowa(rows), d_colb(cols);
+    TmpBuf<int> d_selrows(nR), d_selcols(nC), d_rowa(rows), d_colb(cols);
     d_selrows.upload(g.sel_rows.data(), nR, s);
     d_selcols.upload(g.sel_cols.data(), nC, s);
     d_rowa.upload(g.rowa.data(), rows, s);
     d_colb.upload(g.colb.data(), cols, s);
-    DevBuf<double> Er((size_t)rows * nR), Ec((size_t)cols * nC), EcT((size_t)cols * nC), Gt(256);
+    TmpBuf<double> Er((size_t)rows * nR), Ec((size_t)cols * nC), EcT((size_t)cols * nC), Gt(256);
     launch_tables(rows, cols, nR, nC, d_selrows.p, d_selcols.p, hx, hy, Er.p, Ec.p, EcT.p, Gt.p, s);
     std::vector<int32_t> sel_h(p);
     for (int a = 0; a < nR; ++a)
         for (int b = 0; b < nC; ++b) sel_h[a * nC + b] = g.sel_rows[a] * cols + g.sel_cols[b];
-    DevBuf<int32_t> d_sel(p);
+    TmpBuf<int32_t> d_sel(p);
     d_sel.upload(sel_h.data(), p, s);
-    DevBuf<uint8_t> Ysel(p);
+    TmpBuf<uint8_t> Ysel(p);
     std::vector<uint8_t> ysel_h;
     if (sample_lum_host) {
         Ysel.upload(sample_lum_host, p, s);
@@ -239,13 +253,13 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     tb.rowa = d_rowa.p; tb.colb = d_colb.p;
 
     // ---- Ka and its eigen-decomposition (filter.cpp:133-137,144,262)
-    DevBuf<double> Ka((size_t)p * p), U((size_t)p * p), lam(p);
-    DevBuf<int> d_cnt(4);
+    TmpBuf<double> Ka((size_t)p * p), U((size_t)p * p), lam(p);
+    TmpBuf<int> d_cnt(4);
     launch_ka(p, nC, d_selrows.p, d_selcols.p, Ysel.p, hx, hy, Ka.p, s);
     f->times_ms[0] = t_setup.stop();
     tr("setup tables Ka");
     Timer t_eig1(s);
-    EigWorkspace ws;
+    static thread_local EigWorkspace ws;   // grow-only, reused by every training call of this thread
     f->eig_sweeps[0] = sym_eig(Ka.p, p, p, kEps, /*psd_hint=*/true, U.p, lam.p, d_cnt.p, ws, s);
     const int r = read_int(d_cnt.p, s);
     f->times_ms[1] = t_eig1.stop();
@@ -255,9 +269,9 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
 
     // ---- Sinkhorn on the factors (filter.cpp:230-245)
     Timer t_sink(s);
-    DevBuf<double> inv_lam(p), xsel(p), ysel(p), svec(p), tvec(p), t2(p), wvec(p), lt(p);
-    DevBuf<double> xfull((size_t)nloc), cfull((size_t)nloc);
-    DevBuf<double> spart(((size_t)nrows + cdiv(nrows, 32) + 1) * p);
+    TmpBuf<double> inv_lam(p), xsel(p), ysel(p), svec(p), tvec(p), t2(p), wvec(p), lt(p);
+    TmpBuf<double> xfull((size_t)nloc), cfull((size_t)nloc);
+    TmpBuf<double> spart(((size_t)nrows + cdiv(nrows, 32) + 1) * p);
     copy_dd(inv_lam.p, lam.p, p, s);
     guarded_reciprocal(inv_lam.p, r, kEps, s);            // filter.cpp:265-266
     // t = phi^T x = U_r^T x_sel + Lam^-1 U_r^T (Kab x_rest)
@@ -285,7 +299,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     do_allreduce(f.get(), svec.p, p);
     launch_fill(xsel.p, p, 1.0, s);
     phiT_x(xsel.p, svec.p);
-    DevBuf<double> csel(p), rsel(p);
+    TmpBuf<double> csel(p), rsel(p);
     for (int it = 0; it < T; ++it) {
         half_step(csel.p, true);                           // c = recip(K~ r)          (:239-240)
         copy_dd(cfull.p, xfull.p, (size_t)nloc, s);
@@ -299,9 +313,9 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
 
     // ---- Gram of the rest pixels (filter.cpp:296 "Wab * Wab^T" in factor form, App. A.5)
     Timer t_gram(s);
-    DevBuf<double> Gp((size_t)p * p);
+    TmpBuf<double> Gp((size_t)p * p);
     {
-        DevBuf<double> gscratch(gram_scratch_doubles(tb));
+        TmpBuf<double> gscratch(gram_scratch_doubles(tb));
         Timer t_gk(s);
         launch_gram(tb, cfull.p, gscratch.p, Gp.p, s);
         f->times_ms[7] = t_gk.stop();                       // gram_kernel + its partial-tile reduce only
@@ -314,7 +328,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     // ---- small algebra: Wa, Wab Wab^T, orthogonalisation (filter.cpp:247-250, 282-327)
     Timer t_small(s);
     // phi_top = U[0:r,0:r] (the first r samples are the "landmarks", filter.cpp:247)
-    DevBuf<double> Lm((size_t)r * r), Ct((size_t)r * r), Wa((size_t)r * r), Bm((size_t)r * p),
+    TmpBuf<double> Lm((size_t)r * r), Ct((size_t)r * r), Wa((size_t)r * r), Bm((size_t)r * p),
         T1((size_t)r * p), WW((size_t)r * r);
     scale_rows_cols(r, r, U.p, p, rsel.p, lam.p, Lm.p, r, s);          // L = diag(rvec) phi_top Lam
     scale_rows_cols(r, r, U.p, p, csel.p, nullptr, Ct.p, r, s);        // diag(c) phi_top
@@ -327,7 +341,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     if (p > r) {
         // samples r..p-1 are demoted to "rest" by filter.cpp:247: add L (dem^T dem) L^T
         const int nd = p - r;
-        DevBuf<double> dem((size_t)nd * r), D2((size_t)r * r), T3((size_t)r * r);
+        TmpBuf<double> dem((size_t)nd * r), D2((size_t)r * r), T3((size_t)r * r);
         scale_rows_cols(nd, r, U.p + r, p, csel.p + r, nullptr, dem.p, nd, s);
         dgemm(true, false, r, r, nd, 1.0, dem.p, nd, dem.p, nd, 0.0, D2.p, r, s);
         dgemm(false, false, r, r, r, 1.0, Lm.p, r, D2.p, r, 0.0, T3.p, r, s);
@@ -335,7 +349,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     }
     tr("small: Wa, WW");
     // eig(Wa) -> Wa^-1/2 (pseudo-inverse root on lambda >= 1e-10, filter.cpp:287-292)
-    DevBuf<double> Ua((size_t)r * r), la(r), irl(r), UaS((size_t)r * r), irw((size_t)r * r);
+    TmpBuf<double> Ua((size_t)r * r), la(r), irl(r), UaS((size_t)r * r), irw((size_t)r * r);
     f->eig_sweeps[1] = sym_eig(Wa.p, r, r, kEps, /*psd_hint=*/false, Ua.p, la.p, d_cnt.p, ws, s);
     const int r2 = read_int(d_cnt.p, s);
     tr("small: eig Wa");
@@ -344,24 +358,38 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     guarded_inv_sqrt(la.p, irl.p, r2, kEps, s);
     scale_rows_cols(r, r2, Ua.p, r, nullptr, irl.p, UaS.p, r, s);
     dgemm(false, true, r, r, r2, 1.0, UaS.p, r, Ua.p, r, 0.0, irw.p, r, s);          // invRootWa (:292)
-    // Q = Wa + invRootWa (Wab Wab^T) invRootWa  (:296)
-    DevBuf<double> T2((size_t)r * r), Q((size_t)r * r);
-    dgemm(false, false, r, r, r, 1.0, irw.p, r, WW.p, r, 0.0, T2.p, r, s);
-    copy_dd(Q.p, Wa.p, (size_t)r * r, s);
-    dgemm(false, false, r, r, r, 1.0, T2.p, r, irw.p, r, 1.0, Q.p, r, s);
+    // Q = Wa + invRootWa (Wab Wab^T) invRootWa  (:296).  With Wa = Ua La Ua^T (lower triangle, as Eigen reads
+    // it) and invRootWa = U+ L+^-1/2 U+^T, Q is block diagonal in the basis Ua:
+    //     Ua^T Q Ua = diag( L+ + L+^-1/2 (U+^T WW U+) L+^-1/2 ,  La_rest ),   La_rest < 1e-10,
+    // so every eigenpair the reference keeps (lambda >= 1e-10, :213-216) is an eigenpair of the r2 x r2 block
+    // M = L+ + L+^-1/2 (U+^T WW U+) L+^-1/2 with eigenvector U+ z.  The third eigensolve is done on M.
+    TmpBuf<double> T2((size_t)r * r), Mq((size_t)r2 * r2), Zq((size_t)r2 * r2), Sq(r);
+    dgemm(false, false, r, r2, r, 1.0, WW.p, r, Ua.p, r, 0.0, T2.p, r, s);           // WW U+
+    dgemm(true, false, r2, r2, r, 1.0, Ua.p, r, T2.p, r, 0.0, Mq.p, r2, s);          // U+^T WW U+
+    scale_rows_cols(r2, r2, Mq.p, r2, irl.p, irl.p, Mq.p, r2, s);
+    add_diag(Mq.p, r2, la.p, s);
     tr("small: invroot, Q");
-    DevBuf<double> Vq((size_t)r * r), Sq(r);
-    f->eig_sweeps[2] = sym_eig(Q.p, r, r, kEps, /*psd_hint=*/false, Vq.p, Sq.p, d_cnt.p, ws, s);
+    f->eig_sweeps[2] = sym_eig(Mq.p, r2, r2, kEps, /*psd_hint=*/false, Zq.p, Sq.p, d_cnt.p, ws, s);
     const int nq = read_int(d_cnt.p, s);
     tr("small: eig Q");
+    TmpBuf<double> Q;
+    if (g_keep_stages) {
+        // the full Q of the reference, only for the stage-parity hook
+        Q.alloc((size_t)r * r);
+        dgemm(false, false, r, r, r, 1.0, irw.p, r, WW.p, r, 0.0, T2.p, r, s);
+        copy_dd(Q.p, Wa.p, (size_t)r * r, s);
+        dgemm(false, false, r, r, r, 1.0, T2.p, r, irw.p, r, 1.0, Q.p, r, s);
+    }
     const int k = std::min(nEig, nq);                                                // :314
     f->k = k;
     if (k < 1) throw Unsupported{"Q has no eigenvalue >= 1e-10"};
     f->S.resize(k);
     NLE_CUDA(cudaMemcpyAsync(f->S.data(), Sq.p, (size_t)k * sizeof(double), cudaMemcpyDeviceToHost, s));
     // Mv = invRootWa Vq Sq^-1/2 (r x k)
-    DevBuf<double> irs(k), VqS((size_t)r * k), Mv((size_t)r * k);
+    TmpBuf<double> irs(k), VqS((size_t)r * k), Mv((size_t)r * k);
     guarded_inv_sqrt(Sq.p, irs.p, k, kEps, s);                                       // :319-321
+    TmpBuf<double> Vq((size_t)r * k);
+    dgemm(false, false, r, k, r2, 1.0, Ua.p, r, Zq.p, r2, 0.0, Vq.p, r, s);          // eigenvectors of Q: U+ z
     scale_rows_cols(r, k, Vq.p, r, nullptr, irs.p, VqS.p, r, s);
     dgemm(false, false, r, k, r, 1.0, irw.p, r, VqS.p, r, 0.0, Mv.p, r, s);
     f->times_ms[4] = t_small.stop();
@@ -369,15 +397,14 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
 
     // ---- extension V = [Wa ; Wab^T] invRootWa Vq Sq^-1/2 (:324-327) and un-permute (:502)
     Timer t_ext(s);
-    f->V.alloc((size_t)nloc * k);
-    DevBuf<double> Vtop((size_t)r * k), Zr((size_t)r * k), RM((size_t)r * k), Y1((size_t)r * k),
+    TmpBuf<double> Vtop((size_t)r * k), Zr((size_t)r * k), RM((size_t)r * k), Y1((size_t)r * k),
         Y((size_t)p * k);
     dgemm(false, false, r, k, r, 1.0, Wa.p, r, Mv.p, r, 0.0, Vtop.p, r, s);          // rows of Wa
     launch_scatter_rows(tb, d_sel.p, 0, r, Vtop.p, r, k, f->V.p, s);
     dgemm(true, false, r, k, r, 1.0, Lm.p, r, Mv.p, r, 0.0, Zr.p, r, s);             // Z_rest = L^T Mv
     if (p > r) {
         const int nd = p - r;
-        DevBuf<double> Vd((size_t)nd * k);
+        TmpBuf<double> Vd((size_t)nd * k);
         dgemm(false, false, nd, k, r, 1.0, U.p + r, p, Zr.p, r, 0.0, Vd.p, nd, s);
         scale_rows_cols(nd, k, Vd.p, nd, csel.p + r, nullptr, Vd.p, nd, s);
         launch_scatter_rows(tb, d_sel.p, r, nd, Vd.p, nd, k, f->V.p, s);
@@ -396,15 +423,15 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     f->ascratch.alloc((size_t)apply_blocks(nloc) * k + 16);
     f->avec.alloc(4 * (size_t)k + 16);
     if (g_keep_stages) {
-        f->Ka = std::move(Ka);
+        f->Ka.alloc((size_t)p * p); copy_dd(f->Ka.p, Ka.p, (size_t)p * p, s);
         f->lam.alloc(r); copy_dd(f->lam.p, lam.p, r, s);
         f->rvec_head.alloc(r); copy_dd(f->rvec_head.p, rsel.p, r, s);
         launch_gather_c_sel(tb, d_sel.p, csel.p, cfull.p, s);
-        f->c = std::move(cfull);
-        f->Wa = std::move(Wa);
-        f->Q = std::move(Q);
+        f->c.alloc((size_t)nloc); copy_dd(f->c.p, cfull.p, (size_t)nloc, s);
+        f->Wa.alloc((size_t)r * r); copy_dd(f->Wa.p, Wa.p, (size_t)r * r, s);
+        f->Q.alloc((size_t)r * r); copy_dd(f->Q.p, Q.p, (size_t)r * r, s);
         f->la.alloc(r2); copy_dd(f->la.p, la.p, r2, s);
-        f->Gram = std::move(Gp);
+        f->Gram.alloc((size_t)p * p); copy_dd(f->Gram.p, Gp.p, (size_t)p * p, s);
         NLE_CUDA(cudaStreamSynchronize(s));
     }
     return f;
@@ -748,9 +775,12 @@ static int train_host_u8(const uint8_t* lum, int rows, int cols, int row0, int r
         for (int a = 0; a < g.nR; ++a)
             for (int b = 0; b < g.nC; ++b) ys[a * g.nC + b] = lum[(size_t)g.sel_rows[a] * cols + g.sel_cols[b]];
         const size_t nloc = (size_t)(row1 - row0) * cols;
+        Trace tr(nullptr);
         DevBuf<uint8_t> d(nloc);
         d.upload(lum + (size_t)row0 * cols, nloc, nullptr);
+        tr("host: upload slab");
         auto f = train_core(d.p, rows, cols, row0, row1, ys.data(), nRS, nCS, hx, hy, T, nEig, ar, user);
+        tr("host: train_core total");
         *out = f.release();
     });
 }
@@ -858,12 +888,16 @@ int nle_b200_enhance_luminance_u8(const nle_b200_filter* f, const uint8_t* lum, 
         if (m < 1) throw InvalidArg{"at least one weight is required"};
         auto* ff = const_cast<nle_b200_filter*>(f);
         const size_t n = (size_t)f->nloc;
+        Trace tr(f->stream);
         if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
         ff->io8_in.upload(lum, n, f->stream);
+        tr("host enhance: upload");
         auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);
         apply_core(f, ff->io8_in.p, nullptr, fS.data(), nullptr, ff->io8_out.p);
+        tr("host enhance: apply");
         ff->io8_out.download(out, n, f->stream);
         NLE_CUDA(cudaStreamSynchronize(f->stream));
+        tr("host enhance: download");
     });
 }
 
@@ -911,7 +945,9 @@ int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t 
     });
 }
 
-void nle_b200_free(nle_b200_filter* f) { delete f; }
+void nle_b200_free(nle_b200_filter* f) {
+    Trace tr(nullptr);
+    struct AtExit { Trace& t; ~AtExit() { t("free"); } } at_exit{tr}; delete f; }
 
 double nle_b200_fp64_fma_peak_tflops(void) {
     double out = 0.0;

@@ -77,6 +77,40 @@ struct DevBuf {
     }
 };
 
+// Bump allocator for the temporaries of ONE training call (thread-local, reset at the start of the call).
+// In steady state (same image shape) a training call performs no device allocation at all: the arena
+// is a single chunk that is simply rewound.  If a call outgrows it, extra chunks are appended and the
+// next reset() coalesces them into one chunk of the total size.
+struct Arena {
+    struct Chunk { char* p; size_t cap; };
+    std::vector<Chunk> chunks;
+    size_t cur = 0, off = 0, total_used = 0;
+    void* alloc(size_t bytes);
+    void reset();
+    void release_all();
+    ~Arena() { release_all(); }
+};
+Arena& thread_arena();
+
+// Non-owning typed view of arena memory (same surface as DevBuf where train_core needs it).
+template <typename T>
+struct TmpBuf {
+    T* p = nullptr;
+    size_t n = 0;
+    TmpBuf() = default;
+    explicit TmpBuf(size_t count) { alloc(count); }
+    void alloc(size_t count) {
+        n = count;
+        p = count ? static_cast<T*>(thread_arena().alloc(count * sizeof(T))) : nullptr;
+    }
+    void upload(const T* h, size_t count, cudaStream_t s) {
+        NLE_CUDA(cudaMemcpyAsync(p, h, count * sizeof(T), cudaMemcpyHostToDevice, s));
+    }
+    void download(T* h, size_t count, cudaStream_t s) const {
+        NLE_CUDA(cudaMemcpyAsync(h, p, count * sizeof(T), cudaMemcpyDeviceToHost, s));
+    }
+};
+
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 int sm_count();

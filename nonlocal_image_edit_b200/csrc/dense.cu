@@ -32,6 +32,48 @@ void pool_free(void* p) {
     if (p) cudaFreeAsync(p, (cudaStream_t) nullptr);
 }
 
+void* Arena::alloc(size_t bytes) {
+    bytes = (bytes + 255) & ~(size_t)255;
+    total_used += bytes;
+    while (cur < chunks.size()) {
+        if (off + bytes <= chunks[cur].cap) {
+            void* r = chunks[cur].p + off;
+            off += bytes;
+            return r;
+        }
+        ++cur;
+        off = 0;
+    }
+    size_t cap = bytes > ((size_t)64 << 20) ? bytes : ((size_t)64 << 20);
+    Chunk c{static_cast<char*>(pool_alloc(cap)), cap};
+    chunks.push_back(c);
+    cur = chunks.size() - 1;
+    off = bytes;
+    return c.p;
+}
+
+void Arena::release_all() {
+    for (auto& c : chunks) pool_free(c.p);
+    chunks.clear();
+    cur = off = 0;
+}
+
+void Arena::reset() {
+    // the previous call has synchronised its stream before returning, nothing is in flight
+    if (chunks.size() > 1) {
+        size_t want = total_used + (total_used >> 3);
+        release_all();
+        Chunk c{static_cast<char*>(pool_alloc(want)), want};
+        chunks.push_back(c);
+    }
+    cur = off = total_used = 0;
+}
+
+Arena& thread_arena() {
+    static thread_local Arena a;
+    return a;
+}
+
 int sm_count() {
     static int n = 0;
     if (!n) {
@@ -125,18 +167,44 @@ void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const do
 }
 
 // ------------------------------------------------------------------------------------------
-// y = A x : one thread per row, rows coalesced; columns split over blockIdx.y would need atomics,
-// so each thread walks all n columns (m,n <= a few thousand).  Fixed summation order.
-__global__ void dgemv_n_kernel(int m, int n, const double* __restrict__ A, int lda,
-                               const double* __restrict__ x, double* __restrict__ y) {
-    extern __shared__ double xs[];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) xs[j] = x[j];
-    __syncthreads();
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= m) return;
+// y = A x : CTA = 16 rows x 16 warps; lane pairs cover the 16 rows (128-byte row segments), the warps
+// (and the two lane halves) stride over the columns, partial sums are combined in shared memory in
+// a fixed order.  m, n <= a few thousand: the matrix is L2 resident, so this is latency bound and
+// wants many loads in flight rather than few long dot products.
+constexpr int GV_ROWS = 16, GV_WARPS = 16;
+__global__ void __launch_bounds__(GV_WARPS * 32)
+dgemv_n_kernel(int m, int n, const double* __restrict__ A, int lda,
+               const double* __restrict__ x, double* __restrict__ y) {
+    __shared__ double part[GV_WARPS * 2][GV_ROWS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane & 15, half = lane >> 4;
+    const int i = blockIdx.x * GV_ROWS + r;
+    const int slot = warp * 2 + half;          // column phase 0..31
     double acc = 0.0;
-    for (int j = 0; j < n; ++j) acc = fma(A[i + (size_t)j * lda], xs[j], acc);
-    y[i] = acc;
+    if (i < m) {
+        const double* a = A + i;
+        int j = slot;
+        for (; j + 3 * 32 < n; j += 4 * 32) {
+            const double a0 = a[(size_t)j * lda], a1 = a[(size_t)(j + 32) * lda];
+            const double a2 = a[(size_t)(j + 64) * lda], a3 = a[(size_t)(j + 96) * lda];
+            acc = fma(a0, x[j], acc);
+            acc = fma(a1, x[j + 32], acc);
+            acc = fma(a2, x[j + 64], acc);
+            acc = fma(a3, x[j + 96], acc);
+        }
+        for (; j < n; j += 32) acc = fma(a[(size_t)j * lda], x[j], acc);
+    }
+    part[slot][r] = acc;
+    __syncthreads();
+    if (threadIdx.x < GV_ROWS) {
+        const int ii = blockIdx.x * GV_ROWS + threadIdx.x;
+        if (ii < m) {
+            double s = 0.0;
+#pragma unroll
+            for (int q = 0; q < GV_WARPS * 2; ++q) s += part[q][threadIdx.x];
+            y[ii] = s;
+        }
+    }
 }
 
 // y = A^T x : one warp per column (coalesced along the column), fixed shuffle-tree order.
@@ -155,7 +223,7 @@ __global__ void dgemv_t_kernel(int m, int n, const double* __restrict__ A, int l
 
 void dgemv_n(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s) {
     if (m <= 0) return;
-    dgemv_n_kernel<<<cdiv(m, 64), 64, (size_t)n * sizeof(double), s>>>(m, n, A, lda, x, y);
+    dgemv_n_kernel<<<cdiv(m, GV_ROWS), GV_WARPS * 32, 0, s>>>(m, n, A, lda, x, y);
     NLE_LAUNCH_CHECK();
 }
 

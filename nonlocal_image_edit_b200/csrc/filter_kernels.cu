@@ -305,22 +305,36 @@ void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart,
 // SURVEY App. A.5).  FP64 SYRK whose K dimension is the pixel axis; the operand tiles
 // a_ij = c_j K(i,j) are generated in shared memory and never touch HBM.
 // CTA = 128x128 output tile (upper-triangular tile pairs only) x one contiguous range of image rows.
-constexpr int GT = 128;   // tile edge (samples)
-constexpr int GKC = 16;   // pixels per chunk
+constexpr int GT = 128;    // tile edge (samples)
+constexpr int GKC = 16;    // pixels per chunk
+constexpr int GLD = GT + 8;   // padded row: the 4 k-rows of a DMMA fragment fall into 2 disjoint bank groups
 
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe (SASS: DMMA).
+// lane = 4*g + t :  a = A[g][t],  b = B[t][g],  d0/d1 = D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void gram_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// 8 warps as 4 (M) x 2 (N): warp tile 32 x 64 = 4 x 8 DMMA tiles, 64 FP64 accumulators per lane.
+// Per 4-pixel step a warp issues 12 LDS.64 and 32 DMMA (8192 FMA); the DFMA formulation it replaces
+// needed 64 LDS and 256 DFMA for the same work and stalled on issue/shared-memory at 50 % of the pipe.
 __global__ void __launch_bounds__(256, 1)
 gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int nsplit,
             double* __restrict__ part) {
     extern __shared__ double gsm[];
-    double (*As)[GKC][GT] = reinterpret_cast<double (*)[GKC][GT]>(gsm);                      // [2][GKC][GT]
-    double (*Bs)[GKC][GT] = reinterpret_cast<double (*)[GKC][GT]>(gsm + 2 * GKC * GT);       // [2][GKC][GT]
-    double* Gs = gsm + 4 * GKC * GT;                                                         // [256]
-    double (*pc)[GKC] = reinterpret_cast<double (*)[GKC]>(Gs + 256);                         // [2][GKC]
-    int (*pcol)[GKC] = reinterpret_cast<int (*)[GKC]>(Gs + 256 + 2 * GKC);                   // [2][GKC]
-    int (*plev)[GKC] = pcol + 2;                                                             // [2][GKC]
+    double (*As)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm);                     // [2][GKC][GLD]
+    double (*Bs)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm + 2 * GKC * GLD);     // [2][GKC][GLD]
+    double* Gs = gsm + 4 * GKC * GLD;                                                         // [256]
+    double (*pc)[GKC] = reinterpret_cast<double (*)[GKC]>(Gs + 256);                          // [2][GKC]
+    int (*pcol)[GKC] = reinterpret_cast<int (*)[GKC]>(Gs + 256 + 2 * GKC);                    // [2][GKC]
+    int (*plev)[GKC] = pcol + 2;                                                              // [2][GKC]
 
     const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
     const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
     // tile pair from linear upper-triangular index
     int tp = blockIdx.x, ti = 0;
@@ -344,11 +358,11 @@ gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int ns
     const int aB = vB ? iB / nC : 0, bB = vB ? iB - aB * nC : 0;
     const int yA = vA ? (int)t.Ysel[iA] : 0, yB = vB ? (int)t.Ysel[iB] : 0;
 
-    double acc[8][8];
+    double acc[4][8][2];
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 8; ++v) acc[u][v] = 0.0;
+        for (int v = 0; v < 8; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
 
     const int chunks_per_row = (W + GKC - 1) / GKC;
     const long long nchunks = (long long)(re - rb) * chunks_per_row;
@@ -403,22 +417,24 @@ gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int ns
         for (long long ch = 0; ch < nchunks; ++ch) {
             const int buf = (int)(ch & 1);
             const bool more = ch + 1 < nchunks;
-            if (more) generate(ch + 1, buf ^ 1);          // table loads in flight during the FMA block
+            if (more) generate(ch + 1, buf ^ 1);          // table loads in flight during the DMMA block
             // meta slot `buf` (chunk ch) was last read before the previous barrier -> refill for ch+2
             if (ch + 2 < nchunks) load_meta(ch + 2, buf);
-            const double (*Ap)[GT] = As[buf];
-            const double (*Bp)[GT] = diag ? As[buf] : Bs[buf];
-#pragma unroll 4
-            for (int kk = 0; kk < GKC; ++kk) {
-                double a[8], b[8];
+            const double (*Ap)[GLD] = As[buf];
+            const double (*Bp)[GLD] = diag ? As[buf] : Bs[buf];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a[u] = Ap[kk][ty + 16 * u];
+            for (int k4 = 0; k4 < GKC / 4; ++k4) {
+                const double* ar = &Ap[k4 * 4 + tq][wm * 32 + g];
+                const double* br = &Bp[k4 * 4 + tq][wn * 64 + g];
+                double a[4], b[8];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) b[v] = Bp[kk][tx + 16 * v];
+                for (int u = 0; u < 4; ++u) a[u] = ar[u * 8];
 #pragma unroll
-                for (int u = 0; u < 8; ++u)
+                for (int v = 0; v < 8; ++v) b[v] = br[v * 8];
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+                for (int u = 0; u < 4; ++u)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
             }
             if (more) stash(buf ^ 1);                      // tiles of buf^1 were consumed at ch-1
             __syncthreads();
@@ -426,9 +442,12 @@ gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int ns
     }
     double* out = part + ((size_t)split * gridDim.x + blockIdx.x) * (GT * GT);
 #pragma unroll
-    for (int u = 0; u < 8; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 8; ++v) out[(ty + 16 * u) * GT + tx + 16 * v] = acc[u][v];
+        for (int v = 0; v < 8; ++v) {
+            const int row = wm * 32 + u * 8 + g, col = wn * 64 + v * 8 + 2 * tq;
+            *reinterpret_cast<double2*>(out + row * GT + col) = make_double2(acc[u][v][0], acc[u][v][1]);
+        }
 }
 
 __global__ void gram_reduce_kernel(const double* __restrict__ part, int p, int ntile, int ntp,
@@ -463,7 +482,7 @@ size_t gram_scratch_doubles(const AffinityTables& t) {
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
     int ntile, ntp, nsplit;
     gram_geometry(t, ntile, ntp, nsplit);
-    const size_t smem = (size_t)(4 * GKC * GT + 256 + 2 * GKC) * sizeof(double) + 4 * GKC * sizeof(int);
+    const size_t smem = (size_t)(4 * GKC * GLD + 256 + 2 * GKC) * sizeof(double) + 4 * GKC * sizeof(int);
     static bool configured = false;
     if (!configured) {
         NLE_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
