@@ -86,7 +86,7 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
-    def stop(self):
+    def stop(self, first_line=0):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -95,7 +95,7 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, smax, reasons = [], [], set()
-        for ln in self.lines:
+        for ln in self.lines[first_line:]:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 9:
                 continue
@@ -236,24 +236,35 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def timed(fn, steps, collect=None):
+    step_ms = {}
+
+    def timed(fn, steps, collect=None, tag="dev"):
         barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(steps):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+        ev[0].record()
+        for i in range(steps):
             h = fn()
             if collect is not None:
                 collect(h)
             lib.nle_b200_free(h)
-        e1.record()
+            ev[i + 1].record()
         barrier()
-        ms = e0.elapsed_time(e1)
+        ms = ev[0].elapsed_time(ev[steps])
+        step_ms[tag] = [round(ev[i].elapsed_time(ev[i + 1]), 3) for i in range(steps)]
         if world > 1:
             t = torch.tensor([ms], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             ms = float(t.item())
         return ms
 
+    # nvidia-smi takes ~1 s to start and stalls CUDA calls of this process while it initialises: start it
+    # before the warm-up and keep only the samples taken inside the timed region.
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        t_wait = time.time()
+        while not sampler.lines and time.time() - t_wait < 8.0:
+            time.sleep(0.05)
     for _ in range(max(3, args.warmup)):
         lib.nle_b200_free(step_dev())
     for _ in range(2):
@@ -271,14 +282,12 @@ def run_b200(args, rank, world, local_rank):
         lib.nle_b200_filter_info(h, C.byref(inf))
         infos.append(inf)
 
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
     lib.nle_b200_launch_count(1)
+    first_line = len(sampler.lines)
     ms_dev = timed(step_dev, args.steps, collect)
     launches = int(lib.nle_b200_launch_count(0))
-    clocks = sampler.stop() if rank == 0 else None
-    ms_host = timed(step_host, args.steps)
+    clocks = sampler.stop(first_line) if rank == 0 else None
+    ms_host = timed(step_host, args.steps, tag="e2e")
 
     if rank != 0:
         if world > 1:
@@ -331,6 +340,7 @@ def run_b200(args, rank, world, local_rank):
         "stage_ms": {"setup_tables_Ka": float(st[0]), "eig_Ka": float(st[1]), "sinkhorn_passes": float(st[2]),
                      "gram": float(st[3]), "small_algebra_2eigs": float(st[4]), "extension": float(st[5]),
                      "train_total": float(st[6]), "gram_kernel_only": float(st[7])},
+        "step_ms": step_ms,
         "filter": {"p": inf.p, "r": inf.r, "r2": inf.r2, "k": inf.k, "eig_sweeps": list(inf.eig_sweeps)},
     }
     print(json.dumps(line), flush=True)

@@ -109,6 +109,22 @@ struct nle_b200_filter {
 
 namespace nle {
 
+// The eigenvector matrix V (nloc x k doubles, 0.4 GB at the bench config) is by far the largest buffer and the
+// only long-lived one.  A freed filter parks its V here (one slot per thread) and the next training call of
+// the thread takes it back if it is large enough, so steady-state train/free cycles never go back to the
+// driver for it (a fresh 400 MB mapping costs 0.1-1 s and the general pool fragments under the small I/O
+// buffers of the host-pointer path).
+static thread_local DevBuf<double> g_v_cache;
+
+static void take_v(DevBuf<double>& V, size_t count) {
+    if (g_v_cache.p && g_v_cache.n >= count) {
+        V = std::move(g_v_cache);
+    } else {
+        g_v_cache.release();
+        V.alloc(count);
+    }
+}
+
 static void do_allreduce(nle_b200_filter* f, double* buf, size_t count) {
     if (!f->allreduce) return;
     int rc = f->allreduce(buf, count, (void*)f->stream, f->user);
@@ -217,7 +233,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     // V is the one large, long-lived buffer (nloc x k doubles, k <= nEig).  Take it from the pool BEFORE the
     // temporaries so that the block a previous filter released is reused for it instead of being carved up
     // (a fresh 400 MB mapping costs ~1 s on this driver).
-    f->V.alloc((size_t)nloc * std::min(nEig, p));
+    take_v(f->V, (size_t)nloc * std::min(nEig, p));
     // ---- tables and sample data
     TmpBuf<int> d_selrows(nR), d_selcols(nC), d_rowa(rows), d_colb(cols);
     d_selrows.upload(g.sel_rows.data(), nR, s);
@@ -287,8 +303,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         dgemv_n(p, r, U.p, p, lt.p, x_sel_out, s);         // samples: U[s,:] Lam t
         guarded_reciprocal(x_sel_out, p, kEps, s);
         if (need_rest) {
-            launch_pass_dot(tb, wvec.p, xfull.p, s);
-            launch_pass_reduce(tb, xfull.p, spart.p, svec.p, s);
+            launch_pass_fused(tb, wvec.p, xfull.p, spart.p, svec.p, s);
             do_allreduce(f.get(), svec.p, p);
         }
     };
@@ -947,7 +962,10 @@ int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t 
 
 void nle_b200_free(nle_b200_filter* f) {
     Trace tr(nullptr);
-    struct AtExit { Trace& t; ~AtExit() { t("free"); } } at_exit{tr}; delete f; }
+    struct AtExit { Trace& t; ~AtExit() { t("free"); } } at_exit{tr};
+    if (f && f->V.p && f->V.n >= g_v_cache.n) g_v_cache = std::move(f->V);
+    delete f;
+}
 
 double nle_b200_fp64_fma_peak_tflops(void) {
     double out = 0.0;

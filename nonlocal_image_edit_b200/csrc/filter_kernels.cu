@@ -265,6 +265,103 @@ pass_reduce_kernel(AffinityTables t, const double* __restrict__ x, double* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// One Sinkhorn half-iteration over the rest pixels in ONE kernel: the "dot" half (x = recip(k_j^T w))
+// followed, for the same image row, by the "reduce" half (s += K(:,j) x_j).  Same arithmetic and
+// summation order as pass_dot_kernel + pass_reduce_kernel (bit-identical results); the level list
+// is built once, x never has to be re-read from HBM, and one launch replaces two.
+__global__ void __launch_bounds__(256)
+pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ x,
+                  double* __restrict__ spart) {
+    extern __shared__ double smd[];
+    const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
+    double* wp = smd;                        // p
+    double* Gs = wp + p;                     // 256
+    double* F = Gs + 256;                    // 256 * nC   (F table, then reused as the histogram Hh)
+    double* xrow = F + (size_t)256 * nC;     // W
+    int* flags = reinterpret_cast<int*>(xrow + W);
+    int* levidx = flags + 256;
+    int* lev = levidx + 256;
+    int* wcount = lev + 256;
+    uint8_t* Ys = reinterpret_cast<uint8_t*>(wcount + 8);
+    uint8_t* Lrow = Ys + ((p + 15) / 16) * 16;
+    uint8_t* lirow = Lrow + ((W + 15) / 16) * 16;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < p; i += 256) Ys[i] = t.Ysel[i];
+    Gs[tid] = t.Gt[tid];
+    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
+        const int row = t.row0 + rl;
+        const uint8_t* Lg = t.lum + (size_t)rl * W;
+        __syncthreads();
+        for (int c = tid; c < W; c += 256) Lrow[c] = Lg[c];
+        const double* er = t.Er + (size_t)row * nR;
+        for (int i = tid; i < p; i += 256) wp[i] = er[i / nC] * w[i];
+        __syncthreads();
+        const int nlev = build_levels(Lrow, W, flags, levidx, lev, wcount);
+        // ---- dot half
+        for (int e = tid; e < nlev * nC; e += 256) {
+            int li = e / nC, b = e - li * nC;
+            int lvl = lev[li];
+            double acc = 0.0;
+            for (int a = 0; a < nR; ++a) {
+                int i = a * nC + b;
+                int d = lvl - (int)Ys[i];
+                acc = fma(wp[i], Gs[d < 0 ? -d : d], acc);
+            }
+            F[e] = acc;
+        }
+        __syncthreads();
+        const int a_row = t.rowa[row];
+        double* xo = x + (size_t)rl * W;
+        for (int c = tid; c < W; c += 256) {
+            double r = 0.0;
+            const int li = levidx[Lrow[c]];
+            if (!(a_row >= 0 && t.colb[c] >= 0)) {
+                const double* f = F + (size_t)li * nC;
+                double acc = 0.0;
+                for (int b = 0; b < nC; ++b) acc = fma(t.EcT[(size_t)b * W + c], f[b], acc);
+                r = (fabs(acc) >= kEps) ? 1.0 / acc : 0.0;
+            }
+            xo[c] = r;
+            xrow[c] = r;
+            lirow[c] = (uint8_t)li;
+        }
+        __syncthreads();
+        // ---- reduce half (F is now the histogram Hh)
+        double* Hh = F;
+        for (int e = tid; e < nlev * nC; e += 256) Hh[e] = 0.0;
+        __syncthreads();
+        for (int c0 = 0; c0 < W; c0 += 32) {
+            int c = c0 + lane;
+            int li_l = (c < W) ? (int)lirow[c] : 0;
+            bool mine = (c < W) && ((li_l & 7) == warp) && (xrow[c] != 0.0);
+            unsigned m = __ballot_sync(0xffffffffu, mine);
+            while (m) {
+                int j = __ffs(m) - 1;
+                m &= m - 1;
+                int col = c0 + j;
+                int li = __shfl_sync(0xffffffffu, li_l, j);
+                double xv = xrow[col];
+                const double* ec = t.Ec + (size_t)col * nC;
+                double* h = Hh + (size_t)li * nC;
+                for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+            }
+        }
+        __syncthreads();
+        double* so = spart + (size_t)rl * p;
+        for (int i = tid; i < p; i += 256) {
+            int a = i / nC, b = i - a * nC;
+            int yi = (int)Ys[i];
+            double acc = 0.0;
+            for (int li = 0; li < nlev; ++li) {
+                int d = lev[li] - yi;
+                acc = fma(Gs[d < 0 ? -d : d], Hh[(size_t)li * nC + b], acc);
+            }
+            so[i] = er[a] * acc;
+        }
+    }
+}
+
 // s[i] = sum over rows of spart[row][i]; two deterministic stages (row chunks, then chunks).
 __global__ void colsum_stage_kernel(const double* __restrict__ in, int nrows, int p, int rows_per,
                                     double* __restrict__ out) {
@@ -300,6 +397,30 @@ void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart,
     NLE_LAUNCH_CHECK();
 }
 
+void launch_pass_fused(const AffinityTables& t, const double* w, double* x, double* spart, double* s_out,
+                       cudaStream_t s) {
+    size_t smem = pass_smem_bytes(t, true) + (size_t)t.p * 8;
+    if (smem > 227 * 1024) {   // very wide grids: fall back to the two separate passes
+        launch_pass_dot(t, w, x, s);
+        launch_pass_reduce(t, x, spart, s_out, s);
+        return;
+    }
+    static size_t configured = 0;
+    if (smem > configured) {
+        NLE_CUDA(cudaFuncSetAttribute(pass_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    pass_fused_kernel<<<t.nrows, 256, smem, s>>>(t, w, x, spart);
+    NLE_LAUNCH_CHECK();
+    int rows_per = 32;
+    int nchunks = cdiv(t.nrows, rows_per);
+    double* stage = spart + (size_t)t.nrows * t.p;
+    colsum_stage_kernel<<<dim3(cdiv(t.p, 128), nchunks), 128, 0, s>>>(spart, t.nrows, t.p, rows_per, stage);
+    NLE_LAUNCH_CHECK();
+    colsum_stage_kernel<<<dim3(cdiv(t.p, 128), 1), 128, 0, s>>>(stage, nchunks, t.p, nchunks, s_out);
+    NLE_LAUNCH_CHECK();
+}
+
 // =============================================================================================
 // Weighted Gram  G = sum_j c_j^2 k_j k_j^T   (the "Wab Wab^T" of filter.cpp:296 in factor form,
 // SURVEY App. A.5).  FP64 SYRK whose K dimension is the pixel axis; the operand tiles
@@ -317,24 +438,29 @@ __device__ __forceinline__ void gram_dmma(double& d0, double& d1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-// 8 warps as 4 (M) x 2 (N): warp tile 32 x 64 = 4 x 8 DMMA tiles, 64 FP64 accumulators per lane.
-// Per 4-pixel step a warp issues 12 LDS.64 and 32 DMMA (8192 FMA); the DFMA formulation it replaces
-// needed 64 LDS and 256 DFMA for the same work and stalled on issue/shared-memory at 50 % of the pipe.
-__global__ void __launch_bounds__(256, 1)
+// Warp-specialised: 16 warps = 8 PRODUCER warps (two per SM sub-core) that generate the operand tiles
+// a_ij = c_j K(i,j) into double-buffered shared memory, and 8 CONSUMER warps (two per sub-core) that do
+// nothing but LDS + DMMA.  Why: the FP64 tensor unit is per sub-core and one DMMA.8x8x4 occupies it for
+// 16 cycles (ptxas pads the DMMA stream with NOPs accordingly), so a single warp can saturate it; with
+// all warps generating in lockstep the unit idled 32 % of the time (profiles/r1c_gram_kernel_full.md),
+// and with only 4 producer warps the producers' DMULs -- which queue behind the DMMAs on the same FP64
+// pipe -- made the producer as slow as the consumer (profiles/k1).  The register file is rebalanced with
+// setmaxnreg: producers 80, consumers 176 registers per thread (512 * 128 = 65536 at launch).
+// Consumers: 4 (M) x 2 (N) warps, warp tile 32 x 64 = 4 x 8 DMMA tiles, 64 FP64 accumulators per lane;
+// per 4-pixel step a warp issues 12 LDS.64 and 32 DMMA (8192 FMA).
+constexpr int GRAM_THREADS = 512;
+constexpr int GRAM_PRODUCERS = 256;
+
+__global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int nsplit,
             double* __restrict__ part) {
     extern __shared__ double gsm[];
     double (*As)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm);                     // [2][GKC][GLD]
     double (*Bs)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm + 2 * GKC * GLD);     // [2][GKC][GLD]
     double* Gs = gsm + 4 * GKC * GLD;                                                         // [256]
-    double (*pc)[GKC] = reinterpret_cast<double (*)[GKC]>(Gs + 256);                          // [2][GKC]
-    int (*pcol)[GKC] = reinterpret_cast<int (*)[GKC]>(Gs + 256 + 2 * GKC);                    // [2][GKC]
-    int (*plev)[GKC] = pcol + 2;                                                              // [2][GKC]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
-    const int g = lane >> 2, tq = lane & 3;
-    const int wm = warp & 3, wn = warp >> 2;
     const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
     // tile pair from linear upper-triangular index
     int tp = blockIdx.x, ti = 0;
@@ -348,96 +474,140 @@ gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int ns
     const int split = blockIdx.y;
     const int rb = (int)(((long long)t.nrows * split) / nsplit);
     const int re = (int)(((long long)t.nrows * (split + 1)) / nsplit);
+    const int chunks_per_row = (W + GKC - 1) / GKC;
+    const long long nchunks = (long long)(re - rb) * chunks_per_row;
 
-    Gs[tid] = t.Gt[tid];
-    // generation role: sample sIdx of each tile, pixel half gh (8 pixels of the 16-pixel chunk)
-    const int sIdx = tid & 127, gh = tid >> 7;
-    const int iA = ti * GT + sIdx, iB = tj * GT + sIdx;
-    const bool vA = iA < p, vB = iB < p;
-    const int aA = vA ? iA / nC : 0, bA = vA ? iA - aA * nC : 0;
-    const int aB = vB ? iB / nC : 0, bB = vB ? iB - aB * nC : 0;
-    const int yA = vA ? (int)t.Ysel[iA] : 0, yB = vB ? (int)t.Ysel[iB] : 0;
+    if (tid < 256) Gs[tid] = t.Gt[tid];
+    __syncthreads();
 
+    if (tid < GRAM_PRODUCERS) {
+        // ------------------------------------------------------------------ producers
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
+        // Per chunk: (1) stage  EcC[kk][b] = c_j * Ec[col_kk][b]  (16 x nC contiguous doubles of the Ec table,
+        // prefetched into registers one chunk ahead so no L2 latency sits on the critical path) and the 16
+        // pixel levels; (2) each thread emits 8 (+8) tile entries: sample sIdx, pixels 8*ph .. 8*ph+7:
+        // a = Er[row][a_i] * EcC[kk][b_i] * Gt[|l_kk - Y_i|]  -- 2 LDS + 2 DMUL + 1 STS per entry.
+        double* EcC = Gs + 256;                                     // [2][GKC * nC]
+        int* levs = reinterpret_cast<int*>(EcC + 2 * GKC * nC);     // [2][GKC]
+        const int sIdx = tid & 127, ph = tid >> 7;
+        const int iA = ti * GT + sIdx, iB = tj * GT + sIdx;
+        const bool vA = iA < p, vB = iB < p;
+        const int aA = vA ? iA / nC : 0, bA = vA ? iA - aA * nC : 0;
+        const int aB = vB ? iB / nC : 0, bB = vB ? iB - aB * nC : 0;
+        const int yA = vA ? (int)t.Ysel[iA] : 0, yB = vB ? (int)t.Ysel[iB] : 0;
+        double erA = 0.0, erB = 0.0;
+        int cur_row = -1;
+        constexpr int MAXE = 4;                  // prefetched elements per thread (covers nC <= 64)
+        const int nstage = GKC * nC;
+        int ekk[MAXE];                           // pixel (0..15) of staged element q -- chunk invariant
+#pragma unroll
+        for (int q = 0; q < MAXE; ++q) ekk[q] = (tid + GRAM_PRODUCERS * q) / nC;
+        double pe[MAXE], pcj[MAXE];
+        int plev = 0;
+        // chunk cursor without 64-bit divisions: (prow, pcol0) is the chunk being prefetched
+        int prow = rb, pcol0 = 0;
+        auto prefetch = [&](bool live) {
+#pragma unroll
+            for (int q = 0; q < MAXE; ++q) {
+                const int e = tid + GRAM_PRODUCERS * q;
+                pe[q] = 0.0; pcj[q] = 0.0;
+                if (live && e < nstage && pcol0 + ekk[q] < W) {
+                    pe[q] = t.Ec[(size_t)pcol0 * nC + e];
+                    pcj[q] = cvec[(size_t)prow * W + pcol0 + ekk[q]];
+                }
+            }
+            plev = 0;
+            if (live && tid < GKC && pcol0 + tid < W) plev = (int)t.lum[(size_t)prow * W + pcol0 + tid];
+        };
+        prefetch(nchunks > 0);
+        int crow = rb, ccol0 = 0;                // chunk being emitted
+        for (long long ch = 0; ch < nchunks; ++ch) {
+            const int buf = (int)(ch & 1);
+            double* ecc = EcC + (size_t)buf * nstage;
+            const int* lvs = levs + buf * GKC + ph * 8;
+#pragma unroll
+            for (int q = 0; q < MAXE; ++q) {
+                const int e = tid + GRAM_PRODUCERS * q;
+                if (e < nstage) ecc[e] = pe[q] * pcj[q];
+            }
+            if (tid < GKC) levs[buf * GKC + tid] = plev;
+            if (nstage > GRAM_PRODUCERS * MAXE) {
+                // very wide sample grids (nC > 64): the remainder is staged without the register prefetch
+                for (int e = tid + GRAM_PRODUCERS * MAXE; e < nstage; e += GRAM_PRODUCERS) {
+                    const int col = ccol0 + e / nC;
+                    ecc[e] = (col < W) ? t.Ec[(size_t)ccol0 * nC + e] * cvec[(size_t)crow * W + col] : 0.0;
+                }
+            }
+            pcol0 += GKC;
+            if (pcol0 >= W) { pcol0 = 0; ++prow; }
+            prefetch(ch + 1 < nchunks);
+            asm volatile("bar.sync 1, 256;" ::: "memory");     // producers only: staging visible
+            if (crow != cur_row) {
+                cur_row = crow;
+                const double* er = t.Er + (size_t)(t.row0 + crow) * nR;
+                erA = vA ? er[aA] : 0.0;
+                erB = vB ? er[aB] : 0.0;
+            }
+            // all shared-memory reads first, then the stores: the compiler cannot reorder them itself because
+            // tiles and tables live in the same dynamic shared array
+            const double* eccp = ecc + (size_t)(ph * 8) * nC;
+            double va[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int dA = lvs[q] - yA;
+                va[q] = eccp[q * nC + bA] * Gs[dA < 0 ? -dA : dA];
+            }
+            if (!diag) {
+                double vb[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const int dB = lvs[q] - yB;
+                    vb[q] = eccp[q * nC + bB] * Gs[dB < 0 ? -dB : dB];
+                }
+#pragma unroll
+                for (int q = 0; q < 8; ++q) Bs[buf][ph * 8 + q][sIdx] = erB * vb[q];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) As[buf][ph * 8 + q][sIdx] = erA * va[q];
+            ccol0 += GKC;
+            if (ccol0 >= W) { ccol0 = 0; ++crow; }
+            __syncthreads();   // barrier #ch: chunk ch is in shared memory, consumers are done with chunk ch-1
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    const int cw = warp - GRAM_PRODUCERS / 32;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = cw & 3, wn = cw >> 2;
     double acc[4][8][2];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
         for (int v = 0; v < 8; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
-
-    const int chunks_per_row = (W + GKC - 1) / GKC;
-    const long long nchunks = (long long)(re - rb) * chunks_per_row;
-    double regA[8], regB[8];
-    double erA = 0.0, erB = 0.0;
-    int cur_row = -1;
-
-    auto load_meta = [&](long long ch, int buf) {
-        if (tid < GKC) {
-            int rl = rb + (int)(ch / chunks_per_row);
-            int c = (int)(ch % chunks_per_row) * GKC + tid;
-            bool ok = c < W;
-            int cc = ok ? c : W - 1;
-            pcol[buf][tid] = cc;
-            plev[buf][tid] = (int)t.lum[(size_t)rl * W + cc];
-            pc[buf][tid] = ok ? cvec[(size_t)rl * W + cc] : 0.0;
-        }
-    };
-    auto generate = [&](long long ch, int buf) {
-        int rl = rb + (int)(ch / chunks_per_row);
-        if (rl != cur_row) {
-            cur_row = rl;
-            const double* er = t.Er + (size_t)(t.row0 + rl) * nR;
-            erA = vA ? er[aA] : 0.0;
-            erB = vB ? er[aB] : 0.0;
-        }
+    // A warp whose 32 x 64 sub-tile lies entirely in the padding (p is not a multiple of 128) or strictly
+    // below the diagonal of a diagonal tile (only i <= j is ever read back) issues no DMMA.
+    const bool wactive = (ti * GT + wm * 32 < p) && (tj * GT + wn * 64 < p) && !(diag && wm * 32 >= wn * 64 + 64);
+    for (long long ch = 0; ch < nchunks; ++ch) {
+        const int buf = (int)(ch & 1);
+        __syncthreads();       // barrier #ch
+        if (!wactive) continue;
+        const double (*Ap)[GLD] = As[buf];
+        const double (*Bp)[GLD] = diag ? As[buf] : Bs[buf];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            int kk = gh * 8 + q;
-            int col = pcol[buf][kk], lv = plev[buf][kk];
-            double cj = pc[buf][kk];
-            int dA = lv - yA, dB = lv - yB;
-            regA[q] = erA * cj * t.Ec[(size_t)col * nC + bA] * Gs[dA < 0 ? -dA : dA];
-            if (!diag) regB[q] = erB * cj * t.Ec[(size_t)col * nC + bB] * Gs[dB < 0 ? -dB : dB];
-        }
-    };
-    auto stash = [&](int buf) {
+        for (int k4 = 0; k4 < GKC / 4; ++k4) {
+            const double* ar = &Ap[k4 * 4 + tq][wm * 32 + g];
+            const double* br = &Bp[k4 * 4 + tq][wn * 64 + g];
+            double a[4], b[8];
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-            As[buf][gh * 8 + q][sIdx] = regA[q];
-            if (!diag) Bs[buf][gh * 8 + q][sIdx] = regB[q];
-        }
-    };
-
-    if (nchunks > 0) {
-        load_meta(0, 0);
-        __syncthreads();
-        generate(0, 0);
-        stash(0);
-        if (nchunks > 1) load_meta(1, 1);
-        __syncthreads();
-        for (long long ch = 0; ch < nchunks; ++ch) {
-            const int buf = (int)(ch & 1);
-            const bool more = ch + 1 < nchunks;
-            if (more) generate(ch + 1, buf ^ 1);          // table loads in flight during the DMMA block
-            // meta slot `buf` (chunk ch) was last read before the previous barrier -> refill for ch+2
-            if (ch + 2 < nchunks) load_meta(ch + 2, buf);
-            const double (*Ap)[GLD] = As[buf];
-            const double (*Bp)[GLD] = diag ? As[buf] : Bs[buf];
+            for (int u = 0; u < 4; ++u) a[u] = ar[u * 8];
 #pragma unroll
-            for (int k4 = 0; k4 < GKC / 4; ++k4) {
-                const double* ar = &Ap[k4 * 4 + tq][wm * 32 + g];
-                const double* br = &Bp[k4 * 4 + tq][wn * 64 + g];
-                double a[4], b[8];
+            for (int v = 0; v < 8; ++v) b[v] = br[v * 8];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) a[u] = ar[u * 8];
+            for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 8; ++v) b[v] = br[v * 8];
-#pragma unroll
-                for (int u = 0; u < 4; ++u)
-#pragma unroll
-                    for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
-            }
-            if (more) stash(buf ^ 1);                      // tiles of buf^1 were consumed at ch-1
-            __syncthreads();
+                for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
     }
     double* out = part + ((size_t)split * gridDim.x + blockIdx.x) * (GT * GT);
@@ -456,7 +626,8 @@ __global__ void gram_reduce_kernel(const double* __restrict__ part, int p, int n
     if (i >= p) return;
     int ti = i / GT, tj = j / GT;
     int r = i % GT, c = j % GT;
-    if (ti > tj) { int tmp = ti; ti = tj; tj = tmp; tmp = r; r = c; c = tmp; }
+    // only the upper triangle (tile pairs ti <= tj, and r <= c inside diagonal tiles) is computed
+    if (ti > tj || (ti == tj && r > c)) { int tmp = ti; ti = tj; tj = tmp; tmp = r; r = c; c = tmp; }
     // linear index of (ti,tj), ti<=tj : sum_{q<ti} (ntile-q) + (tj-ti)
     int tp = ti * ntile - (ti * (ti - 1)) / 2 + (tj - ti);
     double acc = 0.0;
@@ -482,13 +653,13 @@ size_t gram_scratch_doubles(const AffinityTables& t) {
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
     int ntile, ntp, nsplit;
     gram_geometry(t, ntile, ntp, nsplit);
-    const size_t smem = (size_t)(4 * GKC * GLD + 256 + 2 * GKC) * sizeof(double) + 4 * GKC * sizeof(int);
-    static bool configured = false;
-    if (!configured) {
+    const size_t smem = (size_t)(4 * GKC * GLD + 256 + 2 * GKC * t.nC) * sizeof(double) + 2 * GKC * sizeof(int);
+    static size_t configured = 0;
+    if (smem > configured) {
         NLE_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        configured = true;
+        configured = smem;
     }
-    gram_kernel<<<dim3(ntp, nsplit), 256, smem, s>>>(t, c, ntile, nsplit, scratch);
+    gram_kernel<<<dim3(ntp, nsplit), GRAM_THREADS, smem, s>>>(t, c, ntile, nsplit, scratch);
     NLE_LAUNCH_CHECK();
     gram_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(scratch, t.p, ntile, ntp, nsplit, G);
     NLE_LAUNCH_CHECK();

@@ -37,6 +37,10 @@ void launch_pass_dot(const AffinityTables& t, const double* w, double* x, cudaSt
 void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart, double* s_out,
                         cudaStream_t s);
 
+// Both halves in one kernel (bit-identical to launch_pass_dot followed by launch_pass_reduce).
+void launch_pass_fused(const AffinityTables& t, const double* w, double* x, double* spart, double* s_out,
+                       cudaStream_t s);
+
 // Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab.
 size_t gram_scratch_doubles(const AffinityTables& t);
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G,
