@@ -438,26 +438,46 @@ __device__ __forceinline__ void gram_dmma(double& d0, double& d1, double a, doub
                  : "d"(a), "d"(b));
 }
 
-// Warp-specialised: 16 warps = 8 PRODUCER warps (two per SM sub-core) that generate the operand tiles
-// a_ij = c_j K(i,j) into double-buffered shared memory, and 8 CONSUMER warps (two per sub-core) that do
-// nothing but LDS + DMMA.  Why: the FP64 tensor unit is per sub-core and one DMMA.8x8x4 occupies it for
-// 16 cycles (ptxas pads the DMMA stream with NOPs accordingly), so a single warp can saturate it; with
-// all warps generating in lockstep the unit idled 32 % of the time (profiles/r1c_gram_kernel_full.md),
-// and with only 4 producer warps the producers' DMULs -- which queue behind the DMMAs on the same FP64
-// pipe -- made the producer as slow as the consumer (profiles/k1).  The register file is rebalanced with
-// setmaxnreg: producers 80, consumers 176 registers per thread (512 * 128 = 65536 at launch).
+// CE[j][b] = c_j * Ec[col_j][b] for every slab pixel j (nloc x nC): takes the per-pixel Sinkhorn weight out of
+// the tile producers' critical burst (see gram_kernel).
+__global__ void gram_ce_kernel(AffinityTables t, const double* __restrict__ cvec, double* __restrict__ CE) {
+    const long long total = (long long)t.nrows * t.cols * t.nC;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+        const long long j = e / t.nC;
+        const int b = (int)(e - j * t.nC);
+        const int col = (int)(j % t.cols);
+        CE[e] = cvec[j] * t.Ec[(size_t)col * t.nC + b];
+    }
+}
+
+// Warp-specialised: 16 warps = 8 PRODUCER warps (two per SM sub-core) that generate the operand tile
+// a_ij = c_j K(i,j) in shared memory, and 8 CONSUMER warps (two per sub-core) that do nothing but
+// LDS + DMMA.  Findings that shaped it (ncu captures summarised under profiles/):
+//   * the FP64 tensor unit is per sub-core and one DMMA.8x8x4 occupies it for 16 cycles (ptxas pads the
+//     DMMA stream with NOPs accordingly), so the two consumer warps of a sub-core can saturate it;
+//   * an FP64 multiply issued while the DMMA stream is running queues behind it for 100-170 cycles
+//     ("math pipe throttle" was 46-61 % of the producers' time in every variant that multiplied
+//     concurrently, even with a single multiply per entry), which made the producers the bottleneck.
+// So the producers do all their loads (CE, levels, table look-ups) while the consumers run the DMMAs of
+// chunk c, keep the raw factors in registers, and multiply + store chunk c+1 in a short burst between
+// the consumers' "done" (barrier 2) and "tile full" (barrier 1) -- the only time the FP64 pipe is shared.
+// Entry:  a = (CE[j][b_i] * Gt[|l_j - Y_i|]) * Er[row][a_i]  with CE[j][b] = c_j * Ec[col_j][b], a global table
+// written by gram_ce_kernel and streamed through L2.  (A per-row shared-memory table Er*Gt that brings the
+// burst down to one multiply per entry was measured too: same speed, so the simpler form is kept.)
+// Register file: setmaxnreg gives the producers 88 and the consumers 168 registers per thread
+// (512 * 128 = 65536 at launch).
 // Consumers: 4 (M) x 2 (N) warps, warp tile 32 x 64 = 4 x 8 DMMA tiles, 64 FP64 accumulators per lane;
 // per 4-pixel step a warp issues 12 LDS.64 and 32 DMMA (8192 FMA).
 constexpr int GRAM_THREADS = 512;
 constexpr int GRAM_PRODUCERS = 256;
 
 __global__ void __launch_bounds__(GRAM_THREADS, 1)
-gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int nsplit,
+gram_kernel(AffinityTables t, const double* __restrict__ CE, int ntile, int nsplit,
             double* __restrict__ part) {
     extern __shared__ double gsm[];
-    double (*As)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm);                     // [2][GKC][GLD]
-    double (*Bs)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm + 2 * GKC * GLD);     // [2][GKC][GLD]
-    double* Gs = gsm + 4 * GKC * GLD;                                                         // [256]
+    double (*As)[GLD] = reinterpret_cast<double (*)[GLD]>(gsm);                 // [GKC][GLD]
+    double (*Bs)[GLD] = reinterpret_cast<double (*)[GLD]>(gsm + GKC * GLD);     // [GKC][GLD]
+    double* Gs = gsm + 2 * GKC * GLD;                                           // [256]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -482,102 +502,85 @@ gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int ns
 
     if (tid < GRAM_PRODUCERS) {
         // ------------------------------------------------------------------ producers
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 80;");
-        // Per chunk: (1) stage  EcC[kk][b] = c_j * Ec[col_kk][b]  (16 x nC contiguous doubles of the Ec table,
-        // prefetched into registers one chunk ahead so no L2 latency sits on the critical path) and the 16
-        // pixel levels; (2) each thread emits 8 (+8) tile entries: sample sIdx, pixels 8*ph .. 8*ph+7:
-        // a = Er[row][a_i] * EcC[kk][b_i] * Gt[|l_kk - Y_i|]  -- 2 LDS + 2 DMUL + 1 STS per entry.
-        double* EcC = Gs + 256;                                     // [2][GKC * nC]
-        int* levs = reinterpret_cast<int*>(EcC + 2 * GKC * nC);     // [2][GKC]
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        // thread = (sample sIdx of each tile, pixel half ph): 8 (+8) tile entries per chunk
         const int sIdx = tid & 127, ph = tid >> 7;
         const int iA = ti * GT + sIdx, iB = tj * GT + sIdx;
-        const bool vA = iA < p, vB = iB < p;
+        const bool vA = iA < p, vB = (iB < p) && !diag;
         const int aA = vA ? iA / nC : 0, bA = vA ? iA - aA * nC : 0;
         const int aB = vB ? iB / nC : 0, bB = vB ? iB - aB * nC : 0;
         const int yA = vA ? (int)t.Ysel[iA] : 0, yB = vB ? (int)t.Ysel[iB] : 0;
+        const bool lum_vec = (W % 8 == 0) && ((reinterpret_cast<size_t>(t.lum) & 7) == 0);
         double erA = 0.0, erB = 0.0;
-        int cur_row = -1;
-        constexpr int MAXE = 4;                  // prefetched elements per thread (covers nC <= 64)
-        const int nstage = GKC * nC;
-        int ekk[MAXE];                           // pixel (0..15) of staged element q -- chunk invariant
+        double ceA[8], ceB[8], gA[8], gB[8];
+        int prow = rb, pcol0 = 0;      // chunk cursor (no 64-bit divisions in the loop)
+        // all loads of one chunk: CE values, pixel levels -> Gt look-ups, Er on a new row
+        auto prep = [&]() {
+            const size_t j0 = (size_t)prow * W + pcol0 + ph * 8;
+            const double* ce = CE + j0 * nC;
+            const uint8_t* lv = t.lum + j0;
+            const int nok = min(8, W - (pcol0 + ph * 8));      // valid pixels among this thread's 8 (<= 0: none)
+            // ---- issue every global load first (one 64-bit load for the 8 levels when the row allows it)
+            unsigned long long lw = 0ull;
+            if (lum_vec) {
+                if (nok > 0) lw = *reinterpret_cast<const unsigned long long*>(lv);
+            } else {
 #pragma unroll
-        for (int q = 0; q < MAXE; ++q) ekk[q] = (tid + GRAM_PRODUCERS * q) / nC;
-        double pe[MAXE], pcj[MAXE];
-        int plev = 0;
-        // chunk cursor without 64-bit divisions: (prow, pcol0) is the chunk being prefetched
-        int prow = rb, pcol0 = 0;
-        auto prefetch = [&](bool live) {
-#pragma unroll
-            for (int q = 0; q < MAXE; ++q) {
-                const int e = tid + GRAM_PRODUCERS * q;
-                pe[q] = 0.0; pcj[q] = 0.0;
-                if (live && e < nstage && pcol0 + ekk[q] < W) {
-                    pe[q] = t.Ec[(size_t)pcol0 * nC + e];
-                    pcj[q] = cvec[(size_t)prow * W + pcol0 + ekk[q]];
-                }
+                for (int q = 0; q < 8; ++q)
+                    if (q < nok) lw |= (unsigned long long)lv[q] << (8 * q);
             }
-            plev = 0;
-            if (live && tid < GKC && pcol0 + tid < W) plev = (int)t.lum[(size_t)prow * W + pcol0 + tid];
-        };
-        prefetch(nchunks > 0);
-        int crow = rb, ccol0 = 0;                // chunk being emitted
-        for (long long ch = 0; ch < nchunks; ++ch) {
-            const int buf = (int)(ch & 1);
-            double* ecc = EcC + (size_t)buf * nstage;
-            const int* lvs = levs + buf * GKC + ph * 8;
-#pragma unroll
-            for (int q = 0; q < MAXE; ++q) {
-                const int e = tid + GRAM_PRODUCERS * q;
-                if (e < nstage) ecc[e] = pe[q] * pcj[q];
+            if (pcol0 == 0) {
+                const double* er = t.Er + (size_t)(t.row0 + prow) * nR;
+                erA = vA ? er[aA] : 0.0;
+                erB = vB ? er[aB] : 0.0;
             }
-            if (tid < GKC) levs[buf * GKC + tid] = plev;
-            if (nstage > GRAM_PRODUCERS * MAXE) {
-                // very wide sample grids (nC > 64): the remainder is staged without the register prefetch
-                for (int e = tid + GRAM_PRODUCERS * MAXE; e < nstage; e += GRAM_PRODUCERS) {
-                    const int col = ccol0 + e / nC;
-                    ecc[e] = (col < W) ? t.Ec[(size_t)ccol0 * nC + e] * cvec[(size_t)crow * W + col] : 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                ceA[q] = (q < nok && vA) ? ce[(size_t)q * nC + bA] : 0.0;
+                if (!diag) ceB[q] = (q < nok && vB) ? ce[(size_t)q * nC + bB] : 0.0;
+            }
+            // ---- then the Gt look-ups (shared memory)
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int l = (int)((lw >> (8 * q)) & 0xffull);
+                const int dA = l - yA;
+                gA[q] = Gs[dA < 0 ? -dA : dA];
+                if (!diag) {
+                    const int dB = l - yB;
+                    gB[q] = Gs[dB < 0 ? -dB : dB];
                 }
             }
             pcol0 += GKC;
             if (pcol0 >= W) { pcol0 = 0; ++prow; }
-            prefetch(ch + 1 < nchunks);
-            asm volatile("bar.sync 1, 256;" ::: "memory");     // producers only: staging visible
-            if (crow != cur_row) {
-                cur_row = crow;
-                const double* er = t.Er + (size_t)(t.row0 + crow) * nR;
-                erA = vA ? er[aA] : 0.0;
-                erB = vB ? er[aB] : 0.0;
-            }
-            // all shared-memory reads first, then the stores: the compiler cannot reorder them itself because
-            // tiles and tables live in the same dynamic shared array
-            const double* eccp = ecc + (size_t)(ph * 8) * nC;
-            double va[8];
+        };
+        // the only FP64 arithmetic of the producers: 2 multiplies per entry, issued while the DMMA stream is idle
+        auto burst = [&]() {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-                const int dA = lvs[q] - yA;
-                va[q] = eccp[q * nC + bA] * Gs[dA < 0 ? -dA : dA];
-            }
+            for (int q = 0; q < 8; ++q) As[ph * 8 + q][sIdx] = (ceA[q] * gA[q]) * erA;
             if (!diag) {
-                double vb[8];
 #pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const int dB = lvs[q] - yB;
-                    vb[q] = eccp[q * nC + bB] * Gs[dB < 0 ? -dB : dB];
-                }
-#pragma unroll
-                for (int q = 0; q < 8; ++q) Bs[buf][ph * 8 + q][sIdx] = erB * vb[q];
+                for (int q = 0; q < 8; ++q) Bs[ph * 8 + q][sIdx] = (ceB[q] * gB[q]) * erB;
             }
-#pragma unroll
-            for (int q = 0; q < 8; ++q) As[buf][ph * 8 + q][sIdx] = erA * va[q];
-            ccol0 += GKC;
-            if (ccol0 >= W) { ccol0 = 0; ++crow; }
-            __syncthreads();   // barrier #ch: chunk ch is in shared memory, consumers are done with chunk ch-1
+        };
+        if (nchunks > 0) {
+            prep();
+            burst();
+            asm volatile("bar.arrive 1, 512;" ::: "memory");          // tile 0 full
+        }
+        for (long long ch = 0; ch < nchunks; ++ch) {
+            const bool more = ch + 1 < nchunks;
+            if (more) prep();                                          // overlaps the consumers' DMMAs of chunk ch
+            asm volatile("bar.sync 2, 512;" ::: "memory");             // consumers have issued every DMMA of chunk ch
+            if (more) {
+                burst();
+                asm volatile("bar.arrive 1, 512;" ::: "memory");      // tile ch+1 full
+            }
         }
         return;
     }
 
     // ---------------------------------------------------------------------- consumers
-    asm volatile("setmaxnreg.inc.sync.aligned.u32 176;");
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
     const int cw = warp - GRAM_PRODUCERS / 32;
     const int g = lane >> 2, tq = lane & 3;
     const int wm = cw & 3, wn = cw >> 2;
@@ -589,26 +592,26 @@ gram_kernel(AffinityTables t, const double* __restrict__ cvec, int ntile, int ns
     // A warp whose 32 x 64 sub-tile lies entirely in the padding (p is not a multiple of 128) or strictly
     // below the diagonal of a diagonal tile (only i <= j is ever read back) issues no DMMA.
     const bool wactive = (ti * GT + wm * 32 < p) && (tj * GT + wn * 64 < p) && !(diag && wm * 32 >= wn * 64 + 64);
+    const double (*Bp)[GLD] = diag ? As : Bs;
     for (long long ch = 0; ch < nchunks; ++ch) {
-        const int buf = (int)(ch & 1);
-        __syncthreads();       // barrier #ch
-        if (!wactive) continue;
-        const double (*Ap)[GLD] = As[buf];
-        const double (*Bp)[GLD] = diag ? As[buf] : Bs[buf];
+        asm volatile("bar.sync 1, 512;" ::: "memory");                 // tile ch full
+        if (wactive) {
 #pragma unroll
-        for (int k4 = 0; k4 < GKC / 4; ++k4) {
-            const double* ar = &Ap[k4 * 4 + tq][wm * 32 + g];
-            const double* br = &Bp[k4 * 4 + tq][wn * 64 + g];
-            double a[4], b[8];
+            for (int k4 = 0; k4 < GKC / 4; ++k4) {
+                const double* ar = &As[k4 * 4 + tq][wm * 32 + g];
+                const double* br = &Bp[k4 * 4 + tq][wn * 64 + g];
+                double a[4], b[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = ar[u * 8];
+                for (int u = 0; u < 4; ++u) a[u] = ar[u * 8];
 #pragma unroll
-            for (int v = 0; v < 8; ++v) b[v] = br[v * 8];
+                for (int v = 0; v < 8; ++v) b[v] = br[v * 8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+                for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+                    for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+            }
         }
+        asm volatile("bar.arrive 2, 512;" ::: "memory");               // done reading tile ch, DMMAs issued
     }
     double* out = part + ((size_t)split * gridDim.x + blockIdx.x) * (GT * GT);
 #pragma unroll
@@ -647,19 +650,22 @@ static void gram_geometry(const AffinityTables& t, int& ntile, int& ntp, int& ns
 size_t gram_scratch_doubles(const AffinityTables& t) {
     int ntile, ntp, nsplit;
     gram_geometry(t, ntile, ntp, nsplit);
-    return (size_t)ntp * nsplit * GT * GT;
+    return (size_t)ntp * nsplit * GT * GT + (size_t)t.nrows * t.cols * t.nC;   // partial tiles + CE table
 }
 
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
     int ntile, ntp, nsplit;
     gram_geometry(t, ntile, ntp, nsplit);
-    const size_t smem = (size_t)(4 * GKC * GLD + 256 + 2 * GKC * t.nC) * sizeof(double) + 2 * GKC * sizeof(int);
+    double* CE = scratch + (size_t)ntp * nsplit * GT * GT;
+    gram_ce_kernel<<<sm_count() * 8, 256, 0, s>>>(t, c, CE);
+    NLE_LAUNCH_CHECK();
+    const size_t smem = (size_t)(2 * GKC * GLD + 256) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
         NLE_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         configured = smem;
     }
-    gram_kernel<<<dim3(ntp, nsplit), GRAM_THREADS, smem, s>>>(t, c, ntile, nsplit, scratch);
+    gram_kernel<<<dim3(ntp, nsplit), GRAM_THREADS, smem, s>>>(t, CE, ntile, nsplit, scratch);
     NLE_LAUNCH_CHECK();
     gram_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(scratch, t.p, ntile, ntp, nsplit, G);
     NLE_LAUNCH_CHECK();
