@@ -276,7 +276,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     tr("setup tables Ka");
     Timer t_eig1(s);
     static thread_local EigWorkspace ws;   // grow-only, reused by every training call of this thread
-    f->eig_sweeps[0] = sym_eig(Ka.p, p, p, kEps, /*psd_hint=*/true, U.p, lam.p, d_cnt.p, ws, s);
+    f->eig_sweeps[0] = sym_eig(Ka.p, p, p, kEps, /*psd_hint=*/true, U.p, lam.p, d_cnt.p, ws, s, /*vec_limit=*/p);
     const int r = read_int(d_cnt.p, s);
     f->times_ms[1] = t_eig1.stop();
     tr("eig Ka");
@@ -365,7 +365,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     tr("small: Wa, WW");
     // eig(Wa) -> Wa^-1/2 (pseudo-inverse root on lambda >= 1e-10, filter.cpp:287-292)
     TmpBuf<double> Ua((size_t)r * r), la(r), irl(r), UaS((size_t)r * r), irw((size_t)r * r);
-    f->eig_sweeps[1] = sym_eig(Wa.p, r, r, kEps, /*psd_hint=*/false, Ua.p, la.p, d_cnt.p, ws, s);
+    f->eig_sweeps[1] = sym_eig(Wa.p, r, r, kEps, /*psd_hint=*/false, Ua.p, la.p, d_cnt.p, ws, s, /*vec_limit=*/r);
     const int r2 = read_int(d_cnt.p, s);
     tr("small: eig Wa");
     f->r2 = r2;
@@ -384,7 +384,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     scale_rows_cols(r2, r2, Mq.p, r2, irl.p, irl.p, Mq.p, r2, s);
     add_diag(Mq.p, r2, la.p, s);
     tr("small: invroot, Q");
-    f->eig_sweeps[2] = sym_eig(Mq.p, r2, r2, kEps, /*psd_hint=*/false, Zq.p, Sq.p, d_cnt.p, ws, s);
+    f->eig_sweeps[2] = sym_eig(Mq.p, r2, r2, kEps, /*psd_hint=*/false, Zq.p, Sq.p, d_cnt.p, ws, s, /*vec_limit=*/nEig);
     const int nq = read_int(d_cnt.p, s);
     tr("small: eig Q");
     TmpBuf<double> Q;

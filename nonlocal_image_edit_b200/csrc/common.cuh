@@ -152,8 +152,11 @@ struct EigWorkspace {
 // d_r (device int) receives the length of the prefix with D >= eps.  `psd_hint` selects a small
 // spectral shift (inputs known to be positive semi-definite up to rounding).
 // Returns the number of Jacobi sweeps used (0 when the direct solver was used).
-bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double** lam_out, double** vec_out);
+bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, int* count, EigWorkspace& ws,
+                     cudaStream_t s, double** lam_out, double** vec_out);
+// vec_limit >= 0: the caller only uses the eigenvectors of the first min(vec_limit, *d_r) eigenvalues (the
+// remaining columns of U are unspecified); < 0: all n columns are valid.
 int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
-            int* d_r, EigWorkspace& ws, cudaStream_t s);
+            int* d_r, EigWorkspace& ws, cudaStream_t s, int vec_limit = -1);
 
 }  // namespace nle

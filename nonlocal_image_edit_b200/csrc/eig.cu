@@ -453,7 +453,7 @@ static bool use_jacobi() {
 // Direct path: tridiagonalisation + divide & conquer (eig_dc.cu), then the same descending sort and
 // ">= eps prefix" cut as the Jacobi path.
 static bool sym_eig_direct(const double* M, int ldm, int n, double eps, double* U, double* D, int* d_r,
-                           EigWorkspace& ws, cudaStream_t s) {
+                           EigWorkspace& ws, cudaStream_t s, int vec_limit) {
     if ((size_t)ws.As.n < (size_t)n * n) ws.As.alloc((size_t)n * n);
     if ((size_t)ws.lam_unsorted.n < (size_t)n + 8) ws.lam_unsorted.alloc(n + 8);
     if ((size_t)ws.order.n < (size_t)n) ws.order.alloc(n);
@@ -461,9 +461,7 @@ static bool sym_eig_direct(const double* M, int ldm, int n, double eps, double* 
     NLE_LAUNCH_CHECK();
     double* lam = nullptr;
     double* vec = nullptr;
-    if (!sym_eig_dc_core(ws.As.p, n, ws, s, &lam, &vec)) return false;
-    eig_rank_kernel<<<cdiv(n, 128), 128, 0, s>>>(lam, n, ws.order.p);
-    NLE_LAUNCH_CHECK();
+    if (!sym_eig_dc_core(ws.As.p, n, eps, vec_limit, ws.order.p, d_r, ws, s, &lam, &vec)) return false;
     set_int_kernel<<<1, 1, 0, s>>>(d_r, n);
     NLE_LAUNCH_CHECK();
     eig_scatter_kernel<<<dim3(cdiv(n, 256) > 8 ? 8 : cdiv(n, 256), n), 256, 0, s>>>(vec, n, lam, ws.order.p, n, eps, U, D, d_r);
@@ -472,10 +470,10 @@ static bool sym_eig_direct(const double* M, int ldm, int n, double eps, double* 
 }
 
 int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
-            int* d_r, EigWorkspace& ws, cudaStream_t s) {
+            int* d_r, EigWorkspace& ws, cudaStream_t s, int vec_limit) {
     (void)psd_hint;
     if (n > 0 && !use_jacobi()) {
-        if (sym_eig_direct(M, ldm, n, eps, U, D, d_r, ws, s)) return 0;
+        if (sym_eig_direct(M, ldm, n, eps, U, D, d_r, ws, s, vec_limit)) return 0;
         if (getenv("NLE_B200_EIG_STRICT")) throw NoConvergence{"eigensolver: direct solver failed its sanity check (n=" + std::to_string(n) + ")"};
     }
     bool ok = true;

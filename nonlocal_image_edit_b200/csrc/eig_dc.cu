@@ -24,6 +24,7 @@
 // scripts/proto_eig_dc.py is the NumPy prototype of exactly this structure (checked against LAPACK).
 #include <cooperative_groups.h>
 
+#include <chrono>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -601,26 +602,83 @@ dc_copy_deflated_kernel(int n, int depth, const double* __restrict__ Q, int ldq,
 }
 
 // ---------------------------------------------------------------------------------------------
-// U = H_0 H_1 ... H_{n-3} Z in place; one warp per column, the column lives in shared memory.
-__global__ void backtransform_kernel(const double* __restrict__ A, int lda, const double* __restrict__ tau, int n,
-                                     double* __restrict__ Z, int ldz, int ncols) {
+// rank[j] = position of lam[j] in descending order (ties by index); *count = #(lam >= eps)  (zeroed by the caller)
+__global__ void dc_rank_count_kernel(const double* __restrict__ lam, int n, double eps, int* __restrict__ order,
+                                     int* __restrict__ count) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n) return;
+    const double lj = lam[j];
+    int rank = 0;
+    for (int l = 0; l < n; ++l) {
+        const double ll = lam[l];
+        rank += (ll > lj) || (ll == lj && l < j);
+    }
+    order[j] = rank;
+    if (lj >= eps) atomicAdd(count, 1);
+}
+
+// gdot[j] = v_{j-1} . v_j  (rows j+1..n-1), j >= 1: lets the back-transformation apply two reflectors per pass
+__global__ void reflector_dots_kernel(const double* __restrict__ A, int lda, int n, double* __restrict__ gdot) {
+    const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (j < 1 || j > n - 3) return;
+    const double* v0 = A + (size_t)(j - 1) * lda;
+    const double* v1 = A + (size_t)j * lda;
+    double acc = 0.0;
+    for (int i = j + 1 + lane; i < n; i += 32) acc = fma(v0[i], v1[i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) gdot[j] = acc;
+}
+
+// U = H_0 H_1 ... H_{n-3} Z in place; one warp per column, the column lives in shared memory, two reflectors
+// per pass:  z <- H_{j-1} H_j z  needs  d1 = v_j.z,  d2 = v_{j-1}.z - tau_j d1 (v_{j-1}.v_j)  -- both dots in one
+// sweep over z, one shuffle reduction, one update sweep.  Only columns the caller needs are transformed:
+// those whose eigenvalue ranks below min(vec_limit, *count).
+__global__ void backtransform_kernel(const double* __restrict__ A, int lda, const double* __restrict__ tau,
+                                     const double* __restrict__ gdot, int n, double* __restrict__ Z, int ldz,
+                                     const int* __restrict__ order, const int* __restrict__ count, int vec_limit) {
     extern __shared__ double zsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
     const int col = blockIdx.x * wpb + warp;
-    if (col >= ncols) return;
+    if (col >= n) return;
+    if (vec_limit >= 0) {
+        const int lim = min(vec_limit, *count);
+        if (order[col] >= lim) return;
+    }
     double* z = zsm + (size_t)warp * n;
     double* zc = Z + (size_t)col * ldz;
     for (int i = lane; i < n; i += 32) z[i] = zc[i];
     __syncwarp();
-    for (int j = n - 3; j >= 0; --j) {
-        const double t = tau[j];
-        if (t == 0.0) continue;
-        const double* v = A + (size_t)j * lda;
+    int j = n - 3;
+    for (; j >= 1; j -= 2) {
+        const double t1 = tau[j], t0 = tau[j - 1];
+        const double* v1 = A + (size_t)j * lda;          // rows j+1..
+        const double* v0 = A + (size_t)(j - 1) * lda;    // rows j..   (v0[j] == 1)
+        double d1 = 0.0, d0 = 0.0;
+        for (int i = j + 1 + lane; i < n; i += 32) {
+            const double zi = z[i];
+            d1 = fma(v1[i], zi, d1);
+            d0 = fma(v0[i], zi, d0);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        }
+        const double zj = z[j];
+        const double s1 = t1 * d1;
+        const double s0 = t0 * ((d0 + zj) - s1 * gdot[j]);
+        for (int i = j + 1 + lane; i < n; i += 32) z[i] = fma(-s0, v0[i], fma(-s1, v1[i], z[i]));
+        if (lane == 0) z[j] = zj - s0;
+        __syncwarp();
+    }
+    if (j == 0) {
+        const double t = tau[0];
+        const double* v = A;
         double dot = 0.0;
-        for (int i = j + 1 + lane; i < n; i += 32) dot = fma(v[i], z[i], dot);
+        for (int i = 1 + lane; i < n; i += 32) dot = fma(v[i], z[i], dot);
         dot = warp_sum(dot) * t;
-        for (int i = j + 1 + lane; i < n; i += 32) z[i] = fma(-dot, v[i], z[i]);
+        for (int i = 1 + lane; i < n; i += 32) z[i] = fma(-dot, v[i], z[i]);
         __syncwarp();
     }
     for (int i = lane; i < n; i += 32) zc[i] = z[i];
@@ -652,10 +710,17 @@ void EigWorkspace::reserve_dc(int n) {
 }
 
 // Eigen-decomposition of the symmetric matrix As (n x n, ld n, full storage; DESTROYED).
-// Results: eigenvalues (unsorted) in *lam_out, eigenvectors in the columns of *vec_out (ld n).
+// Results: eigenvalues (unsorted) in *lam_out, eigenvectors in the columns of *vec_out (ld n); order[j] = rank
+// of eigenvalue j in descending order, *count = #(eigenvalues >= eps).  vec_limit >= 0: only the eigenvectors
+// ranked below min(vec_limit, *count) are back-transformed (the others are left in the tridiagonal basis).
 // Returns false if a device-side sanity check failed (caller falls back to Jacobi).
-bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double** lam_out, double** vec_out) {
+bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, int* count, EigWorkspace& ws,
+                     cudaStream_t s, double** lam_out, double** vec_out) {
     ws.reserve_dc(n);
+    // developer timing (NLE_B200_EIG_PROF=1): wall-clock per phase with the stream drained
+    const bool prof = getenv("NLE_B200_EIG_PROF") != nullptr;
+    auto tnow = [&]() { if (prof) cudaStreamSynchronize(s); return std::chrono::steady_clock::now(); };
+    auto t_start = tnow();
     double* dd = ws.dcd.p;
     double* d0 = dd;                 // tridiagonal diagonal
     double* e0 = dd + n;             // off-diagonal
@@ -695,6 +760,7 @@ bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double
         NLE_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(grid), dim3(kTrdThreads), args, smem, s));
         ++g_launches;
     }
+    auto t_trd = tnow();
     // ---- 2. divide & conquer on (d0, e0)
     int depth = 0;
     while (((n + (1 << depth) - 1) >> depth) > kLeaf) ++depth;
@@ -731,6 +797,7 @@ bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double
         std::swap(Qc, Qn);
         std::swap(dc, dn);
     }
+    auto t_dc = tnow();
     // ---- 3. back-transformation (in place in Qc)
     {
         int dev = 0, max_smem = 0;
@@ -741,8 +808,22 @@ bool sym_eig_dc_core(double* As, int n, EigWorkspace& ws, cudaStream_t s, double
         if (wpb < 1) throw Unsupported{"eigensolver: back-transformation column does not fit in shared memory (n=" + std::to_string(n) + ")"};
         const size_t smem = (size_t)wpb * n * sizeof(double);
         NLE_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        backtransform_kernel<<<cdiv(n, wpb), wpb * 32, smem, s>>>(As, n, tau, n, Qc, n, n);
+        NLE_CUDA(cudaMemsetAsync(count, 0, sizeof(int), s));
+        dc_rank_count_kernel<<<cdiv(n, 128), 128, 0, s>>>(dc, n, eps, order, count);
         NLE_LAUNCH_CHECK();
+        double* gdot = pbuf;      // the symv exchange buffer of the tridiagonalisation is free again
+        if (n >= 4) {
+            reflector_dots_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(As, n, n, gdot);
+            NLE_LAUNCH_CHECK();
+        }
+        backtransform_kernel<<<cdiv(n, wpb), wpb * 32, smem, s>>>(As, n, tau, gdot, n, Qc, n, order, count, vec_limit);
+        NLE_LAUNCH_CHECK();
+    }
+    auto t_bt = tnow();
+    if (prof) {
+        auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+        fprintf(stderr, "[eig_dc n=%d] tridiag %.3f ms, divide&conquer %.3f ms, back-transform %.3f ms\n", n,
+                ms(t_start, t_trd), ms(t_trd, t_dc), ms(t_dc, t_bt));
     }
     dc_check_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(Qc, n, n, fail);
     NLE_LAUNCH_CHECK();
