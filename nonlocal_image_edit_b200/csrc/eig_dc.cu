@@ -154,12 +154,18 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
             for (int i = j + 1 + tid; i < n; i += kTrdThreads) col[i] = v[i];
             if (tid == 0) { d[j] = diag_j; e[j] = beta_j; tau[j] = tau_j; }
         }
-        // (1) w = tau*p - (tau^2/2)(p.v) v
+        // (1) w = tau*p - (tau^2/2)(p.v) v      (the loads of p and of column j+1 are issued together: both only
+        //     depend on the grid barrier, and their L2 round trips are the longest links of the per-step chain)
         double part = 0.0;
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) {
-            const double pi = __ldcg(p + i);
-            w[i] = pi;
-            part = fma(pi, v[i], part);
+        {
+            const double* col = A + (size_t)(j + 1) * lda;
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) {
+                const double pi = __ldcg(p + i);
+                const double ci = __ldcg(col + i);
+                w[i] = pi;
+                cn[i] = ci;
+                part = fma(pi, v[i], part);
+            }
         }
         const double dot = block_sum(part, red, phase);
         const double kappa = 0.5 * tau_j * tau_j * dot;
@@ -167,9 +173,8 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
         __syncthreads();
         // (2) updated column j+1 (rows j+1..n-1) -> next diagonal and next reflector
         {
-            const double* col = A + (size_t)(j + 1) * lda;
             const double wj1 = w[j + 1];   // v[j+1] == 1
-            for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = __ldcg(col + i) - v[i] * wj1 - w[i];
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
             __syncthreads();
         }
         const double diag_next = cn[j + 1];
@@ -189,13 +194,25 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
             const double wc = w[c], vc = v[c];
             double acc = 0.0;
             int i = j + 2 + lane;
-            // batches of 8 independent loads to cover the L2 latency
-            for (; i + 7 * 32 < n; i += 8 * 32) {
-                double a[8];
+            // batches of 16 independent loads to cover the L2 latency (the column is the longest link of the step)
+            for (; i + 15 * 32 < n; i += 16 * 32) {
+                double a[16];
 #pragma unroll
-                for (int u = 0; u < 8; ++u) a[u] = __ldcg(col + i + 32 * u);
+                for (int u = 0; u < 16; ++u) a[u] = __ldcg(col + i + 32 * u);
 #pragma unroll
-                for (int u = 0; u < 8; ++u) {
+                for (int u = 0; u < 16; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = fma(-w[ii], vc, fma(-v[ii], wc, a[u]));
+                    acc = fma(a[u], cn[ii], acc);
+                    __stcg(col + ii, a[u]);
+                }
+            }
+            for (; i + 3 * 32 < n; i += 4 * 32) {
+                double a[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) a[u] = __ldcg(col + i + 32 * u);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
                     const int ii = i + 32 * u;
                     a[u] = fma(-w[ii], vc, fma(-v[ii], wc, a[u]));
                     acc = fma(a[u], cn[ii], acc);
