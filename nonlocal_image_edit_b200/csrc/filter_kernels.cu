@@ -12,6 +12,8 @@
 // table of 256 x nC entries (a "bilateral grid" in luminance), which removes the p*N exponentials
 // AND most of the p*N multiply-adds; the Gram and extension kernels use it to generate FP64 operand
 // tiles in shared memory with three table look-ups per element.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace nle {
@@ -764,11 +766,163 @@ extension_kernel(AffinityTables t, const double* __restrict__ cvec, const double
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Extension on the FP64 tensor pipe:  V(pixels x k) = diag(c) * K_B^T(pixels x p) * Y(p x k).
+// Same organisation as gram_kernel (see there for the measurements behind it): 8 producer warps generate the
+// operand tile K(i,j) for 256 pixels x 16 samples -- loads and the first multiply (Ec*Er) while the consumers
+// run the DMMAs of the previous chunk, the last multiply (*Gt) and the stores in a burst between two named
+// barriers -- and stream the matching 16 x 56 slice of Y (repacked row-major, zero padded) into a double
+// buffer; 8 consumer warps hold a 32 x 56 block of V each (4 x 7 DMMA tiles, 56 accumulators per lane).
+constexpr int XM = 256;       // pixels per CTA
+constexpr int XN = 56;        // eigenvector columns per CTA (7 DMMA tiles); 56 % 16 == 8 keeps B fragments conflict-free
+constexpr int XK = 16;        // samples per chunk
+constexpr int XLD = XM + 8;
+
+__global__ void ext_pack_y_kernel(const double* __restrict__ Y, int p, int k, int kp, double* __restrict__ Yt) {
+    // Yt[i][v] = Y[i + v*p] for v < k, 0 for k <= v < kp   (row-major, ld kp)
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)p * kp) return;
+    const int i = (int)(e / kp), v = (int)(e - (long long)i * kp);
+    Yt[e] = (v < k) ? Y[i + (size_t)v * p] : 0.0;
+}
+
+__global__ void __launch_bounds__(512, 1)
+extension_dmma_kernel(AffinityTables t, const double* __restrict__ cvec, const double* __restrict__ Yt, int kp,
+                      int k, double* __restrict__ V) {
+    extern __shared__ double xsm[];
+    double (*As)[XLD] = reinterpret_cast<double (*)[XLD]>(xsm);                         // [XK][XLD]
+    double (*Bs)[XK][XN] = reinterpret_cast<double (*)[XK][XN]>(xsm + XK * XLD);        // [2][XK][XN]
+    double* Gs = xsm + XK * XLD + 2 * XK * XN;                                          // [256]
+    uint8_t* Ys = reinterpret_cast<uint8_t*>(Gs + 256);                                 // [p]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
+    const long long nloc = (long long)t.nrows * W;
+    const long long j0 = (long long)blockIdx.x * XM;
+    const int v0 = blockIdx.y * XN;
+    const int nchunks = (p + XK - 1) / XK;
+    if (tid < 256) Gs[tid] = t.Gt[tid];
+    for (int i = tid; i < p; i += 512) Ys[i] = t.Ysel[i];
+    __syncthreads();
+
+    if (tid < 256) {
+        // ------------------------------------------------------------------ producers (thread = pixel)
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 88;");
+        const long long j = j0 + tid;
+        const bool live = j < nloc;
+        const int rl = live ? (int)(j / W) : 0, col = live ? (int)(j - (long long)rl * W) : 0;
+        const int lv = live ? (int)t.lum[j] : 0;
+        const double* er = t.Er + (size_t)(t.row0 + rl) * nR;
+        const double* ec = t.Ec + (size_t)col * nC;
+        double sp[XK], gg[XK];
+        int pa = 0, pb = 0, pi = 0;        // grid coordinates / index of the first sample of the chunk being prepared
+        auto prep = [&](int buf) {
+            // Y slice of this chunk -> B double buffer (896 doubles, 3.5 per thread, coalesced rows of Yt)
+            for (int e = tid; e < XK * XN; e += 256) {
+                const int kq = e / XN, n = e - kq * XN;
+                const int i = pi + kq;
+                Bs[buf][kq][n] = (i < p) ? Yt[(size_t)i * kp + v0 + n] : 0.0;
+            }
+            int a = pa, b = pb;
+#pragma unroll
+            for (int q = 0; q < XK; ++q) {
+                const bool ok = live && (pi + q < p);
+                const double e1 = ok ? ec[b] : 0.0;
+                const double e2 = ok ? er[a] : 0.0;
+                int d = lv - (int)Ys[min(pi + q, p - 1)];
+                d = d < 0 ? -d : d;
+                gg[q] = Gs[d];
+                sp[q] = e1 * e2;        // spatial factor: off the critical path (overlaps the consumers' DMMAs)
+                if (++b == nC) { b = 0; ++a; }
+            }
+            pa = a; pb = b; pi += XK;
+        };
+        auto burst = [&]() {
+#pragma unroll
+            for (int q = 0; q < XK; ++q) As[q][tid] = sp[q] * gg[q];
+        };
+        if (nchunks > 0) {
+            prep(0);
+            burst();
+            asm volatile("bar.arrive 1, 512;" ::: "memory");
+        }
+        for (int ch = 0; ch < nchunks; ++ch) {
+            const bool more = ch + 1 < nchunks;
+            if (more) prep((ch + 1) & 1);
+            asm volatile("bar.sync 2, 512;" ::: "memory");
+            if (more) {
+                burst();
+                asm volatile("bar.arrive 1, 512;" ::: "memory");
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------------- consumers
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 168;");
+    const int cw = warp - 8;
+    const int g = lane >> 2, tq = lane & 3;
+    double acc[4][7][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 7; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    for (int ch = 0; ch < nchunks; ++ch) {
+        const int buf = ch & 1;
+        asm volatile("bar.sync 1, 512;" ::: "memory");
+#pragma unroll
+        for (int k4 = 0; k4 < XK / 4; ++k4) {
+            const double* ar = &As[k4 * 4 + tq][cw * 32 + g];
+            const double* br = &Bs[buf][k4 * 4 + tq][g];
+            double a[4], b[7];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) a[u] = ar[u * 8];
+#pragma unroll
+            for (int v = 0; v < 7; ++v) b[v] = br[v * 8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 7; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+        }
+        asm volatile("bar.arrive 2, 512;" ::: "memory");
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const long long j = j0 + cw * 32 + u * 8 + g;
+        if (j >= nloc) continue;
+        const int rl = (int)(j / W), col = (int)(j - (long long)rl * W);
+        if (t.rowa[t.row0 + rl] >= 0 && t.colb[col] >= 0) continue;     // sample pixel: scattered separately
+        const double cj = cvec[j];
+        double* vo = V + (size_t)j * k;
+#pragma unroll
+        for (int v = 0; v < 7; ++v) {
+            const int n = v0 + v * 8 + 2 * tq;
+            if (n < k) vo[n] = cj * acc[u][v][0];
+            if (n + 1 < k) vo[n + 1] = cj * acc[u][v][1];
+        }
+    }
+}
+
 void launch_extension(const AffinityTables& t, const double* c, const double* Y, int k, double* V,
                       cudaStream_t s) {
     long long nloc = (long long)t.nrows * t.cols;
     if (k <= 0 || nloc <= 0) return;
-    extension_kernel<<<dim3(cdiv(nloc, 256 * EPX), cdiv(k, EV)), 256, 0, s>>>(t, c, Y, k, V);
+    static const bool legacy = getenv("NLE_B200_EXT_LEGACY") != nullptr;
+    if (legacy) {
+        extension_kernel<<<dim3(cdiv(nloc, 256 * EPX), cdiv(k, EV)), 256, 0, s>>>(t, c, Y, k, V);
+        NLE_LAUNCH_CHECK();
+        return;
+    }
+    const int nvb = cdiv(k, XN), kp = nvb * XN;
+    DevBuf<double> Yt((size_t)t.p * kp);   // stream-ordered pool: freed after the kernel in stream order
+    ext_pack_y_kernel<<<cdiv((long long)t.p * kp, 256), 256, 0, s>>>(Y, t.p, k, kp, Yt.p);
+    NLE_LAUNCH_CHECK();
+    const size_t smem = (size_t)(XK * XLD + 2 * XK * XN + 256) * sizeof(double) + ((t.p + 15) / 16) * 16;
+    static size_t configured = 0;
+    if (smem > configured) {
+        NLE_CUDA(cudaFuncSetAttribute(extension_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        configured = smem;
+    }
+    extension_dmma_kernel<<<dim3(cdiv(nloc, XM), nvb), 512, smem, s>>>(t, c, Yt.p, kp, k, V);
     NLE_LAUNCH_CHECK();
 }
 
