@@ -277,7 +277,7 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
                   double* __restrict__ spart) {
     extern __shared__ double smd[];
     const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
-    double* wp = smd;                        // p
+    double* wp = smd;                        // p          (dot half; reused as the Ec staging area in the reduce half)
     double* Gs = wp + p;                     // 256
     double* F = Gs + 256;                    // 256 * nC   (F table, then reused as the histogram Hh)
     double* xrow = F + (size_t)256 * nC;     // W
@@ -291,6 +291,7 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     for (int i = tid; i < p; i += 256) Ys[i] = t.Ysel[i];
     Gs[tid] = t.Gt[tid];
+    const bool stage_ec = (32 * nC <= p);    // the 32 x nC slice of Ec fits in the wp area (nR >= 32)
     for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
         const int row = t.row0 + rl;
         const uint8_t* Lg = t.lum + (size_t)rl * W;
@@ -300,17 +301,32 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
         for (int i = tid; i < p; i += 256) wp[i] = er[i / nC] * w[i];
         __syncthreads();
         const int nlev = build_levels(Lrow, W, flags, levidx, lev, wcount);
-        // ---- dot half
-        for (int e = tid; e < nlev * nC; e += 256) {
-            int li = e / nC, b = e - li * nC;
-            int lvl = lev[li];
-            double acc = 0.0;
-            for (int a = 0; a < nR; ++a) {
-                int i = a * nC + b;
-                int d = lvl - (int)Ys[i];
-                acc = fma(wp[i], Gs[d < 0 ? -d : d], acc);
+        // ---- dot half:  F[li][b] = sum_a wp[a][b] * Gt[|lev[li] - Y[a][b]|]  (ascending a).  Four outputs per
+        // thread in flight: the loop is a chain of dependent shared-memory look-ups and one FMA, so a single
+        // chain leaves the SM idle (ncu: 45 % short-scoreboard stalls, 24 % issue utilisation).
+        const int nF = nlev * nC;
+        for (int e0 = tid; e0 < nF; e0 += 1024) {
+            int bb[4], lvl[4];
+            double acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int e = min(e0 + 256 * u, nF - 1);
+                const int li = e / nC;
+                bb[u] = e - li * nC;
+                lvl[u] = lev[li];
+                acc[u] = 0.0;
             }
-            F[e] = acc;
+            for (int a = 0; a < nR; ++a) {
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = a * nC + bb[u];
+                    const int d = lvl[u] - (int)Ys[i];
+                    acc[u] = fma(wp[i], Gs[d < 0 ? -d : d], acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                if (e0 + 256 * u < nF) F[e0 + 256 * u] = acc[u];
         }
         __syncthreads();
         const int a_row = t.rowa[row];
@@ -332,34 +348,96 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
         // ---- reduce half (F is now the histogram Hh)
         double* Hh = F;
         for (int e = tid; e < nlev * nC; e += 256) Hh[e] = 0.0;
-        __syncthreads();
-        for (int c0 = 0; c0 < W; c0 += 32) {
-            int c = c0 + lane;
-            int li_l = (c < W) ? (int)lirow[c] : 0;
-            bool mine = (c < W) && ((li_l & 7) == warp) && (xrow[c] != 0.0);
-            unsigned m = __ballot_sync(0xffffffffu, mine);
-            while (m) {
-                int j = __ffs(m) - 1;
-                m &= m - 1;
-                int col = c0 + j;
-                int li = __shfl_sync(0xffffffffu, li_l, j);
-                double xv = xrow[col];
-                const double* ec = t.Ec + (size_t)col * nC;
-                double* h = Hh + (size_t)li * nC;
-                for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+        // Hh[li][b] += Ec[col][b] * x_col, each (li, b) bin owned by one lane and filled in ascending column order.
+        // The Ec rows of 32 consecutive pixels are staged in shared memory (prefetched one chunk ahead in
+        // registers): reading them straight from L2 inside the serial per-pixel loop cost 29 % of the kernel.
+        if (stage_ec) {
+            constexpr int NPF = 8;                       // staged elements per thread: 32 * nC <= 256 * NPF (nC <= 64)
+            double* stage = wp;
+            const int nst = 32 * nC;
+            double pf[NPF];
+            auto fetch = [&](int c0) {
+#pragma unroll
+                for (int q = 0; q < NPF; ++q) {
+                    const int e = tid + 256 * q;
+                    pf[q] = (e < nst && c0 * nC + e < W * nC) ? t.Ec[(size_t)c0 * nC + e] : 0.0;
+                }
+            };
+            const bool wide = nst > 256 * NPF;
+            if (!wide) fetch(0);
+            for (int c0 = 0; c0 < W; c0 += 32) {
+                __syncthreads();                          // previous chunk consumed (and Hh zeroed on the first pass)
+                if (!wide) {
+#pragma unroll
+                    for (int q = 0; q < NPF; ++q) {
+                        const int e = tid + 256 * q;
+                        if (e < nst) stage[e] = pf[q];
+                    }
+                    if (c0 + 32 < W) fetch(c0 + 32);
+                } else {
+                    for (int e = tid; e < nst; e += 256) stage[e] = (c0 * nC + e < W * nC) ? t.Ec[(size_t)c0 * nC + e] : 0.0;
+                }
+                __syncthreads();
+                const int c = c0 + lane;
+                const int li_l = (c < W) ? (int)lirow[c] : 0;
+                const bool mine = (c < W) && ((li_l & 7) == warp) && (xrow[c] != 0.0);
+                unsigned m = __ballot_sync(0xffffffffu, mine);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int li = __shfl_sync(0xffffffffu, li_l, j);
+                    const double xv = xrow[c0 + j];
+                    const double* ec = stage + j * nC;
+                    double* h = Hh + (size_t)li * nC;
+                    for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+                }
+            }
+        } else {
+            __syncthreads();
+            for (int c0 = 0; c0 < W; c0 += 32) {
+                int c = c0 + lane;
+                int li_l = (c < W) ? (int)lirow[c] : 0;
+                bool mine = (c < W) && ((li_l & 7) == warp) && (xrow[c] != 0.0);
+                unsigned m = __ballot_sync(0xffffffffu, mine);
+                while (m) {
+                    int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    int col = c0 + j;
+                    int li = __shfl_sync(0xffffffffu, li_l, j);
+                    double xv = xrow[col];
+                    const double* ec = t.Ec + (size_t)col * nC;
+                    double* h = Hh + (size_t)li * nC;
+                    for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+                }
             }
         }
         __syncthreads();
+        // s[a][b] = er[a] * sum_li Gt[|lev[li] - Y[a][b]|] * Hh[li][b]  (ascending li), four outputs in flight
         double* so = spart + (size_t)rl * p;
-        for (int i = tid; i < p; i += 256) {
-            int a = i / nC, b = i - a * nC;
-            int yi = (int)Ys[i];
-            double acc = 0.0;
-            for (int li = 0; li < nlev; ++li) {
-                int d = lev[li] - yi;
-                acc = fma(Gs[d < 0 ? -d : d], Hh[(size_t)li * nC + b], acc);
+        for (int i0 = tid; i0 < p; i0 += 1024) {
+            int bb[4], yy[4];
+            double acc[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = min(i0 + 256 * u, p - 1);
+                bb[u] = i % nC;
+                yy[u] = (int)Ys[i];
+                acc[u] = 0.0;
             }
-            so[i] = er[a] * acc;
+            for (int li = 0; li < nlev; ++li) {
+                const int lvl = lev[li];
+                const double* hrow = Hh + (size_t)li * nC;
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int d = lvl - yy[u];
+                    acc[u] = fma(Gs[d < 0 ? -d : d], hrow[bb[u]], acc[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = i0 + 256 * u;
+                if (i < p) so[i] = er[i / nC] * acc[u];
+            }
         }
     }
 }
