@@ -292,6 +292,8 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
     for (int i = tid; i < p; i += 256) Ys[i] = t.Ysel[i];
     Gs[tid] = t.Gt[tid];
     const bool stage_ec = (32 * nC <= p);    // the 32 x nC slice of Ec fits in the wp area (nR >= 32)
+    const int ngrp = 256 / nC;               // thread groups of the (column, group) decomposition; 0: generic path
+    const int tb = tid % nC, tg = tid / nC;
     for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
         const int row = t.row0 + rl;
         const uint8_t* Lg = t.lum + (size_t)rl * W;
@@ -305,28 +307,53 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
         // thread in flight: the loop is a chain of dependent shared-memory look-ups and one FMA, so a single
         // chain leaves the SM idle (ncu: 45 % short-scoreboard stalls, 24 % issue utilisation).
         const int nF = nlev * nC;
-        for (int e0 = tid; e0 < nF; e0 += 1024) {
-            int bb[4], lvl[4];
-            double acc[4];
+        if (ngrp > 0) {
+            // thread = (grid column tb, group tg); 8 levels per thread: wp and Y are read once per 8 multiply-adds
+            if (tg < ngrp) {
+                for (int l0 = tg * 8; l0 < nlev; l0 += ngrp * 8) {
+                    int lv8[8];
+                    double acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int e = min(e0 + 256 * u, nF - 1);
-                const int li = e / nC;
-                bb[u] = e - li * nC;
-                lvl[u] = lev[li];
-                acc[u] = 0.0;
-            }
-            for (int a = 0; a < nR; ++a) {
+                    for (int u = 0; u < 8; ++u) { lv8[u] = lev[min(l0 + u, nlev - 1)]; acc[u] = 0.0; }
+                    for (int a = 0; a < nR; ++a) {
+                        const int i = a * nC + tb;
+                        const double wv = wp[i];
+                        const int yv = (int)Ys[i];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int i = a * nC + bb[u];
-                    const int d = lvl[u] - (int)Ys[i];
-                    acc[u] = fma(wp[i], Gs[d < 0 ? -d : d], acc[u]);
+                        for (int u = 0; u < 8; ++u) {
+                            const int d = lv8[u] - yv;
+                            acc[u] = fma(wv, Gs[d < 0 ? -d : d], acc[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u)
+                        if (l0 + u < nlev) F[(l0 + u) * nC + tb] = acc[u];
                 }
             }
+        } else {
+            for (int e0 = tid; e0 < nF; e0 += 1024) {
+                int bb[4], lvl[4];
+                double acc[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
-                if (e0 + 256 * u < nF) F[e0 + 256 * u] = acc[u];
+                for (int u = 0; u < 4; ++u) {
+                    const int e = min(e0 + 256 * u, nF - 1);
+                    const int li = e / nC;
+                    bb[u] = e - li * nC;
+                    lvl[u] = lev[li];
+                    acc[u] = 0.0;
+                }
+                for (int a = 0; a < nR; ++a) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int i = a * nC + bb[u];
+                        const int d = lvl[u] - (int)Ys[i];
+                        acc[u] = fma(wp[i], Gs[d < 0 ? -d : d], acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                    if (e0 + 256 * u < nF) F[e0 + 256 * u] = acc[u];
+            }
         }
         __syncthreads();
         const int a_row = t.rowa[row];
@@ -414,29 +441,55 @@ pass_fused_kernel(AffinityTables t, const double* __restrict__ w, double* __rest
         __syncthreads();
         // s[a][b] = er[a] * sum_li Gt[|lev[li] - Y[a][b]|] * Hh[li][b]  (ascending li), four outputs in flight
         double* so = spart + (size_t)rl * p;
-        for (int i0 = tid; i0 < p; i0 += 1024) {
-            int bb[4], yy[4];
-            double acc[4];
+        if (ngrp > 0) {
+            // thread = (grid column tb, group tg); 8 grid rows per thread: Hh and the level are read once per 8 FMAs
+            if (tg < ngrp) {
+                for (int a0 = tg * 8; a0 < nR; a0 += ngrp * 8) {
+                    int yy[8];
+                    double acc[8];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = min(i0 + 256 * u, p - 1);
-                bb[u] = i % nC;
-                yy[u] = (int)Ys[i];
-                acc[u] = 0.0;
-            }
-            for (int li = 0; li < nlev; ++li) {
-                const int lvl = lev[li];
-                const double* hrow = Hh + (size_t)li * nC;
+                    for (int u = 0; u < 8; ++u) { yy[u] = (int)Ys[min(a0 + u, nR - 1) * nC + tb]; acc[u] = 0.0; }
+                    for (int li = 0; li < nlev; ++li) {
+                        const int lvl = lev[li];
+                        const double h = Hh[(size_t)li * nC + tb];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int d = lvl - yy[u];
-                    acc[u] = fma(Gs[d < 0 ? -d : d], hrow[bb[u]], acc[u]);
+                        for (int u = 0; u < 8; ++u) {
+                            const int d = lvl - yy[u];
+                            acc[u] = fma(Gs[d < 0 ? -d : d], h, acc[u]);
+                        }
+                    }
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const int a = a0 + u;
+                        if (a < nR) so[a * nC + tb] = er[a] * acc[u];
+                    }
                 }
             }
+        } else {
+            for (int i0 = tid; i0 < p; i0 += 1024) {
+                int bb[4], yy[4];
+                double acc[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-                const int i = i0 + 256 * u;
-                if (i < p) so[i] = er[i / nC] * acc[u];
+                for (int u = 0; u < 4; ++u) {
+                    const int i = min(i0 + 256 * u, p - 1);
+                    bb[u] = i % nC;
+                    yy[u] = (int)Ys[i];
+                    acc[u] = 0.0;
+                }
+                for (int li = 0; li < nlev; ++li) {
+                    const int lvl = lev[li];
+                    const double* hrow = Hh + (size_t)li * nC;
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int d = lvl - yy[u];
+                        acc[u] = fma(Gs[d < 0 ? -d : d], hrow[bb[u]], acc[u]);
+                    }
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int i = i0 + 256 * u;
+                    if (i < p) so[i] = er[i / nC] * acc[u];
+                }
             }
         }
     }
