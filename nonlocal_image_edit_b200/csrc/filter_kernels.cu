@@ -608,9 +608,9 @@ __global__ void __launch_bounds__(GRAM_THREADS, 1)
 gram_kernel(AffinityTables t, const double* __restrict__ CE, int ntile, int nsplit,
             double* __restrict__ part) {
     extern __shared__ double gsm[];
-    double (*As)[GLD] = reinterpret_cast<double (*)[GLD]>(gsm);                 // [GKC][GLD]
-    double (*Bs)[GLD] = reinterpret_cast<double (*)[GLD]>(gsm + GKC * GLD);     // [GKC][GLD]
-    double* Gs = gsm + 2 * GKC * GLD;                                           // [256]
+    double (*As)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm);                     // [2][GKC][GLD]
+    double (*Bs)[GKC][GLD] = reinterpret_cast<double (*)[GKC][GLD]>(gsm + 2 * GKC * GLD);     // [2][GKC][GLD]
+    double* Gs = gsm + 4 * GKC * GLD;                                                         // [256]
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
@@ -687,25 +687,27 @@ gram_kernel(AffinityTables t, const double* __restrict__ CE, int ntile, int nspl
             if (pcol0 >= W) { pcol0 = 0; ++prow; }
         };
         // the only FP64 arithmetic of the producers: 2 multiplies per entry, issued while the DMMA stream is idle
-        auto burst = [&]() {
+        auto burst = [&](int buf) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q) As[ph * 8 + q][sIdx] = (ceA[q] * gA[q]) * erA;
+            for (int q = 0; q < 8; ++q) As[buf][ph * 8 + q][sIdx] = (ceA[q] * gA[q]) * erA;
             if (!diag) {
 #pragma unroll
-                for (int q = 0; q < 8; ++q) Bs[ph * 8 + q][sIdx] = (ceB[q] * gB[q]) * erB;
+                for (int q = 0; q < 8; ++q) Bs[buf][ph * 8 + q][sIdx] = (ceB[q] * gB[q]) * erB;
             }
         };
         if (nchunks > 0) {
             prep();
-            burst();
+            burst(0);
             asm volatile("bar.arrive 1, 512;" ::: "memory");          // tile 0 full
         }
         for (long long ch = 0; ch < nchunks; ++ch) {
             const bool more = ch + 1 < nchunks;
             if (more) prep();                                          // overlaps the consumers' DMMAs of chunk ch
-            asm volatile("bar.sync 2, 512;" ::: "memory");             // consumers have issued every DMMA of chunk ch
+            // the consumers signal when only the last quarter of chunk ch is left: the burst (into the other tile
+            // buffer) overlaps that tail instead of leaving the tensor pipe idle
+            asm volatile("bar.sync 2, 512;" ::: "memory");
             if (more) {
-                burst();
+                burst((int)((ch + 1) & 1));
                 asm volatile("bar.arrive 1, 512;" ::: "memory");      // tile ch+1 full
             }
         }
@@ -725,13 +727,17 @@ gram_kernel(AffinityTables t, const double* __restrict__ CE, int ntile, int nspl
     // A warp whose 32 x 64 sub-tile lies entirely in the padding (p is not a multiple of 128) or strictly
     // below the diagonal of a diagonal tile (only i <= j is ever read back) issues no DMMA.
     const bool wactive = (ti * GT + wm * 32 < p) && (tj * GT + wn * 64 < p) && !(diag && wm * 32 >= wn * 64 + 64);
-    const double (*Bp)[GLD] = diag ? As : Bs;
     for (long long ch = 0; ch < nchunks; ++ch) {
+        const int buf = (int)(ch & 1);
+        const double (*Ap)[GLD] = As[buf];
+        const double (*Bp)[GLD] = diag ? As[buf] : Bs[buf];
         asm volatile("bar.sync 1, 512;" ::: "memory");                 // tile ch full
-        if (wactive) {
 #pragma unroll
-            for (int k4 = 0; k4 < GKC / 4; ++k4) {
-                const double* ar = &As[k4 * 4 + tq][wm * 32 + g];
+        for (int k4 = 0; k4 < GKC / 4; ++k4) {
+            if (k4 == GKC / 4 - 1) asm volatile("bar.arrive 2, 512;" ::: "memory");   // last quarter: producers may burst
+                                                                                          // (signalling at half was measured slower)
+            if (wactive) {
+                const double* ar = &Ap[k4 * 4 + tq][wm * 32 + g];
                 const double* br = &Bp[k4 * 4 + tq][wn * 64 + g];
                 double a[4], b[8];
 #pragma unroll
@@ -744,7 +750,6 @@ gram_kernel(AffinityTables t, const double* __restrict__ CE, int ntile, int nspl
                     for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
             }
         }
-        asm volatile("bar.arrive 2, 512;" ::: "memory");               // done reading tile ch, DMMAs issued
     }
     double* out = part + ((size_t)split * gridDim.x + blockIdx.x) * (GT * GT);
 #pragma unroll
@@ -792,7 +797,7 @@ void launch_gram(const AffinityTables& t, const double* c, double* scratch, doub
     double* CE = scratch + (size_t)ntp * nsplit * GT * GT;
     gram_ce_kernel<<<sm_count() * 8, 256, 0, s>>>(t, c, CE);
     NLE_LAUNCH_CHECK();
-    const size_t smem = (size_t)(2 * GKC * GLD + 256) * sizeof(double);
+    const size_t smem = (size_t)(4 * GKC * GLD + 256) * sizeof(double);
     static size_t configured = 0;
     if (smem > configured) {
         NLE_CUDA(cudaFuncSetAttribute(gram_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -921,9 +926,9 @@ __global__ void __launch_bounds__(512, 1)
 extension_dmma_kernel(AffinityTables t, const double* __restrict__ cvec, const double* __restrict__ Yt, int kp,
                       int k, double* __restrict__ V) {
     extern __shared__ double xsm[];
-    double (*As)[XLD] = reinterpret_cast<double (*)[XLD]>(xsm);                         // [XK][XLD]
-    double (*Bs)[XK][XN] = reinterpret_cast<double (*)[XK][XN]>(xsm + XK * XLD);        // [2][XK][XN]
-    double* Gs = xsm + XK * XLD + 2 * XK * XN;                                          // [256]
+    double (*As)[XK][XLD] = reinterpret_cast<double (*)[XK][XLD]>(xsm);                     // [2][XK][XLD]
+    double (*Bs)[XK][XN] = reinterpret_cast<double (*)[XK][XN]>(xsm + 2 * XK * XLD);        // [2][XK][XN]
+    double* Gs = xsm + 2 * XK * XLD + 2 * XK * XN;                                          // [256]
     uint8_t* Ys = reinterpret_cast<uint8_t*>(Gs + 256);                                 // [p]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int p = t.p, nC = t.nC, nR = t.nR, W = t.cols;
@@ -967,21 +972,21 @@ extension_dmma_kernel(AffinityTables t, const double* __restrict__ cvec, const d
             }
             pa = a; pb = b; pi += XK;
         };
-        auto burst = [&]() {
+        auto burst = [&](int buf) {
 #pragma unroll
-            for (int q = 0; q < XK; ++q) As[q][tid] = sp[q] * gg[q];
+            for (int q = 0; q < XK; ++q) As[buf][q][tid] = sp[q] * gg[q];
         };
         if (nchunks > 0) {
             prep(0);
-            burst();
+            burst(0);
             asm volatile("bar.arrive 1, 512;" ::: "memory");
         }
         for (int ch = 0; ch < nchunks; ++ch) {
             const bool more = ch + 1 < nchunks;
             if (more) prep((ch + 1) & 1);
-            asm volatile("bar.sync 2, 512;" ::: "memory");
+            asm volatile("bar.sync 2, 512;" ::: "memory");      // consumers are in the last quarter of chunk ch
             if (more) {
-                burst();
+                burst((ch + 1) & 1);
                 asm volatile("bar.arrive 1, 512;" ::: "memory");
             }
         }
@@ -1002,7 +1007,8 @@ extension_dmma_kernel(AffinityTables t, const double* __restrict__ cvec, const d
         asm volatile("bar.sync 1, 512;" ::: "memory");
 #pragma unroll
         for (int k4 = 0; k4 < XK / 4; ++k4) {
-            const double* ar = &As[k4 * 4 + tq][cw * 32 + g];
+            if (k4 == XK / 4 - 1) asm volatile("bar.arrive 2, 512;" ::: "memory");
+            const double* ar = &As[buf][k4 * 4 + tq][cw * 32 + g];
             const double* br = &Bs[buf][k4 * 4 + tq][g];
             double a[4], b[7];
 #pragma unroll
@@ -1014,7 +1020,6 @@ extension_dmma_kernel(AffinityTables t, const double* __restrict__ cvec, const d
 #pragma unroll
                 for (int v = 0; v < 7; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
-        asm volatile("bar.arrive 2, 512;" ::: "memory");
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
@@ -1047,7 +1052,7 @@ void launch_extension(const AffinityTables& t, const double* c, const double* Y,
     DevBuf<double> Yt((size_t)t.p * kp);   // stream-ordered pool: freed after the kernel in stream order
     ext_pack_y_kernel<<<cdiv((long long)t.p * kp, 256), 256, 0, s>>>(Y, t.p, k, kp, Yt.p);
     NLE_LAUNCH_CHECK();
-    const size_t smem = (size_t)(XK * XLD + 2 * XK * XN + 256) * sizeof(double) + ((t.p + 15) / 16) * 16;
+    const size_t smem = (size_t)(2 * XK * XLD + 2 * XK * XN + 256) * sizeof(double) + ((t.p + 15) / 16) * 16;
     static size_t configured = 0;
     if (smem > configured) {
         NLE_CUDA(cudaFuncSetAttribute(extension_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
