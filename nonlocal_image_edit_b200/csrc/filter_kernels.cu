@@ -785,13 +785,22 @@ static void gram_geometry(const AffinityTables& t, int& ntile, int& ntp, int& ns
     if (nsplit < 1) nsplit = 1;
 }
 
+// Default: the cell-contracted Gram (gram_cells.cu).  NLE_B200_GRAM=pixel selects the pixel-axis SYRK below
+// (same result up to FP64 re-association; kept as a cross-check and for the parity tests).
+static bool gram_pixel_path() {
+    static const bool v = [] { const char* e = getenv("NLE_B200_GRAM"); return e && std::string(e) == "pixel"; }();
+    return v;
+}
+
 size_t gram_scratch_doubles(const AffinityTables& t) {
+    if (!gram_pixel_path()) return gram_cells_scratch_doubles(t);
     int ntile, ntp, nsplit;
     gram_geometry(t, ntile, ntp, nsplit);
     return (size_t)ntp * nsplit * GT * GT + (size_t)t.nrows * t.cols * t.nC;   // partial tiles + CE table
 }
 
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
+    if (!gram_pixel_path()) { launch_gram_cells(t, c, scratch, G, s); return; }
     int ntile, ntp, nsplit;
     gram_geometry(t, ntile, ntp, nsplit);
     double* CE = scratch + (size_t)ntp * nsplit * GT * GT;

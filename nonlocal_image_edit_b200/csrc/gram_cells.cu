@@ -1,0 +1,435 @@
+// Weighted Gram  G = sum_j c_j^2 k_j k_j^T  over the rest pixels (the "Wab Wab^T" of filter.cpp:296 in
+// factor form), contracted through (image row, luminance level) CELLS.
+//
+// With K(i,j) = Er[row][a] * Ec[col][b] * Gt[|l - Y_ab|]  (kernels.cuh) the Gram separates as
+//
+//   G[(a,b),(a',b')] = sum_{row,l}  (Er[row][a] Gt[|l-Y_ab|]) * Hh[row,l][b,b'] * (Er[row][a'] Gt[|l-Y_a'b'|])
+//   Hh[row,l][b,b']  = sum_{col : lum(row,col) = l}  c_j^2 Ec[col][b] Ec[col][b']
+//
+// i.e. the pixel axis (N terms) collapses onto the non-empty cells (row, l) -- at most 256 per image row,
+// K_cells of them in total -- and for every pair of grid columns (b <= b') the nR x nR block of G is a small
+// GEMM whose K dimension is the cell axis.  Work drops from N*p*(p+1) flop (the pixel-axis SYRK of
+// gram_kernel, filter_kernels.cu) to K_cells*p*(p+1): a factor W/nlev (5.9 on the 1024^2 bench image, >= 16
+// on a 4096-wide one), and nothing about it is approximate -- it is a re-association of the same FP64 sum.
+//
+// Kernels:
+//   cell_count_kernel  per image row: number of distinct levels, padded to a multiple of 4
+//   cell_scan_kernel   exclusive scan -> koff[row] (first cell of each row), koff[nrows] = K_pad
+//   cell_hist_kernel   per image row: level list, stable counting sort of the columns by level, Hh for every
+//                      pair (b <= b') accumulated in ascending column order (deterministic), cell levels
+//   gram_cells_kernel  one WARP per (pair, a-block, a'-block, K split): 8*MT x 8*MT FP64 accumulators on the
+//                      FP64 tensor pipe (DMMA m8n8k4); operand fragments are generated straight into
+//                      registers (one table look-up and one or two multiplies per element), no shared-memory
+//                      tiles, no block barriers in the main loop
+//   gram_cells_reduce_kernel  fixed-order sum over the K splits, mirrored into both triangles of G
+#include <algorithm>
+#include <cstdlib>
+
+#include "kernels.cuh"
+
+namespace nle {
+
+namespace {
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+// Distinct luminance levels of one image row (blockDim.x == 256).  levidx[l] = compact index (ascending
+// level) or -1, lev[li] = level.  Returns the number of levels.
+__device__ __forceinline__ int row_levels(const uint8_t* __restrict__ Lrow, int W, int* flags, int* levidx,
+                                          int* lev, int* wcount) {
+    const int tid = threadIdx.x;
+    flags[tid] = 0;
+    __syncthreads();
+    for (int c = tid; c < W; c += 256) flags[Lrow[c]] = 1;
+    __syncthreads();
+    const unsigned m = __ballot_sync(0xffffffffu, flags[tid] != 0);
+    if ((tid & 31) == 0) wcount[tid >> 5] = __popc(m);
+    __syncthreads();
+    int base = 0, total = 0;
+    for (int w = 0; w < 8; ++w) {
+        if (w < (tid >> 5)) base += wcount[w];
+        total += wcount[w];
+    }
+    const int my = base + __popc(m & ((1u << (tid & 31)) - 1u));
+    if (flags[tid]) { levidx[tid] = my; lev[my] = tid; } else levidx[tid] = -1;
+    __syncthreads();
+    return total;
+}
+
+__global__ void __launch_bounds__(256)
+cell_count_kernel(const uint8_t* __restrict__ lum, int nrows, int W, int* __restrict__ cnt) {
+    __shared__ int flags[256];
+    __shared__ int wcount[8];
+    const int tid = threadIdx.x;
+    for (int rl = blockIdx.x; rl < nrows; rl += gridDim.x) {
+        __syncthreads();
+        flags[tid] = 0;
+        __syncthreads();
+        const uint8_t* L = lum + (size_t)rl * W;
+        for (int c = tid; c < W; c += 256) flags[L[c]] = 1;
+        __syncthreads();
+        const unsigned m = __ballot_sync(0xffffffffu, flags[tid] != 0);
+        if ((tid & 31) == 0) wcount[tid >> 5] = __popc(m);
+        __syncthreads();
+        if (tid == 0) {
+            int total = 0;
+            for (int w = 0; w < 8; ++w) total += wcount[w];
+            cnt[rl] = (total + 3) & ~3;
+        }
+    }
+}
+
+// koff[0] = 0, koff[i+1] = koff[i] + cnt[i]   (single CTA of 1024 threads; nrows is a few thousand)
+__global__ void __launch_bounds__(1024)
+cell_scan_kernel(const int* __restrict__ cnt, int nrows, int* __restrict__ koff) {
+    __shared__ int part[1024];
+    const int tid = threadIdx.x;
+    const int per = (nrows + 1023) / 1024;
+    const int r0 = min(nrows, tid * per), r1 = min(nrows, r0 + per);
+    int s = 0;
+    for (int r = r0; r < r1; ++r) s += cnt[r];
+    part[tid] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int run = 0;
+        for (int i = 0; i < 1024; ++i) { const int v = part[i]; part[i] = run; run += v; }
+        koff[nrows] = run;
+    }
+    __syncthreads();
+    int run = part[tid];
+    for (int r = r0; r < r1; ++r) { koff[r] = run; run += cnt[r]; }
+}
+
+// linear index of the pair (b <= b') in the upper triangle of an nC x nC matrix, row by row
+__host__ __device__ __forceinline__ int pair_start(int b, int nC) { return b * nC - (b * (b - 1)) / 2; }
+__device__ __forceinline__ void pair_decode(int q, int nC, int& b, int& bp) {
+    int lo = 0;
+    while (lo + 1 < nC && pair_start(lo + 1, nC) <= q) ++lo;
+    b = lo;
+    bp = lo + (q - pair_start(lo, nC));
+}
+
+constexpr int HS = 32;      // sorted pixels staged per step
+constexpr int HPT = 4;      // pairs per thread and batch
+
+// One CTA per image row.  Hh[(koff[row] + li) * ld + q] for every pair q; cell_lev[koff[row] + li].
+__global__ void __launch_bounds__(256)
+cell_hist_kernel(AffinityTables t, const double* __restrict__ cvec, const int* __restrict__ koff, int npairs,
+                 int ld, uint8_t* __restrict__ cell_lev, double* __restrict__ Hh) {
+    extern __shared__ double hsm[];
+    const int nC = t.nC, W = t.cols;
+    double* stA = hsm;                          // HS * nC   c_j^2 * Ec[col][.]
+    double* stB = stA + HS * nC;                // HS * nC   Ec[col][.]
+    int* flags = reinterpret_cast<int*>(stB + HS * nC);
+    int* levidx = flags + 256;
+    int* lev = levidx + 256;
+    int* cstart = lev + 256;                    // 257: first sorted position of each cell
+    int* wcount = cstart + 260;
+    int* sorted = wcount + 8;                   // W: columns ordered by (level, column)
+    uint8_t* Lrow = reinterpret_cast<uint8_t*>(sorted + W);           // W
+    uint8_t* lis = Lrow + ((W + 15) / 16) * 16;                       // W: cell index of each sorted position
+    const int tid = threadIdx.x;
+    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
+        __syncthreads();
+        const uint8_t* Lg = t.lum + (size_t)rl * W;
+        for (int c = tid; c < W; c += 256) Lrow[c] = Lg[c];
+        __syncthreads();
+        const int nlev = row_levels(Lrow, W, flags, levidx, lev, wcount);
+        const int npad = (nlev + 3) & ~3;
+        const int k0 = koff[rl];
+        // stable counting sort of the columns by level: thread li scans the row (ascending column)
+        if (tid < nlev) {
+            const int lv = lev[tid];
+            int n = 0;
+            for (int c = 0; c < W; ++c) n += (Lrow[c] == lv);
+            flags[tid] = n;                       // flags is free again: per-cell pixel count
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int li = 0; li < nlev; ++li) { cstart[li] = run; run += flags[li]; }
+            cstart[nlev] = run;
+        }
+        __syncthreads();
+        if (tid < nlev) {
+            const int lv = lev[tid];
+            int pos = cstart[tid];
+            for (int c = 0; c < W; ++c)
+                if (Lrow[c] == lv) { sorted[pos] = c; lis[pos] = (uint8_t)tid; ++pos; }
+        }
+        if (tid < npad) cell_lev[k0 + tid] = (uint8_t)(tid < nlev ? lev[tid] : 0);
+        __syncthreads();
+        const double* cg = cvec + (size_t)rl * W;
+        for (int q0 = 0; q0 < npairs; q0 += 256 * HPT) {
+            int qb[HPT], qbp[HPT];
+            double acc[HPT];
+#pragma unroll
+            for (int i = 0; i < HPT; ++i) {
+                const int q = q0 + tid + 256 * i;
+                if (q < npairs) pair_decode(q, nC, qb[i], qbp[i]); else { qb[i] = 0; qbp[i] = 0; }
+                acc[i] = 0.0;
+            }
+            int cur = 0;
+            auto flush = [&](int li) {
+                double* h = Hh + (size_t)(k0 + li) * ld;
+#pragma unroll
+                for (int i = 0; i < HPT; ++i) {
+                    const int q = q0 + tid + 256 * i;
+                    if (q < npairs) h[q] = acc[i];
+                    acc[i] = 0.0;
+                }
+            };
+            for (int s0 = 0; s0 < W; s0 += HS) {
+                __syncthreads();
+                const int ns = min(HS, W - s0);
+                for (int e = tid; e < ns * nC; e += 256) {
+                    const int sI = e / nC, b = e - sI * nC;
+                    const int col = sorted[s0 + sI];
+                    const double cj = cg[col];
+                    const double ev = t.Ec[(size_t)col * nC + b];
+                    stA[e] = (cj * cj) * ev;
+                    stB[e] = ev;
+                }
+                __syncthreads();
+                for (int sI = 0; sI < ns; ++sI) {
+                    const int li = (int)lis[s0 + sI];
+                    if (li != cur) { flush(cur); cur = li; }
+                    const double* sa = stA + sI * nC;
+                    const double* sb = stB + sI * nC;
+#pragma unroll
+                    for (int i = 0; i < HPT; ++i) acc[i] = fma(sa[qb[i]], sb[qbp[i]], acc[i]);
+                }
+            }
+            flush(cur);
+            // padding cells carry zero weight
+            for (int li = nlev; li < npad; ++li) {
+                double* h = Hh + (size_t)(k0 + li) * ld;
+#pragma unroll
+                for (int i = 0; i < HPT; ++i) {
+                    const int q = q0 + tid + 256 * i;
+                    if (q < npairs) h[q] = 0.0;
+                }
+            }
+        }
+    }
+}
+
+constexpr int GC_WARPS = 8;
+
+// One warp per task = (pair (b,b'), a-block, a'-block) x K split.  Tile: T x T with T = 8*MT grid rows.
+//   A[k][a ] = Er[row_k][a ] * Gt[|lev_k - Y[a ][b ]|]
+//   B[k][a'] = Er[row_k][a'] * Gt[|lev_k - Y[a'][b']|] * Hh[k][pair]
+// DMMA fragments (lane = 4g + tq): A elem (m = g, k = tq), B elem (k = tq, n = g), D elems (g, 2tq), (g, 2tq+1).
+// The 256-entry Gt table is replicated 16x in shared memory, interleaved so that lane L always reads bank pair
+// (L & 15): the 64-bit look-ups of a warp (two 16-lane phases) are conflict-free whatever the levels are.
+template <int MT>
+__global__ void __launch_bounds__(GC_WARPS * 32, 1)
+gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __restrict__ cell_lev,
+                  const double* __restrict__ Hh, int ld, int nab, int ntasks, int nsplit, int accumulate,
+                  double* __restrict__ part) {
+    __shared__ double Gs16[256 * 16];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int e = tid; e < 256 * 16; e += GC_WARPS * 32) Gs16[e] = t.Gt[e >> 4];
+    __syncthreads();
+    const int task = blockIdx.x * GC_WARPS + warp;
+    if (task >= ntasks) return;
+    const int nC = t.nC, nR = t.nR;
+    constexpr int T = 8 * MT;
+    const int pair = task / (nab * nab);
+    const int rem = task - pair * nab * nab;
+    const int ab = rem / nab, abp = rem - ab * nab;
+    int b, bp;
+    pair_decode(pair, nC, b, bp);
+    const int g = lane >> 2, tq = lane & 3;
+    const int split = blockIdx.y;
+
+    int yA[MT], yB[MT], aA[MT], aB[MT];
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+        aA[u] = ab * T + 8 * u + g;
+        aB[u] = abp * T + 8 * u + g;
+        yA[u] = aA[u] < nR ? (int)t.Ysel[aA[u] * nC + b] : 0;
+        yB[u] = aB[u] < nR ? (int)t.Ysel[aB[u] * nC + bp] : 0;
+    }
+    double acc[MT][MT][2];
+#pragma unroll
+    for (int u = 0; u < MT; ++u)
+#pragma unroll
+        for (int v = 0; v < MT; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+
+    const int nsteps = koff[t.nrows] >> 2;
+    int k = (int)(((long long)nsteps * split) / nsplit) * 4;
+    const int kend = (int)(((long long)nsteps * (split + 1)) / nsplit) * 4;
+    // image row of the first cell
+    int row = 0;
+    {
+        int lo = 0, hi = t.nrows - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (koff[mid] <= k) lo = mid; else hi = mid - 1;
+        }
+        row = lo;
+    }
+    int krow_end = koff[row + 1];
+    double erA[MT], erB[MT];
+    auto load_er = [&]() {
+        const double* er = t.Er + (size_t)(t.row0 + row) * nR;
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+            erA[u] = aA[u] < nR ? er[aA[u]] : 0.0;
+            erB[u] = aB[u] < nR ? er[aB[u]] : 0.0;
+        }
+    };
+    load_er();
+    const double* gs = Gs16 + (lane & 15);
+    const double* hp = Hh + pair;
+
+    while (k < kend) {
+        const int kk = k + lane;
+        int lv32 = 0;
+        double hh32 = 0.0;
+        if (kk < kend) {
+            lv32 = (int)cell_lev[kk];
+            hh32 = hp[(size_t)kk * ld];
+        }
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int ks = k + 4 * i;
+            if (ks >= kend) break;
+            if (ks >= krow_end) {
+                do { ++row; krow_end = koff[row + 1]; } while (ks >= krow_end);
+                load_er();
+            }
+            const int lv = __shfl_sync(0xffffffffu, lv32, 4 * i + tq);
+            const double hh = __shfl_sync(0xffffffffu, hh32, 4 * i + tq);
+            double a[MT], bf[MT];
+#pragma unroll
+            for (int u = 0; u < MT; ++u) {
+                const int dA = lv - yA[u], dB = lv - yB[u];
+                a[u] = erA[u] * gs[(dA < 0 ? -dA : dA) << 4];
+                bf[u] = (erB[u] * hh) * gs[(dB < 0 ? -dB : dB) << 4];
+            }
+#pragma unroll
+            for (int u = 0; u < MT; ++u)
+#pragma unroll
+                for (int v = 0; v < MT; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], bf[v]);
+        }
+        k += 32;
+    }
+
+    double* out = part + ((size_t)split * ntasks + task) * (T * T);
+#pragma unroll
+    for (int u = 0; u < MT; ++u)
+#pragma unroll
+        for (int v = 0; v < MT; ++v) {
+            double2* o = reinterpret_cast<double2*>(out + (8 * u + g) * T + 8 * v + 2 * tq);
+            double2 val = make_double2(acc[u][v][0], acc[u][v][1]);
+            if (accumulate) { const double2 old = *o; val.x += old.x; val.y += old.y; }
+            *o = val;
+        }
+}
+
+__global__ void gram_cells_reduce_kernel(const double* __restrict__ part, int p, int nR, int nC, int T, int nab,
+                                         int ntasks, int nsplit, double* __restrict__ G) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
+    if (i >= p) return;
+    int a = i / nC, b = i - a * nC, ap = j / nC, bp = j - ap * nC;
+    if (b > bp || (b == bp && a > ap)) { int tmp = a; a = ap; ap = tmp; tmp = b; b = bp; bp = tmp; }
+    const int pair = pair_start(b, nC) + (bp - b);
+    const int task = pair * nab * nab + (a / T) * nab + (ap / T);
+    const size_t off = (size_t)task * (T * T) + (size_t)(a % T) * T + (ap % T);
+    double acc = 0.0;
+    for (int s = 0; s < nsplit; ++s) acc += part[(size_t)s * ntasks * (T * T) + off];
+    G[i + (size_t)j * p] = acc;
+}
+
+struct CellGeom {
+    int npairs, ld, MT, T, nab, ntasks, ncta, nsplit, capc, rows_batch;
+    size_t hh_doubles, part_doubles, lev_bytes, int_count;
+};
+
+CellGeom cell_geometry(const AffinityTables& t) {
+    CellGeom g;
+    g.npairs = t.nC * (t.nC + 1) / 2;
+    g.ld = (g.npairs + 3) & ~3;
+    const int tiles = cdiv(t.nR, 8);
+    int nab = cdiv(tiles, 5);
+    g.MT = cdiv(tiles, nab);
+    g.nab = nab;
+    g.T = 8 * g.MT;
+    g.ntasks = g.npairs * nab * nab;
+    g.ncta = cdiv(g.ntasks, GC_WARPS);
+    g.nsplit = std::max(1, (7 * sm_count()) / g.ncta);
+    g.nsplit = std::min(g.nsplit, std::max(1, t.nrows));
+    g.capc = std::min(256, (t.cols + 3) & ~3);
+    // Hh is sized for the worst case (every row holds capc cells): bound it to ~2.5 GB per batch of rows
+    const size_t per_row = (size_t)g.capc * g.ld;
+    const size_t budget = (size_t)320 << 20;   // doubles
+    g.rows_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)t.nrows, budget / per_row));
+    g.hh_doubles = per_row * g.rows_batch;
+    g.part_doubles = (size_t)g.nsplit * g.ntasks * g.T * g.T;
+    g.lev_bytes = (size_t)g.capc * g.rows_batch;
+    g.int_count = 2 * (size_t)g.rows_batch + 8;
+    return g;
+}
+
+}  // namespace
+
+size_t gram_cells_scratch_doubles(const AffinityTables& t) {
+    const CellGeom g = cell_geometry(t);
+    return g.hh_doubles + g.part_doubles + (g.lev_bytes + 7) / 8 + (g.int_count * 4 + 7) / 8 + 8;
+}
+
+template <int MT>
+static void launch_gc(const AffinityTables& tb, const CellGeom& g, const int* koff, const uint8_t* cell_lev,
+                      const double* Hh, int accumulate, double* part, cudaStream_t s) {
+    gram_cells_kernel<MT><<<dim3(g.ncta, g.nsplit), GC_WARPS * 32, 0, s>>>(tb, koff, cell_lev, Hh, g.ld, g.nab, g.ntasks,
+                                                                            g.nsplit, accumulate, part);
+    NLE_LAUNCH_CHECK();
+}
+
+void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
+    const CellGeom g = cell_geometry(t);
+    double* Hh = scratch;
+    double* part = Hh + g.hh_doubles;
+    uint8_t* cell_lev = reinterpret_cast<uint8_t*>(part + g.part_doubles);
+    int* cnt = reinterpret_cast<int*>(cell_lev + ((g.lev_bytes + 7) / 8) * 8);
+    int* koff = cnt + g.rows_batch + 4;
+    const size_t hsm = (size_t)2 * HS * t.nC * sizeof(double) + (size_t)(256 * 3 + 260 + 8 + t.cols) * sizeof(int) +
+                       2 * (size_t)((t.cols + 15) / 16) * 16 + 64;
+    if (hsm > 227 * 1024) throw Unsupported{"gram: image too wide for the per-row cell sort (cols=" + std::to_string(t.cols) + ")"};
+    static size_t configured = 0;
+    if (hsm > configured) {
+        NLE_CUDA(cudaFuncSetAttribute(cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+        configured = hsm;
+    }
+    for (int r0 = 0, batch = 0; r0 < t.nrows; r0 += g.rows_batch, ++batch) {
+        AffinityTables tb = t;
+        tb.row0 = t.row0 + r0;
+        tb.nrows = std::min(g.rows_batch, t.nrows - r0);
+        tb.lum = t.lum + (size_t)r0 * t.cols;
+        const double* cb = c + (size_t)r0 * t.cols;
+        cell_count_kernel<<<std::min(tb.nrows, sm_count() * 8), 256, 0, s>>>(tb.lum, tb.nrows, tb.cols, cnt);
+        NLE_LAUNCH_CHECK();
+        cell_scan_kernel<<<1, 1024, 0, s>>>(cnt, tb.nrows, koff);
+        NLE_LAUNCH_CHECK();
+        cell_hist_kernel<<<tb.nrows, 256, hsm, s>>>(tb, cb, koff, g.npairs, g.ld, cell_lev, Hh);
+        NLE_LAUNCH_CHECK();
+        switch (g.MT) {
+            case 1: launch_gc<1>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 2: launch_gc<2>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 3: launch_gc<3>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 4: launch_gc<4>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            default: launch_gc<5>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+        }
+    }
+    gram_cells_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(part, t.p, t.nR, t.nC, g.T, g.nab, g.ntasks,
+                                                                       g.nsplit, G);
+    NLE_LAUNCH_CHECK();
+}
+
+}  // namespace nle

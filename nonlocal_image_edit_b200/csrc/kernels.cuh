@@ -46,6 +46,10 @@ size_t gram_scratch_doubles(const AffinityTables& t);
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G,
                  cudaStream_t s);
 
+// Same Gram through (image row, luminance level) cells (gram_cells.cu): K_cells*p*(p+1) flop instead of N*p*(p+1).
+size_t gram_cells_scratch_doubles(const AffinityTables& t);
+void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s);
+
 // Extension  V_j = c_j * k_j^T Y   for non-sample slab pixels.  Y: p x k (column-major),
 // V: (nrows*cols) x k ROW-major (k fastest).
 void launch_extension(const AffinityTables& t, const double* c, const double* Y, int k, double* V,
