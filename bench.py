@@ -157,7 +157,7 @@ def workload_config(n):
             "baseline_config": "BASELINE.json configs[2]",
             "rows": BASE_ROWS * n, "cols": COLS, "p": 1600, "k": K_EIG, "sinkhorn_iters": T_SINK,
             "parallelism": f"row-sharded x{n}" if n > 1 else "single GPU",
-            "l2_policy": "each step streams >500 MB of scratch (Gram partial tiles, V) through the 126 MB L2; "
+            "l2_policy": "each step streams >1.5 GB of scratch (per-cell histograms, Gram partials, V) through the 126 MB L2; "
                          "inputs are re-uploaded / re-read every step",
             "lab_conversion": "L channel fed directly to the C ABI; BGR<->Lab stays in host OpenCV as in the reference"}
 
@@ -301,20 +301,28 @@ def run_b200(args, rank, world, local_rank):
     st = np.median(np.array(stage_ms), axis=0)
     inf = infos[-1]
 
-    # roofline of the dominant kernel: the fused affinity+Gram kernel (FP64 FMA bound).
-    # algorithmic work per launch = one fused multiply-add per (pixel, sample pair i<=j): N*p*(p+1)/2 FMAs
-    # = N*p*(p+1) flops on this rank's slab (symmetric form).
+    # roofline of the dominant kernel: gram_cells_kernel (FP64 tensor pipe, DMMA).  The Gram is contracted over
+    # the non-empty (image row, luminance level) cells of this rank's slab: algorithmic work per
+    # launch = one fused multiply-add per (cell, sample pair i<=j) = K_cells*p*(p+1) flops.  SURVEY.md 8d's
+    # figure for the same quantity on the pixel axis, N*p*(p+1), is reported next to it: their ratio is the
+    # work the re-association removes, not a roofline fraction.  launch_ms is the CUDA-event time of the whole
+    # Gram stage (cell sort + per-cell histograms + gram_cells_kernel + split reduce), i.e. conservative.
     pp = inf.p
-    gram_flops = float(nloc) * pp * (pp + 1)
+    slab = lum[row0:row1]
+    k_cells = int(sum(np.unique(r).size for r in slab))
+    gram_flops = float(k_cells) * pp * (pp + 1)
+    survey_flops = float(nloc) * pp * (pp + 1)
     peak = lib.nle_b200_fp64_fma_peak_tflops()
     achieved = gram_flops / (st[7] * 1e-3) * 1e-12 if st[7] > 0 else None
-    roofline = {"kernel": "gram_kernel (fused affinity tile generation + FP64 SYRK over pixels)",
+    roofline = {"kernel": "gram_cells_kernel (register-generated affinity fragments + FP64 DMMA over (row, level) cells)",
                 "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
                 "launch_ms": float(st[7]),
                 "peak_source": "measured in this run by nle_b200_fp64_fma_peak_tflops (register-resident DFMA "
                                "microbenchmark); MEASURED_PEAKS.json has no FP64 figure",
-                "algorithmic_flops_per_launch": gram_flops}
+                "algorithmic_flops_per_launch": gram_flops, "cells": k_cells,
+                "pixel_axis_flops_survey_8d": survey_flops,
+                "pixel_axis_equivalent_tflops": survey_flops / (st[7] * 1e-3) * 1e-12 if st[7] > 0 else None}
 
     # CPU baseline on a bounded crop (rank 0, N=1 only)
     cpu = None

@@ -287,7 +287,12 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     Timer t_sink(s);
     TmpBuf<double> inv_lam(p), xsel(p), ysel(p), svec(p), tvec(p), t2(p), wvec(p), lt(p);
     TmpBuf<double> xfull((size_t)nloc), cfull((size_t)nloc);
-    TmpBuf<double> spart(((size_t)nrows + cdiv(nrows, 32) + 1) * p);
+    // Default: level-table GEMM form (sinkhorn_cells.cu).  NLE_B200_SINKHORN=rows (or a grid too wide for its
+    // shared-memory tables) selects the per-row kernels of filter_kernels.cu (same result up to FP64 re-association).
+    static const bool sk_rows_env = [] { const char* e = getenv("NLE_B200_SINKHORN"); return e && std::string(e) == "rows"; }();
+    const bool sk_cells = !sk_rows_env && sinkhorn_cells_supported(tb);
+    TmpBuf<double> spart(sk_cells ? 1 : ((size_t)nrows + cdiv(nrows, 32) + 1) * p);
+    TmpBuf<double> skscratch(sk_cells ? sinkhorn_cells_scratch_doubles(tb) : 1);
     copy_dd(inv_lam.p, lam.p, p, s);
     guarded_reciprocal(inv_lam.p, r, kEps, s);            // filter.cpp:265-266
     // t = phi^T x = U_r^T x_sel + Lam^-1 U_r^T (Kab x_rest)
@@ -303,14 +308,19 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         dgemv_n(p, r, U.p, p, lt.p, x_sel_out, s);         // samples: U[s,:] Lam t
         guarded_reciprocal(x_sel_out, p, kEps, s);
         if (need_rest) {
-            launch_pass_fused(tb, wvec.p, xfull.p, spart.p, svec.p, s);
+            if (sk_cells) launch_sinkhorn_cells(tb, wvec.p, xfull.p, skscratch.p, svec.p, s);
+            else launch_pass_fused(tb, wvec.p, xfull.p, spart.p, svec.p, s);
             do_allreduce(f.get(), svec.p, p);
         }
     };
     // initial r = 1 : s0 = Kab 1
-    launch_fill(xfull.p, nloc, 1.0, s);
-    launch_mask_samples(tb, xfull.p, s);
-    launch_pass_reduce(tb, xfull.p, spart.p, svec.p, s);
+    if (sk_cells) {
+        launch_sinkhorn_cells(tb, nullptr, xfull.p, skscratch.p, svec.p, s);
+    } else {
+        launch_fill(xfull.p, nloc, 1.0, s);
+        launch_mask_samples(tb, xfull.p, s);
+        launch_pass_reduce(tb, xfull.p, spart.p, svec.p, s);
+    }
     do_allreduce(f.get(), svec.p, p);
     launch_fill(xsel.p, p, 1.0, s);
     phiT_x(xsel.p, svec.p);

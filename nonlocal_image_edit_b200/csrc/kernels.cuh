@@ -41,6 +41,13 @@ void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart,
 void launch_pass_fused(const AffinityTables& t, const double* w, double* x, double* spart, double* s_out,
                        cudaStream_t s);
 
+// One Sinkhorn half-iteration with the sample-axis contractions as level-table GEMMs on the FP64 tensor pipe
+// (sinkhorn_cells.cu):  x = recip(k_j^T w) on the rest pixels (w == nullptr: x = 1), then s_out = Kab x.
+bool sinkhorn_cells_supported(const AffinityTables& t);
+size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t);
+void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, double* scratch, double* s_out,
+                           cudaStream_t s);
+
 // Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab.
 size_t gram_scratch_doubles(const AffinityTables& t);
 void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G,

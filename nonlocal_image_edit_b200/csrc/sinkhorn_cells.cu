@@ -1,0 +1,318 @@
+// Sinkhorn half-iteration over the rest pixels (filter.cpp:238-245 in factor form) with the
+// two sample-axis contractions on the FP64 tensor pipe.
+//
+// With K(i,j) = Er[row][a] * Ec[col][b] * Gt[|l - Y_ab|]  (kernels.cuh) one half-iteration is
+//
+//   dot:     y_j  = sum_b Ec[col_j][b] * F[row_j][b][l_j],     F[row][b][l] = sum_a Er[row][a] * (w_ab Gt[|l-Y_ab|])
+//            x_j  = |y_j| >= eps ? 1/y_j : 0                    (inplaceReciprocal, filter.cpp:42-54)
+//   reduce:  s_ab = sum_l Gt[|l-Y_ab|] * M[b][a][l],            M[b][a][l]   = sum_row Er[row][a] * Hx[row][b][l]
+//            Hx[row][b][l] = sum_{col : lum(row,col) = l} Ec[col][b] * x_j
+//
+// F (for every grid column b an (image rows x nR) * (nR x 256) product) and M (its transpose) are plain dense
+// GEMMs over ALL 256 luminance levels: they share the level-by-sample table across image rows, which the
+// per-row kernels of filter_kernels.cu (pass_fused_kernel: one table look-up per (row, level, sample) and
+// multiply-add) could not -- ncu showed those bound by shared-memory look-ups, not by arithmetic.
+//
+//   sk_dot_gemm_kernel      F  = Er * B_b,  B operand generated in registers (one look-up per 8 DMMAs)
+//   sk_pix_kernel           one CTA per image row: y, x, and the per-row histogram Hx (deterministic: every
+//                           (level, b) bin is owned by one lane and filled in ascending column order);
+//                           Hx overwrites F in place
+//   sk_reduce_gemm_kernel   M partials = Er^T * Hx over row splits
+//   sk_reduce_final_kernel  s_ab = sum_l Gt * (sum over splits), fixed order
+#include <algorithm>
+
+#include "kernels.cuh"
+
+namespace nle {
+
+namespace {
+
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+
+constexpr int NL = 256;        // luminance levels
+constexpr int DG_ROWS = 32;    // image rows per CTA of the dot GEMM
+constexpr int DG_MT = DG_ROWS / 8;   // DMMA m-tiles per warp
+
+// F[row][b][l] = sum_a Er[row][a] * w_ab * Gt[|l - Y_ab|].   grid (ceil(nrows/DG_ROWS), nC), 256 threads.
+// Warp w owns levels [32w, 32w+32) (4 n-tiles) for all DG_ROWS rows.
+__global__ void __launch_bounds__(256, 2)
+sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ F) {
+    extern __shared__ double dsm[];
+    const int nR = t.nR, nC = t.nC;
+    const int nRp = (nR + 3) & ~3;
+    const int lda = nRp + ((12 - (nRp & 15)) & 15);          // lda % 16 == 12: conflict-free A fragments
+    double* As = dsm;                                        // DG_ROWS * lda
+    double* Gs = As + DG_ROWS * lda;                         // 256
+    double* wc = Gs + NL;                                    // nRp   w_ab of this grid column
+    int* yc = reinterpret_cast<int*>(wc + nRp);              // nRp   Y_ab
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.y;
+    const int r0 = blockIdx.x * DG_ROWS;
+    Gs[tid] = t.Gt[tid];
+    for (int a = tid; a < nRp; a += 256) {
+        wc[a] = a < nR ? w[a * nC + b] : 0.0;
+        yc[a] = a < nR ? (int)t.Ysel[a * nC + b] : 0;
+    }
+    for (int e = tid; e < DG_ROWS * nRp; e += 256) {
+        const int r = e / nRp, a = e - r * nRp;
+        As[r * lda + a] = (r0 + r < t.nrows && a < nR) ? t.Er[(size_t)(t.row0 + r0 + r) * nR + a] : 0.0;
+    }
+    __syncthreads();
+    double acc[DG_MT][4][2];
+#pragma unroll
+    for (int u = 0; u < DG_MT; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    const int l0 = warp * 32 + g;
+    for (int kk = 0; kk < nRp; kk += 4) {
+        const int a = kk + tq;
+        const double wv = wc[a];
+        const int yv = yc[a];
+        double bf[4], af[DG_MT];
+#pragma unroll
+        for (int v = 0; v < 4; ++v) {
+            const int d = l0 + 8 * v - yv;
+            bf[v] = wv * Gs[d < 0 ? -d : d];
+        }
+#pragma unroll
+        for (int u = 0; u < DG_MT; ++u) af[u] = As[(8 * u + g) * lda + a];
+#pragma unroll
+        for (int u = 0; u < DG_MT; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
+    }
+#pragma unroll
+    for (int u = 0; u < DG_MT; ++u) {
+        const int r = r0 + 8 * u + g;
+        if (r >= t.nrows) continue;
+        double* o = F + ((size_t)r * nC + b) * NL + warp * 32 + 2 * tq;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
+}
+
+// One CTA per image row.  FH row block: [nC][256] in global memory; on entry F (ignored when w_given == 0:
+// the initial pass with x = 1), on exit Hx.  x: slab vector (0 at sample pixels).
+__global__ void __launch_bounds__(256)
+sk_pix_kernel(AffinityTables t, int w_given, double* __restrict__ x, double* __restrict__ FH) {
+    extern __shared__ double psm[];
+    const int nC = t.nC, W = t.cols;
+    const int nCp = nC | 1;                                  // odd stride: transposed copies are conflict-free
+    double* Ts = psm;                                        // NL * nCp   F, then the histogram
+    double* stage = Ts + (size_t)NL * nCp;                   // 32 * nC    Ec rows of 32 consecutive pixels
+    double* xrow = stage + 32 * nC;                          // W
+    uint8_t* Lrow = reinterpret_cast<uint8_t*>(xrow + W);    // W
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
+        const int row = t.row0 + rl;
+        double* fh = FH + (size_t)rl * nC * NL;
+        const uint8_t* Lg = t.lum + (size_t)rl * W;
+        __syncthreads();
+        for (int c = tid; c < W; c += 256) Lrow[c] = Lg[c];
+        const int a_row = t.rowa[row];
+        double* xo = x + (size_t)rl * W;
+        if (w_given) {
+            for (int e = tid; e < nC * NL; e += 256) Ts[(e & (NL - 1)) * nCp + (e >> 8)] = fh[e];
+            __syncthreads();
+            for (int c = tid; c < W; c += 256) {
+                double r = 0.0;
+                if (!(a_row >= 0 && t.colb[c] >= 0)) {
+                    const double* f = Ts + (size_t)Lrow[c] * nCp;
+                    double acc = 0.0;
+                    for (int b = 0; b < nC; ++b) acc = fma(t.EcT[(size_t)b * W + c], f[b], acc);
+                    r = (fabs(acc) >= kEps) ? 1.0 / acc : 0.0;
+                }
+                xo[c] = r;
+                xrow[c] = r;
+            }
+        } else {
+            __syncthreads();
+            for (int c = tid; c < W; c += 256) {
+                const double r = (a_row >= 0 && t.colb[c] >= 0) ? 0.0 : 1.0;
+                xo[c] = r;
+                xrow[c] = r;
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < NL * nCp; e += 256) Ts[e] = 0.0;
+        // Hx[l][b] += Ec[col][b] * x_col: warp `warp` owns the levels with (l & 7) == warp, lanes own b; pixels are
+        // visited in ascending column order, 32 at a time, their Ec rows staged in shared memory
+        for (int c0 = 0; c0 < W; c0 += 32) {
+            __syncthreads();
+            const int nst = min(32, W - c0) * nC;
+            for (int e = tid; e < nst; e += 256) stage[e] = t.Ec[(size_t)c0 * nC + e];
+            __syncthreads();
+            const int c = c0 + lane;
+            const int lv_l = (c < W) ? (int)Lrow[c] : 0;
+            const bool mine = (c < W) && ((lv_l & 7) == warp) && (xrow[c] != 0.0);
+            unsigned m = __ballot_sync(0xffffffffu, mine);
+            while (m) {
+                const int j = __ffs(m) - 1;
+                m &= m - 1;
+                const int lv = __shfl_sync(0xffffffffu, lv_l, j);
+                const double xv = xrow[c0 + j];
+                const double* ec = stage + j * nC;
+                double* h = Ts + (size_t)lv * nCp;
+                for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nC * NL; e += 256) fh[e] = Ts[(e & (NL - 1)) * nCp + (e >> 8)];
+    }
+}
+
+// Mpart[ks][b][a][l] = sum_{row in split ks} Er[row][a] * Hx[row][b][l].
+// grid (nC, nks, nab), 256 threads; warp w owns levels [32w, 32w+32) (4 n-tiles) for MT m-tiles of grid rows.
+template <int MT>
+__global__ void __launch_bounds__(256, 2)
+sk_reduce_gemm_kernel(AffinityTables t, const double* __restrict__ Hx, int nks, int nRp, double* __restrict__ Mpart) {
+    const int nR = t.nR, nC = t.nC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.x, ks = blockIdx.y, a0 = blockIdx.z * (8 * MT);
+    const int rb = (int)(((long long)t.nrows * ks) / nks);
+    const int re = (int)(((long long)t.nrows * (ks + 1)) / nks);
+    double acc[MT][4][2];
+#pragma unroll
+    for (int u = 0; u < MT; ++u)
+#pragma unroll
+        for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    const double* hb = Hx + (size_t)b * NL + warp * 32 + g;
+    auto load = [&](int r, double* af, double* bf) {
+        const int rr = r + tq;
+        const bool ok = rr < re;
+        const double* er = t.Er + (size_t)(t.row0 + rr) * nR;
+        const double* h = hb + (size_t)rr * nC * NL;
+#pragma unroll
+        for (int u = 0; u < MT; ++u) {
+            const int a = a0 + 8 * u + g;
+            af[u] = (ok && a < nR) ? er[a] : 0.0;
+        }
+#pragma unroll
+        for (int v = 0; v < 4; ++v) bf[v] = ok ? h[8 * v] : 0.0;
+    };
+    double af0[MT], bf0[4], af1[MT], bf1[4];
+    if (rb < re) load(rb, af0, bf0);
+    for (int r = rb; r < re; r += 8) {
+        if (r + 4 < re) load(r + 4, af1, bf1);
+#pragma unroll
+        for (int u = 0; u < MT; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], af0[u], bf0[v]);
+        if (r + 4 >= re) break;
+        if (r + 8 < re) load(r + 8, af0, bf0);
+#pragma unroll
+        for (int u = 0; u < MT; ++u)
+#pragma unroll
+            for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], af1[u], bf1[v]);
+    }
+    double* out = Mpart + (((size_t)ks * nC + b) * nRp) * NL;
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+        const int a = a0 + 8 * u + g;
+        if (a >= nRp) continue;
+        double* o = out + (size_t)a * NL + warp * 32 + 2 * tq;
+#pragma unroll
+        for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
+}
+
+// s[a*nC+b] = sum_l Gt[|l - Y_ab|] * sum_ks Mpart[ks][b][a][l].   One warp per sample, fixed summation order.
+__global__ void __launch_bounds__(256)
+sk_reduce_final_kernel(AffinityTables t, const double* __restrict__ Mpart, int nks, int nRp, double* __restrict__ s_out) {
+    const int i = blockIdx.x * 8 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (i >= t.p) return;
+    const int a = i / t.nC, b = i - a * t.nC;
+    const int y = (int)t.Ysel[i];
+    double acc = 0.0;
+    for (int l = lane; l < NL; l += 32) {
+        double m = 0.0;
+        for (int ks = 0; ks < nks; ++ks) m += Mpart[(((size_t)ks * t.nC + b) * nRp + a) * NL + l];
+        const int d = l - y;
+        acc = fma(t.Gt[d < 0 ? -d : d], m, acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) s_out[i] = acc;
+}
+
+struct SkGeom {
+    int nRp, MT, nab, nks;
+    size_t fh_doubles, mpart_doubles, pix_smem, dot_smem;
+};
+
+SkGeom sk_geometry(const AffinityTables& t) {
+    SkGeom g;
+    g.nRp = (t.nR + 7) & ~7;
+    const int tiles = g.nRp / 8;
+    g.nab = cdiv(tiles, 5);
+    g.MT = cdiv(tiles, g.nab);
+    g.nRp = g.nab * g.MT * 8;
+    g.nks = std::max(1, std::min(std::max(1, t.nrows / 32), (2 * sm_count()) / std::max(1, t.nC * g.nab)));
+    g.fh_doubles = (size_t)t.nrows * t.nC * NL;
+    g.mpart_doubles = (size_t)g.nks * t.nC * g.nRp * NL;
+    const int nCp = t.nC | 1;
+    g.pix_smem = ((size_t)NL * nCp + 32 * (size_t)t.nC + t.cols) * sizeof(double) + ((t.cols + 15) / 16) * 16 + 64;
+    const int nR4 = (t.nR + 3) & ~3;
+    const int lda = nR4 + ((12 - (nR4 & 15)) & 15);
+    g.dot_smem = ((size_t)DG_ROWS * lda + NL + nR4) * sizeof(double) + (size_t)nR4 * sizeof(int) + 64;
+    return g;
+}
+
+}  // namespace
+
+bool sinkhorn_cells_supported(const AffinityTables& t) {
+    const SkGeom g = sk_geometry(t);
+    return g.pix_smem <= 227 * 1024 && g.dot_smem <= 227 * 1024;
+}
+
+size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t) {
+    const SkGeom g = sk_geometry(t);
+    return g.fh_doubles + g.mpart_doubles + 8;
+}
+
+template <int MT>
+static void launch_rg(const AffinityTables& t, const SkGeom& g, const double* FH, double* Mpart, cudaStream_t s) {
+    sk_reduce_gemm_kernel<MT><<<dim3(t.nC, g.nks, g.nab), 256, 0, s>>>(t, FH, g.nks, g.nRp, Mpart);
+    NLE_LAUNCH_CHECK();
+}
+
+// One half-iteration:  x = recip(k_j^T w) on the rest pixels (w == nullptr: x = 1), then s = Kab x.
+void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, double* scratch, double* s_out,
+                           cudaStream_t s) {
+    const SkGeom g = sk_geometry(t);
+    double* FH = scratch;
+    double* Mpart = FH + g.fh_doubles;
+    static size_t conf_pix = 0, conf_dot = 0;
+    if (g.pix_smem > conf_pix) {
+        NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
+        conf_pix = g.pix_smem;
+    }
+    if (g.dot_smem > conf_dot) {
+        NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_smem));
+        conf_dot = g.dot_smem;
+    }
+    if (w) {
+        sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH);
+        NLE_LAUNCH_CHECK();
+    }
+    sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
+    NLE_LAUNCH_CHECK();
+    switch (g.MT) {
+        case 1: launch_rg<1>(t, g, FH, Mpart, s); break;
+        case 2: launch_rg<2>(t, g, FH, Mpart, s); break;
+        case 3: launch_rg<3>(t, g, FH, Mpart, s); break;
+        case 4: launch_rg<4>(t, g, FH, Mpart, s); break;
+        default: launch_rg<5>(t, g, FH, Mpart, s); break;
+    }
+    sk_reduce_final_kernel<<<cdiv(t.p, 8), 256, 0, s>>>(t, Mpart, g.nks, g.nRp, s_out);
+    NLE_LAUNCH_CHECK();
+}
+
+}  // namespace nle
