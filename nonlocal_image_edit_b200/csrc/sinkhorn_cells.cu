@@ -20,6 +20,7 @@
 //   sk_reduce_gemm_kernel   M partials = Er^T * Hx over row splits
 //   sk_reduce_final_kernel  s_ab = sum_l Gt * (sum over splits), fixed order
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -166,6 +167,105 @@ sk_pix_kernel(AffinityTables t, int w_given, double* __restrict__ x, double* __r
     }
 }
 
+// Same row pass with the dot and the histogram fused over chunks of PF_CH consecutive pixels: the Ec rows of a
+// chunk are staged ONCE in shared memory (coalesced, prefetched one chunk ahead in registers) and serve both
+// halves, so a row costs nC*W*8 B of Ec traffic instead of twice that through the strided EcT reads of
+// sk_pix_kernel; F and the histogram live in separate shared-memory tables (2 * 256 * nC * 8 B: nC <= 47).
+// 16 warps: in the dot half 8 threads share a pixel (b = sub, sub+8, ...; xor-shuffle tree), in the
+// histogram half warp w owns the levels with (l & 15) == w (lanes over b, ascending column order).
+constexpr int PF_THREADS = 512;
+constexpr int PF_CH = 64;
+constexpr int PF_NPF = 6;       // staged doubles per thread: PF_CH * nC <= PF_THREADS * PF_NPF  (nC <= 48)
+
+__global__ void __launch_bounds__(PF_THREADS, 1)
+sk_pix_fused_kernel(AffinityTables t, int w_given, double* __restrict__ x, double* __restrict__ FH) {
+    extern __shared__ double psm[];
+    const int nC = t.nC, W = t.cols;
+    const int nCp = nC | 1;
+    double* Fs = psm;                                        // NL * nCp
+    double* Hs = Fs + (size_t)NL * nCp;                      // NL * nCp
+    double* stage = Hs + (size_t)NL * nCp;                   // PF_CH * nC
+    double* xs = stage + PF_CH * nC;                         // PF_CH
+    uint8_t* Lrow = reinterpret_cast<uint8_t*>(xs + PF_CH);  // W
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nst = PF_CH * nC;
+    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
+        const int row = t.row0 + rl;
+        double* fh = FH + (size_t)rl * nC * NL;
+        const uint8_t* Lg = t.lum + (size_t)rl * W;
+        const int a_row = t.rowa[row];
+        double* xo = x + (size_t)rl * W;
+        __syncthreads();
+        for (int c = tid; c < W; c += PF_THREADS) Lrow[c] = Lg[c];
+        if (w_given)
+            for (int e = tid; e < nC * NL; e += PF_THREADS) Fs[(e & (NL - 1)) * nCp + (e >> 8)] = fh[e];
+        for (int e = tid; e < NL * nCp; e += PF_THREADS) Hs[e] = 0.0;
+        double pf[PF_NPF];
+        auto fetch = [&](int c0) {
+#pragma unroll
+            for (int q = 0; q < PF_NPF; ++q) {
+                const int e = tid + PF_THREADS * q;
+                pf[q] = (e < nst && (size_t)c0 * nC + e < (size_t)W * nC) ? t.Ec[(size_t)c0 * nC + e] : 0.0;
+            }
+        };
+        fetch(0);
+        for (int c0 = 0; c0 < W; c0 += PF_CH) {
+            __syncthreads();                               // previous chunk consumed; row tables ready
+#pragma unroll
+            for (int q = 0; q < PF_NPF; ++q) {
+                const int e = tid + PF_THREADS * q;
+                if (e < nst) stage[e] = pf[q];
+            }
+            if (c0 + PF_CH < W) fetch(c0 + PF_CH);
+            __syncthreads();
+            // ---- dot half: 8 threads per pixel (b = sub, sub+8, ...), xor-shuffle tree inside the 8-lane group
+            {
+                static_assert(PF_CH * 8 == PF_THREADS, "8 threads per staged pixel");
+                const int j = tid >> 3, sub = tid & 7;
+                const int c = c0 + j;
+                double v = 0.0;
+                if (w_given && c < W) {
+                    const double* f = Fs + (size_t)Lrow[c] * nCp;
+                    const double* ec = stage + j * nC;
+                    for (int b = sub; b < nC; b += 8) v = fma(ec[b], f[b], v);
+                }
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                if (sub == 0 && c < W) {
+                    double r;
+                    if (a_row >= 0 && t.colb[c] >= 0) r = 0.0;
+                    else if (!w_given) r = 1.0;
+                    else r = (fabs(v) >= kEps) ? 1.0 / v : 0.0;
+                    xs[j] = r;
+                }
+            }
+            __syncthreads();
+            if (tid < PF_CH && c0 + tid < W) xo[c0 + tid] = xs[tid];
+            // ---- histogram half
+#pragma unroll
+            for (int half = 0; half < PF_CH / 32; ++half) {
+                const int jl = half * 32 + lane;
+                const int c = c0 + jl;
+                const int lv_l = (c < W) ? (int)Lrow[c] : 0;
+                const bool mine = (c < W) && ((lv_l & 15) == warp) && (xs[jl] != 0.0);
+                unsigned m = __ballot_sync(0xffffffffu, mine);
+                while (m) {
+                    const int j = __ffs(m) - 1;
+                    m &= m - 1;
+                    const int lv = __shfl_sync(0xffffffffu, lv_l, j);
+                    const double xv = xs[half * 32 + j];
+                    const double* ec = stage + (half * 32 + j) * nC;
+                    double* h = Hs + (size_t)lv * nCp;
+                    for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+                }
+            }
+        }
+        __syncthreads();
+        for (int e = tid; e < nC * NL; e += PF_THREADS) fh[e] = Hs[(e & (NL - 1)) * nCp + (e >> 8)];
+    }
+}
+
 // Mpart[ks][b][a][l] = sum_{row in split ks} Er[row][a] * Hx[row][b][l].
 // grid (nC, nks, nab), 256 threads; warp w owns levels [32w, 32w+32) (4 n-tiles) for MT m-tiles of grid rows.
 template <int MT>
@@ -244,7 +344,8 @@ sk_reduce_final_kernel(AffinityTables t, const double* __restrict__ Mpart, int n
 
 struct SkGeom {
     int nRp, MT, nab, nks;
-    size_t fh_doubles, mpart_doubles, pix_smem, dot_smem;
+    size_t fh_doubles, mpart_doubles, pix_smem, pixf_smem, dot_smem;
+    bool fused;
 };
 
 SkGeom sk_geometry(const AffinityTables& t) {
@@ -259,6 +360,8 @@ SkGeom sk_geometry(const AffinityTables& t) {
     g.mpart_doubles = (size_t)g.nks * t.nC * g.nRp * NL;
     const int nCp = t.nC | 1;
     g.pix_smem = ((size_t)NL * nCp + 32 * (size_t)t.nC + t.cols) * sizeof(double) + ((t.cols + 15) / 16) * 16 + 64;
+    g.pixf_smem = ((size_t)2 * NL * nCp + (size_t)PF_CH * t.nC + PF_CH) * sizeof(double) + ((t.cols + 15) / 16) * 16 + 64;
+    g.fused = g.pixf_smem <= 227 * 1024 && PF_CH * t.nC <= PF_THREADS * PF_NPF && t.nC <= 64;
     const int nR4 = (t.nR + 3) & ~3;
     const int lda = nR4 + ((12 - (nR4 & 15)) & 15);
     g.dot_smem = ((size_t)DG_ROWS * lda + NL + nR4) * sizeof(double) + (size_t)nR4 * sizeof(int) + 64;
@@ -269,7 +372,7 @@ SkGeom sk_geometry(const AffinityTables& t) {
 
 bool sinkhorn_cells_supported(const AffinityTables& t) {
     const SkGeom g = sk_geometry(t);
-    return g.pix_smem <= 227 * 1024 && g.dot_smem <= 227 * 1024;
+    return (g.fused || g.pix_smem <= 227 * 1024) && g.dot_smem <= 227 * 1024;
 }
 
 size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t) {
@@ -289,8 +392,14 @@ void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, 
     const SkGeom g = sk_geometry(t);
     double* FH = scratch;
     double* Mpart = FH + g.fh_doubles;
-    static size_t conf_pix = 0, conf_dot = 0;
-    if (g.pix_smem > conf_pix) {
+    static size_t conf_pix = 0, conf_dot = 0, conf_pixf = 0;
+    static const bool unfused_env = getenv("NLE_B200_SK_UNFUSED") != nullptr;
+    const bool fused = g.fused && !unfused_env;
+    if (fused && g.pixf_smem > conf_pixf) {
+        NLE_CUDA(cudaFuncSetAttribute(sk_pix_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pixf_smem));
+        conf_pixf = g.pixf_smem;
+    }
+    if (!fused && g.pix_smem > conf_pix) {
         NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
         conf_pix = g.pix_smem;
     }
@@ -302,7 +411,8 @@ void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, 
         sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH);
         NLE_LAUNCH_CHECK();
     }
-    sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
+    if (fused) sk_pix_fused_kernel<<<t.nrows, PF_THREADS, g.pixf_smem, s>>>(t, w ? 1 : 0, x, FH);
+    else sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
     NLE_LAUNCH_CHECK();
     switch (g.MT) {
         case 1: launch_rg<1>(t, g, FH, Mpart, s); break;
