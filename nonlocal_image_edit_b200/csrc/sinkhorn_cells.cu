@@ -250,14 +250,39 @@ sk_pix_fused_kernel(AffinityTables t, int w_given, double* __restrict__ x, doubl
                 const int lv_l = (c < W) ? (int)Lrow[c] : 0;
                 const bool mine = (c < W) && ((lv_l & 15) == warp) && (xs[jl] != 0.0);
                 unsigned m = __ballot_sync(0xffffffffu, mine);
+                // two pixels in flight when their levels (bins) differ: the update is a dependent LDS-DFMA-STS chain
                 while (m) {
-                    const int j = __ffs(m) - 1;
+                    const int j0 = __ffs(m) - 1;
                     m &= m - 1;
-                    const int lv = __shfl_sync(0xffffffffu, lv_l, j);
-                    const double xv = xs[half * 32 + j];
-                    const double* ec = stage + (half * 32 + j) * nC;
-                    double* h = Hs + (size_t)lv * nCp;
-                    for (int b = lane; b < nC; b += 32) h[b] = fma(ec[b], xv, h[b]);
+                    const int lv0 = __shfl_sync(0xffffffffu, lv_l, j0);
+                    int j1 = -1, lv1 = 0;
+                    if (m) {
+                        j1 = __ffs(m) - 1;
+                        lv1 = __shfl_sync(0xffffffffu, lv_l, j1);
+                        if (lv1 != lv0) m &= m - 1; else j1 = -1;
+                    }
+                    const double xv0 = xs[half * 32 + j0];
+                    const double* ec0 = stage + (half * 32 + j0) * nC;
+                    double* h0 = Hs + (size_t)lv0 * nCp;
+                    const bool tail = lane + 32 < nC;
+                    if (j1 >= 0) {
+                        const double xv1 = xs[half * 32 + j1];
+                        const double* ec1 = stage + (half * 32 + j1) * nC;
+                        double* h1 = Hs + (size_t)lv1 * nCp;
+                        if (lane < nC) {
+                            const double e0 = ec0[lane], g0 = h0[lane], e1 = ec1[lane], g1 = h1[lane];
+                            h0[lane] = fma(e0, xv0, g0);
+                            h1[lane] = fma(e1, xv1, g1);
+                        }
+                        if (tail) {
+                            const double e0 = ec0[lane + 32], g0 = h0[lane + 32], e1 = ec1[lane + 32], g1 = h1[lane + 32];
+                            h0[lane + 32] = fma(e0, xv0, g0);
+                            h1[lane + 32] = fma(e1, xv1, g1);
+                        }
+                    } else {
+                        if (lane < nC) h0[lane] = fma(ec0[lane], xv0, h0[lane]);
+                        if (tail) h0[lane + 32] = fma(ec0[lane + 32], xv0, h0[lane + 32]);
+                    }
                 }
             }
         }
