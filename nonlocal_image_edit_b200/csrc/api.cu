@@ -439,7 +439,13 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     scale_rows_cols(r, k, Mv.p, r, rsel.p, nullptr, RM.p, r, s);
     dgemm(true, false, r, k, r, 1.0, U.p, p, RM.p, r, 0.0, Y1.p, r, s);
     dgemm(false, false, p, k, r, 1.0, U.p, p, Y1.p, r, 0.0, Y.p, p, s);
-    launch_extension(tb, cfull.p, Y.p, k, f->V.p, s);
+    static const bool ext_pixel_env = [] { const char* e = getenv("NLE_B200_EXT"); return e && std::string(e) == "pixel"; }();
+    if (ext_pixel_env) {
+        launch_extension(tb, cfull.p, Y.p, k, f->V.p, s);
+    } else {
+        TmpBuf<double> xscratch(extension_cells_scratch_doubles(tb, k));
+        launch_extension_cells(tb, cfull.p, Y.p, k, xscratch.p, f->V.p, s);
+    }
     NLE_CUDA(cudaStreamSynchronize(s));
     f->times_ms[5] = t_ext.stop();
     tr("extension");

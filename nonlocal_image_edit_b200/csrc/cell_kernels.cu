@@ -22,6 +22,9 @@
 //                      registers (one table look-up and one or two multiplies per element), no shared-memory
 //                      tiles, no block barriers in the main loop
 //   gram_cells_reduce_kernel  fixed-order sum over the K splits, mirrored into both triangles of G
+//
+// The eigenvector extension (filter.cpp:324-327 in factor form) uses the same cells, see the second half of
+// this file:  V_j = c_j sum_b Ec[col_j][b] FX[cell(j)][b][:],   FX[cell][b][:] = sum_a Er[row][a] Gt[|l-Y_ab|] Y[(a,b),:].
 #include <algorithm>
 #include <cstdlib>
 
@@ -377,6 +380,215 @@ CellGeom cell_geometry(const AffinityTables& t) {
     return g;
 }
 
+// =============================================================================================
+// Eigenvector extension through cells.
+//
+//   ext_index_kernel   per image row: level list, stable counting sort of the columns by level; writes for every
+//                      cell its level, image row, first position in the row's sorted column list and pixel count
+//   ext_fx_kernel      FX[cell][b][m] = sum_a (Er[row][a] Gt[|l-Y_ab|]) * Y[(a,b)][m]      DMMA, K = nR
+//                      (cells x nR) * (nR x 56) per grid column b and 56-column block of Y
+//   ext_pix_kernel     one warp per (cell, column block): V[pixel][m] = c_j * sum_b Ec[col_j][b] FX[cell][b][m]
+//                      DMMA with the cell's pixels (8 at a time) as the M tile, K = nC; FX is streamed once
+// Work: K_cells*p*k' + N*nC*k' multiply-adds instead of N*p*k' (extension_dmma_kernel).
+constexpr int XC_N = 56;          // eigenvector columns per block (7 DMMA n-tiles)
+constexpr int XC_CELLS = 256;     // cells per CTA of ext_fx_kernel (8 warps x 4 m-tiles)
+
+__global__ void __launch_bounds__(256)
+ext_index_kernel(const uint8_t* __restrict__ lum, int nrows, int W, const int* __restrict__ koff,
+                 uint8_t* __restrict__ cell_lev, int* __restrict__ cell_row, int* __restrict__ cell_pstart,
+                 int* __restrict__ cell_pcount, int* __restrict__ sorted) {
+    extern __shared__ int ism[];
+    int* flags = ism;              // 256
+    int* levidx = flags + 256;     // 256
+    int* lev = levidx + 256;       // 256
+    int* cstart = lev + 256;       // 260
+    int* wcount = cstart + 260;    // 8
+    uint8_t* Lrow = reinterpret_cast<uint8_t*>(wcount + 8);   // W
+    const int tid = threadIdx.x;
+    for (int rl = blockIdx.x; rl < nrows; rl += gridDim.x) {
+        __syncthreads();
+        const uint8_t* Lg = lum + (size_t)rl * W;
+        for (int c = tid; c < W; c += 256) Lrow[c] = Lg[c];
+        __syncthreads();
+        const int nlev = row_levels(Lrow, W, flags, levidx, lev, wcount);
+        const int npad = (nlev + 3) & ~3;
+        const int k0 = koff[rl];
+        if (tid < nlev) {
+            const int lv = lev[tid];
+            int n = 0;
+            for (int c = 0; c < W; ++c) n += (Lrow[c] == lv);
+            flags[tid] = n;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int run = 0;
+            for (int li = 0; li < nlev; ++li) { cstart[li] = run; run += flags[li]; }
+            cstart[nlev] = run;
+        }
+        __syncthreads();
+        if (tid < nlev) {
+            const int lv = lev[tid];
+            int pos = cstart[tid];
+            int* so = sorted + (size_t)rl * W;
+            for (int c = 0; c < W; ++c)
+                if (Lrow[c] == lv) so[pos++] = c;
+        }
+        if (tid < npad) {
+            const bool real = tid < nlev;
+            cell_lev[k0 + tid] = (uint8_t)(real ? lev[tid] : 0);
+            cell_row[k0 + tid] = rl;
+            cell_pstart[k0 + tid] = rl * W + (real ? cstart[tid] : 0);
+            cell_pcount[k0 + tid] = real ? flags[tid] : 0;
+        }
+    }
+}
+
+// grid (ceil(cap_cells / 256), nC, column blocks); warp = 32 cells (4 m-tiles) x 56 columns (7 n-tiles).
+__global__ void __launch_bounds__(256, 1)
+ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __restrict__ cell_lev,
+              const int* __restrict__ cell_row, const double* __restrict__ Yt, int kp, double* __restrict__ FX) {
+    extern __shared__ double xsm[];
+    const int nR = t.nR, nC = t.nC;
+    const int nR4 = (nR + 3) & ~3;
+    double* Ys = xsm;                                  // nR4 * XC_N   slice of Y for grid column b
+    double* Gs = Ys + (size_t)nR4 * XC_N;              // 256
+    int* ysl = reinterpret_cast<int*>(Gs + 256);       // nR4          sample luminances of grid column b
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int b = blockIdx.y, vb = blockIdx.z;
+    const int K = koff[t.nrows];
+    const int k0 = blockIdx.x * XC_CELLS;
+    if (k0 >= K) return;
+    Gs[tid] = t.Gt[tid];
+    for (int e = tid; e < nR4 * XC_N; e += 256) {
+        const int a = e / XC_N, m = e - a * XC_N;
+        Ys[e] = a < nR ? Yt[(size_t)(a * nC + b) * kp + vb * XC_N + m] : 0.0;
+    }
+    for (int a = tid; a < nR4; a += 256) ysl[a] = a < nR ? (int)t.Ysel[a * nC + b] : 0;
+    __syncthreads();
+    const int kw = k0 + warp * 32;
+    if (kw >= K) return;
+    int crow[4], clev[4];
+    bool cok[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int cell = kw + 8 * u + g;
+        cok[u] = cell < K;
+        crow[u] = cok[u] ? cell_row[cell] : 0;
+        clev[u] = cok[u] ? (int)cell_lev[cell] : 0;
+    }
+    double acc[4][7][2];
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+        for (int v = 0; v < 7; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    for (int kk = 0; kk < nR4; kk += 4) {
+        const int a = kk + tq;
+        const int ya = ysl[a];
+        double af[4], bf[7];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int d = clev[u] - ya;
+            const double er = (cok[u] && a < nR) ? t.Er[(size_t)(t.row0 + crow[u]) * nR + a] : 0.0;
+            af[u] = er * Gs[d < 0 ? -d : d];
+        }
+#pragma unroll
+        for (int v = 0; v < 7; ++v) bf[v] = Ys[a * XC_N + 8 * v + g];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+            for (int v = 0; v < 7; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+        const int cell = kw + 8 * u + g;
+        if (cell >= K) continue;
+        double* o = FX + ((size_t)cell * nC + b) * kp + vb * XC_N + 2 * tq;
+#pragma unroll
+        for (int v = 0; v < 7; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
+}
+
+// One warp per (cell, column block), grid-stride.
+__global__ void __launch_bounds__(256)
+ext_pix_kernel(AffinityTables t, const int* __restrict__ koff, const int* __restrict__ cell_row,
+               const int* __restrict__ cell_pstart, const int* __restrict__ cell_pcount,
+               const int* __restrict__ sorted, const double* __restrict__ cvec, const double* __restrict__ FX,
+               int kp, int nvb, int k, double* __restrict__ V) {
+    const int nC = t.nC, W = t.cols;
+    const int nC4 = (nC + 3) & ~3;
+    const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const long long K = koff[t.nrows];
+    const long long nwork = K * nvb;
+    const long long wstride = (long long)gridDim.x * (blockDim.x >> 5);
+    for (long long wi = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); wi < nwork; wi += wstride) {
+        const int cell = (int)(wi / nvb), vb = (int)(wi - (long long)cell * nvb);
+        const int np = cell_pcount[cell];
+        if (np == 0) continue;
+        const int rl = cell_row[cell];
+        const int* pix = sorted + cell_pstart[cell];
+        const double* fx = FX + (size_t)cell * nC * kp + vb * XC_N + g;
+        for (int p0 = 0; p0 < np; p0 += 8) {
+            const bool pok = p0 + g < np;
+            const int col = pok ? pix[p0 + g] : 0;
+            const double* ec = t.Ec + (size_t)col * nC;
+            double acc[7][2];
+#pragma unroll
+            for (int v = 0; v < 7; ++v) acc[v][0] = acc[v][1] = 0.0;
+            for (int kk = 0; kk < nC4; kk += 4) {
+                const int b = kk + tq;
+                const bool bok = b < nC;
+                const double af = (pok && bok) ? ec[b] : 0.0;
+                double bf[7];
+                const double* f = fx + (size_t)b * kp;
+#pragma unroll
+                for (int v = 0; v < 7; ++v) bf[v] = bok ? f[8 * v] : 0.0;
+#pragma unroll
+                for (int v = 0; v < 7; ++v) dmma884(acc[v][0], acc[v][1], af, bf[v]);
+            }
+            if (!pok) continue;
+            if (t.rowa[t.row0 + rl] >= 0 && t.colb[col] >= 0) continue;      // sample pixel: scattered separately
+            const size_t j = (size_t)rl * W + col;
+            const double cj = cvec[j];
+            double* vo = V + j * k;
+#pragma unroll
+            for (int v = 0; v < 7; ++v) {
+                const int m = vb * XC_N + 8 * v + 2 * tq;
+                if (m < k) vo[m] = cj * acc[v][0];
+                if (m + 1 < k) vo[m + 1] = cj * acc[v][1];
+            }
+        }
+    }
+}
+
+__global__ void ext_pack_yt_kernel(const double* __restrict__ Y, int p, int k, int kp, double* __restrict__ Yt) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)p * kp) return;
+    const int i = (int)(e / kp), v = (int)(e - (long long)i * kp);
+    Yt[e] = (v < k) ? Y[i + (size_t)v * p] : 0.0;
+}
+
+struct ExtGeom {
+    int nvb, kp, capc, rows_batch;
+    size_t fx_doubles, yt_doubles, int_count, lev_bytes;
+};
+
+ExtGeom ext_geometry(const AffinityTables& t, int k) {
+    ExtGeom g;
+    g.nvb = cdiv(k, XC_N);
+    g.kp = g.nvb * XC_N;
+    g.capc = std::min(256, (t.cols + 3) & ~3);
+    const size_t per_row = (size_t)g.capc * t.nC * g.kp;                 // worst case: capc cells in every row
+    const size_t budget = (size_t)1 << 30;                               // doubles (8 GB) per batch of rows
+    g.rows_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)t.nrows, budget / per_row));
+    g.fx_doubles = per_row * g.rows_batch;
+    g.yt_doubles = (size_t)t.p * g.kp;
+    const size_t cells = (size_t)g.capc * g.rows_batch;
+    g.int_count = 2 * (size_t)g.rows_batch + 8 + 3 * cells + (size_t)g.rows_batch * t.cols;
+    g.lev_bytes = cells;
+    return g;
+}
+
 }  // namespace
 
 size_t gram_cells_scratch_doubles(const AffinityTables& t) {
@@ -430,6 +642,57 @@ void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch
     gram_cells_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(part, t.p, t.nR, t.nC, g.T, g.nab, g.ntasks,
                                                                        g.nsplit, G);
     NLE_LAUNCH_CHECK();
+}
+
+size_t extension_cells_scratch_doubles(const AffinityTables& t, int k) {
+    const ExtGeom g = ext_geometry(t, k);
+    return g.fx_doubles + g.yt_doubles + (g.lev_bytes + 7) / 8 + (g.int_count * 4 + 7) / 8 + 16;
+}
+
+// V_j = c_j k_j^T Y for the non-sample slab pixels (same contract as launch_extension).
+void launch_extension_cells(const AffinityTables& t, const double* c, const double* Y, int k, double* scratch, double* V,
+                            cudaStream_t s) {
+    if (k <= 0 || t.nrows <= 0) return;
+    const ExtGeom g = ext_geometry(t, k);
+    double* FX = scratch;
+    double* Yt = FX + g.fx_doubles;
+    uint8_t* cell_lev = reinterpret_cast<uint8_t*>(Yt + g.yt_doubles);
+    int* cnt = reinterpret_cast<int*>(cell_lev + ((g.lev_bytes + 7) / 8) * 8);
+    int* koff = cnt + g.rows_batch + 4;
+    const size_t cells = (size_t)g.capc * g.rows_batch;
+    int* cell_row = koff + g.rows_batch + 4;
+    int* cell_pstart = cell_row + cells;
+    int* cell_pcount = cell_pstart + cells;
+    int* sorted = cell_pcount + cells;
+    ext_pack_yt_kernel<<<cdiv((long long)t.p * g.kp, 256), 256, 0, s>>>(Y, t.p, k, g.kp, Yt);
+    NLE_LAUNCH_CHECK();
+    const size_t ism = (size_t)(256 * 3 + 260 + 8) * sizeof(int) + ((t.cols + 15) / 16) * 16 + 16;
+    const int nR4 = (t.nR + 3) & ~3;
+    const size_t fsm = ((size_t)nR4 * XC_N + 256) * sizeof(double) + (size_t)nR4 * sizeof(int) + 16;
+    if (ism > 227 * 1024 || fsm > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
+    static size_t conf_i = 0, conf_f = 0;
+    if (ism > conf_i) { NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism)); conf_i = ism; }
+    if (fsm > conf_f) { NLE_CUDA(cudaFuncSetAttribute(ext_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)); conf_f = fsm; }
+    for (int r0 = 0; r0 < t.nrows; r0 += g.rows_batch) {
+        AffinityTables tb = t;
+        tb.row0 = t.row0 + r0;
+        tb.nrows = std::min(g.rows_batch, t.nrows - r0);
+        tb.lum = t.lum + (size_t)r0 * t.cols;
+        const double* cb = c + (size_t)r0 * t.cols;
+        double* Vb = V + (size_t)r0 * t.cols * k;
+        cell_count_kernel<<<std::min(tb.nrows, sm_count() * 8), 256, 0, s>>>(tb.lum, tb.nrows, tb.cols, cnt);
+        NLE_LAUNCH_CHECK();
+        cell_scan_kernel<<<1, 1024, 0, s>>>(cnt, tb.nrows, koff);
+        NLE_LAUNCH_CHECK();
+        ext_index_kernel<<<std::min(tb.nrows, sm_count() * 8), 256, ism, s>>>(tb.lum, tb.nrows, tb.cols, koff, cell_lev, cell_row,
+                                                                             cell_pstart, cell_pcount, sorted);
+        NLE_LAUNCH_CHECK();
+        const int cap_cells = g.capc * tb.nrows;
+        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS), t.nC, g.nvb), 256, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX);
+        NLE_LAUNCH_CHECK();
+        ext_pix_kernel<<<sm_count() * 8, 256, 0, s>>>(tb, koff, cell_row, cell_pstart, cell_pcount, sorted, cb, FX, g.kp, g.nvb, k, Vb);
+        NLE_LAUNCH_CHECK();
+    }
 }
 
 }  // namespace nle

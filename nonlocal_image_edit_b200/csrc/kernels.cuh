@@ -61,6 +61,10 @@ void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch
 // V: (nrows*cols) x k ROW-major (k fastest).
 void launch_extension(const AffinityTables& t, const double* c, const double* Y, int k, double* V,
                       cudaStream_t s);
+// Same extension through (image row, luminance level) cells (cell_kernels.cu): K_cells*p*k + N*nC*k multiply-adds.
+size_t extension_cells_scratch_doubles(const AffinityTables& t, int k);
+void launch_extension_cells(const AffinityTables& t, const double* c, const double* Y, int k, double* scratch, double* V,
+                            cudaStream_t s);
 // V[pixel(sel[i0+i]) - slab offset][:] = src(i, :)  for samples that fall in the slab.  src: n x k col-major (ld).
 void launch_scatter_rows(const AffinityTables& t, const int32_t* sel, int i0, int n, const double* src,
                          int ld, int k, double* V, cudaStream_t s);
