@@ -297,16 +297,12 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     guarded_reciprocal(inv_lam.p, r, kEps, s);            // filter.cpp:265-266
     // t = phi^T x = U_r^T x_sel + Lam^-1 U_r^T (Kab x_rest)
     auto phiT_x = [&](const double* x_sel, const double* s_vec) {
-        dgemv_t(p, r, U.p, p, x_sel, tvec.p, s);
-        dgemv_t(p, r, U.p, p, s_vec, t2.p, s);
-        vec_axpy(tvec.p, t2.p, inv_lam.p, r, s);          // tvec += inv_lam o t2
+        sk_phiT(p, r, U.p, p, x_sel, s_vec, inv_lam.p, tvec.p, s);
     };
     // one half-step: x = recip(K~ applied to the vector whose phi^T image is tvec)
     auto half_step = [&](double* x_sel_out, bool need_rest) {
-        dgemv_n(p, r, U.p, p, tvec.p, wvec.p, s);          // w = U_r t       (rest pixels: k_j^T w)
-        vec_mul(lt.p, lam.p, tvec.p, r, s);                // Lam t
-        dgemv_n(p, r, U.p, p, lt.p, x_sel_out, s);         // samples: U[s,:] Lam t
-        guarded_reciprocal(x_sel_out, p, kEps, s);
+        // w = U_r t (rest pixels: k_j^T w) and, for the samples, recip(U[s,:] Lam t) in one pass over U
+        sk_sample_step(p, r, U.p, p, tvec.p, lam.p, kEps, wvec.p, x_sel_out, s);
         if (need_rest) {
             if (sk_cells) launch_sinkhorn_cells(tb, wvec.p, xfull.p, skscratch.p, svec.p, s);
             else launch_pass_fused(tb, wvec.p, xfull.p, spart.p, svec.p, s);

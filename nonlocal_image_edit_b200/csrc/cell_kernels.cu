@@ -291,13 +291,25 @@ gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t*
     const double* gs = Gs16 + (lane & 15);
     const double* hp = Hh + pair;
 
+    // levels and Hh values of 32 cells per lane-load, fetched one block ahead of their use (the HBM round trip of
+    // the Hh stream is ~3 blocks of DMMA work for the two warps of a sub-core)
+    int lv_next = 0;
+    double hh_next = 0.0;
+    if (k + lane < kend) {
+        lv_next = (int)cell_lev[k + lane];
+        hh_next = hp[(size_t)(k + lane) * ld];
+    }
     while (k < kend) {
-        const int kk = k + lane;
-        int lv32 = 0;
-        double hh32 = 0.0;
-        if (kk < kend) {
-            lv32 = (int)cell_lev[kk];
-            hh32 = hp[(size_t)kk * ld];
+        const int lv32 = lv_next;
+        const double hh32 = hh_next;
+        {
+            const int kn = k + 32 + lane;
+            lv_next = 0;
+            hh_next = 0.0;
+            if (kn < kend) {
+                lv_next = (int)cell_lev[kn];
+                hh_next = hp[(size_t)kn * ld];
+            }
         }
 #pragma unroll
         for (int i = 0; i < 8; ++i) {

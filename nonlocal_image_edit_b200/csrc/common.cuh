@@ -122,6 +122,11 @@ void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const do
 // y(m) = A(m x n) x        /  y(n) = A(m x n)^T x
 void dgemv_n(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s);
 void dgemv_t(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s);
+// Fused Sinkhorn sample-side steps (dense.cu): w = U t and xs = recip(U (lam o t)) in one pass; t = U^T x + inv_lam o (U^T sv).
+void sk_sample_step(int m, int n, const double* U, int ldu, const double* t, const double* lam, double eps, double* w,
+                    double* xs, cudaStream_t s);
+void sk_phiT(int m, int n, const double* U, int ldu, const double* x, const double* sv, const double* inv_lam, double* t,
+             cudaStream_t s);
 // out(i,j) = rowscale[i] * A(i,j) * colscale[j]   (either scale may be null)
 void scale_rows_cols(int m, int n, const double* A, int lda, const double* rowscale,
                      const double* colscale, double* out, int ldo, cudaStream_t s);

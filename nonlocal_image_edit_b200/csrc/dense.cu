@@ -221,6 +221,89 @@ __global__ void dgemv_t_kernel(int m, int n, const double* __restrict__ A, int l
     if (lane == 0) y[warp] = acc;
 }
 
+// Sinkhorn half-step, sample side, one pass over U instead of two dgemv_n + two vector kernels:
+//   w[i]  = sum_j U[i,j] t[j]                               (rest pixels use k_j^T w)
+//   xs[i] = recip( sum_j U[i,j] (lam[j] t[j]) )             (samples: U[s,:] Lam t, inplaceReciprocal filter.cpp:42-54)
+// Same column phases and summation order as dgemv_n_kernel.
+__global__ void __launch_bounds__(GV_WARPS * 32)
+sk_sample_step_kernel(int m, int n, const double* __restrict__ A, int lda, const double* __restrict__ t,
+                      const double* __restrict__ lam, double eps, double* __restrict__ w, double* __restrict__ xs) {
+    __shared__ double part[2][GV_WARPS * 2][GV_ROWS + 1];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = lane & 15, half = lane >> 4;
+    const int i = blockIdx.x * GV_ROWS + r;
+    const int slot = warp * 2 + half;
+    double acc0 = 0.0, acc1 = 0.0;
+    if (i < m) {
+        const double* a = A + i;
+        int j = slot;
+        for (; j + 3 * 32 < n; j += 4 * 32) {
+            const double a0 = a[(size_t)j * lda], a1 = a[(size_t)(j + 32) * lda];
+            const double a2 = a[(size_t)(j + 64) * lda], a3 = a[(size_t)(j + 96) * lda];
+            const double t0 = t[j], t1 = t[j + 32], t2 = t[j + 64], t3 = t[j + 96];
+            acc0 = fma(a0, t0, acc0); acc1 = fma(a0, lam[j] * t0, acc1);
+            acc0 = fma(a1, t1, acc0); acc1 = fma(a1, lam[j + 32] * t1, acc1);
+            acc0 = fma(a2, t2, acc0); acc1 = fma(a2, lam[j + 64] * t2, acc1);
+            acc0 = fma(a3, t3, acc0); acc1 = fma(a3, lam[j + 96] * t3, acc1);
+        }
+        for (; j < n; j += 32) {
+            const double a0 = a[(size_t)j * lda], t0 = t[j];
+            acc0 = fma(a0, t0, acc0);
+            acc1 = fma(a0, lam[j] * t0, acc1);
+        }
+    }
+    part[0][slot][r] = acc0;
+    part[1][slot][r] = acc1;
+    __syncthreads();
+    if (threadIdx.x < 2 * GV_ROWS) {
+        const int which = threadIdx.x / GV_ROWS, rr = threadIdx.x % GV_ROWS;
+        const int ii = blockIdx.x * GV_ROWS + rr;
+        if (ii < m) {
+            double sum = 0.0;
+#pragma unroll
+            for (int q = 0; q < GV_WARPS * 2; ++q) sum += part[which][q][rr];
+            if (which == 0) w[ii] = sum;
+            else xs[ii] = (fabs(sum) >= eps) ? 1.0 / sum : 0.0;
+        }
+    }
+}
+
+// t[j] = sum_i U[i,j] x[i] + inv_lam[j] * sum_i U[i,j] s[i]     (phi^T x in factor form): one pass over U instead of
+// two dgemv_t + an axpy; same summation order as dgemv_t_kernel.
+__global__ void sk_phiT_kernel(int m, int n, const double* __restrict__ A, int lda, const double* __restrict__ x,
+                               const double* __restrict__ sv, const double* __restrict__ inv_lam, double* __restrict__ t) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= n) return;
+    const double* col = A + (size_t)warp * lda;
+    double acc0 = 0.0, acc1 = 0.0;
+    for (int i = lane; i < m; i += 32) {
+        const double a = col[i];
+        acc0 = fma(a, x[i], acc0);
+        acc1 = fma(a, sv[i], acc1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
+        acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
+    }
+    if (lane == 0) t[warp] = fma(inv_lam[warp], acc1, acc0);
+}
+
+void sk_sample_step(int m, int n, const double* U, int ldu, const double* t, const double* lam, double eps, double* w,
+                    double* xs, cudaStream_t s) {
+    if (m <= 0) return;
+    sk_sample_step_kernel<<<cdiv(m, GV_ROWS), GV_WARPS * 32, 0, s>>>(m, n, U, ldu, t, lam, eps, w, xs);
+    NLE_LAUNCH_CHECK();
+}
+
+void sk_phiT(int m, int n, const double* U, int ldu, const double* x, const double* sv, const double* inv_lam, double* t,
+             cudaStream_t s) {
+    if (n <= 0) return;
+    sk_phiT_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(m, n, U, ldu, x, sv, inv_lam, t);
+    NLE_LAUNCH_CHECK();
+}
+
 void dgemv_n(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s) {
     if (m <= 0) return;
     dgemv_n_kernel<<<cdiv(m, GV_ROWS), GV_WARPS * 32, 0, s>>>(m, n, A, lda, x, y);
