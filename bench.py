@@ -54,6 +54,16 @@ def synth_luminance(rows, cols, seed=1234):
     return np.clip(np.rint(img), 0, 255).astype(np.uint8)
 
 
+def workload_images(rows, cols):
+    """The bench workload as the reference's CLI sees it: the S-gray image in 3 equal BGR channels, and the L channel of
+    its 8-bit BGR2Lab conversion (what getLuminanceChannel, filter.cpp:460-469, feeds the filter).  Host OpenCV, setup only."""
+    import cv2
+    gray = synth_luminance(rows, cols)
+    bgr = np.ascontiguousarray(np.repeat(gray[:, :, None], 3, axis=2))
+    lum = np.ascontiguousarray(cv2.cvtColor(bgr, cv2.COLOR_BGR2Lab)[:, :, 0])
+    return bgr, lum
+
+
 def nproc_used():
     try:
         return len(os.sched_getaffinity(0))
@@ -129,7 +139,7 @@ def cpu_sample_desc():
 def run_reference(args, rank, world):
     if rank != 0:
         return
-    lum = synth_luminance(BASE_ROWS, COLS)[:CPU_CROP, :CPU_CROP].copy()
+    lum = workload_images(BASE_ROWS, COLS)[1][:CPU_CROP, :CPU_CROP].copy()
     for _ in range(args.warmup):
         cpu_step(lum)
     t0 = time.perf_counter()
@@ -151,7 +161,7 @@ def run_reference(args, rank, world):
 
 
 def workload_config(n):
-    return {"workload": f"synthetic {BASE_ROWS * n}x{COLS} 8-bit luminance (S-gray generator, seed 1234), "
+    return {"workload": f"synthetic {BASE_ROWS * n}x{COLS} gray image (S-gray generator, seed 1234) in 3 equal BGR channels, L of 8-bit BGR2Lab, "
                         f"{GRID[0]}x{GRID[1]}=1600 Nystrom samples, hx={HX:g} hy={HY:g}, T={T_SINK} Sinkhorn iters, "
                         f"k={K_EIG}, weights {WEIGHTS}",
             "baseline_config": "BASELINE.json configs[2]",
@@ -159,7 +169,8 @@ def workload_config(n):
             "parallelism": f"row-sharded x{n}" if n > 1 else "single GPU",
             "l2_policy": "each step streams >1.5 GB of scratch (per-cell histograms, Gram partials, V) through the 126 MB L2; "
                          "inputs are re-uploaded / re-read every step",
-            "lab_conversion": "L channel fed directly to the C ABI; BGR<->Lab stays in host OpenCV as in the reference"}
+            "lab_conversion": "gray image as 3 equal BGR channels; value: L = 8-bit BGR2Lab resident in HBM; e2e: BGR in/out, "
+                              "BGR<->Lab on the device (byte-exact with cv::cvtColor)"}
 
 
 # ---- B200 arm -----------------------------------------------------------------------------------
@@ -177,7 +188,14 @@ def run_b200(args, rank, world, local_rank):
         dist.init_process_group("nccl", device_id=dev)
 
     rows = BASE_ROWS * world
-    lum = synth_luminance(rows, COLS)
+    # the workload as the reference's CLI sees it: a gray image in 3 equal BGR channels; the filter's input is the L
+    # channel of its 8-bit BGR2Lab conversion (filter.cpp:463-466).  The device-resident arm is fed that L channel, the
+    # e2e arm the BGR image itself (colour conversion on the device, byte-exact with cv::cvtColor: csrc/lab.cu).
+    bgr, lum = workload_images(rows, COLS)
+    lab_dev = np.empty_like(bgr)
+    _lib.check(lib.nle_b200_bgr_to_lab_u8(C.c_void_p(bgr.ctypes.data), rows * COLS, C.c_void_p(lab_dev.ctypes.data)))
+    assert np.array_equal(lab_dev[:, :, 0], lum), "device BGR2Lab differs from cv2"
+    del lab_dev
     row0, row1 = rank * BASE_ROWS, (rank + 1) * BASE_ROWS
     nloc = (row1 - row0) * COLS
     weights = (C.c_double * len(WEIGHTS))(*WEIGHTS)
@@ -209,8 +227,8 @@ def run_b200(args, rank, world, local_rank):
             return 1
     cb = _lib.ALLREDUCE_FN(allreduce) if world > 1 else C.cast(None, _lib.ALLREDUCE_FN)
 
-    pinned_in = torch.from_numpy(lum).pin_memory()
-    pinned_out = torch.empty(nloc, dtype=torch.uint8).pin_memory()
+    pinned_in = torch.from_numpy(bgr).pin_memory()
+    pinned_out = torch.empty(nloc * 3, dtype=torch.uint8).pin_memory()
     d_slab = torch.from_numpy(lum[row0:row1].copy()).to(dev)
     d_out = torch.empty(nloc, dtype=torch.uint8, device=dev)
 
@@ -225,10 +243,11 @@ def run_b200(args, rank, world, local_rank):
 
     def step_host():
         h = C.c_void_p()
-        _lib.check(lib.nle_b200_train_u8_sharded(C.c_void_p(pinned_in.data_ptr()), rows, COLS, row0, row1, GRID[0], GRID[1],
-                                                 HX, HY, T_SINK, K_EIG, cb, None, C.byref(h)))
-        _lib.check(lib.nle_b200_enhance_luminance_u8(h, C.c_void_p(pinned_in.data_ptr() + row0 * COLS), weights,
-                                                     len(WEIGHTS), C.c_void_p(pinned_out.data_ptr())))
+        # trainForEnhancement(BGR) + enhance(BGR) -> BGR, host buffers in and out (filter.cpp:514-519, 412-443)
+        _lib.check(lib.nle_b200_train_bgr_u8(C.c_void_p(pinned_in.data_ptr()), rows, COLS, row0, row1, GRID[0], GRID[1],
+                                             HX, HY, T_SINK, K_EIG, cb, None, C.byref(h)))
+        _lib.check(lib.nle_b200_enhance_bgr_u8(h, C.c_void_p(pinned_in.data_ptr() + 3 * row0 * COLS), weights,
+                                               len(WEIGHTS), C.c_void_p(pinned_out.data_ptr())))
         return h
 
     def barrier():
@@ -339,8 +358,9 @@ def run_b200(args, rank, world, local_rank):
         "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(world),
-        "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(nloc + ys.size) * world,
-                "d2h_bytes_per_step": int(nloc) * world, "ms_per_step": ms_host / args.steps},
+        "e2e": {"value": e2e_val, "unit": "MP/s", "h2d_bytes_per_step": int(2 * 3 * nloc + 3 * ys.size) * world,
+                "d2h_bytes_per_step": int(3 * nloc + ys.size) * world, "ms_per_step": ms_host / args.steps,
+                "api": "nle_b200_train_bgr_u8 + nle_b200_enhance_bgr_u8: BGR host image in, BGR host image out"},
         "gpu_launches": launches,
         "clocks": clocks,
         "roofline": roofline,

@@ -143,6 +143,21 @@ int nle_b200_enhance_luminance_u8_dev(const nle_b200_filter* f, const uint8_t* l
 int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, double k,
                                 uint8_t* out);
 
+/* ---- image-level entry points with the colour conversion on the device ------------------------
+ * cv::cvtColor(COLOR_BGR2Lab / COLOR_Lab2BGR) on CV_8UC3 as used by the reference (filter.cpp:423,440,463,528),
+ * byte-exact with OpenCV's fixed-point 8-bit path (csrc/lab.cu).  bgr/lab: interleaved, 3 bytes per pixel. */
+int nle_b200_bgr_to_lab_u8(const uint8_t* bgr, long long npix, uint8_t* lab);
+int nle_b200_lab_to_bgr_u8(const uint8_t* lab, long long npix, uint8_t* bgr);
+/* NLEFilter::trainForEnhancement, filter.cpp:514-519: getLuminanceChannel (BGR2Lab, L) + trainFilter.  `bgr` is the
+ * FULL rows x cols x 3 host image; this rank owns rows [row0,row1) (row0=0,row1=rows and allreduce=NULL: one GPU). */
+int nle_b200_train_bgr_u8(const uint8_t* bgr, int rows, int cols, int row0, int row1, int nRowSamples,
+                          int nColSamples, double hx, double hy, int nSinkhornIter, int nEigenVectors,
+                          nle_b200_allreduce_fn allreduce, void* user, nle_b200_filter** out);
+/* NLEFilter::enhance, filter.cpp:412-443, on the owned slab: BGR2Lab, enhance L (transformEigenValues, apply, clamp,
+ * round), merge with the untouched a,b, Lab2BGR.  bgr_slab/out_slab: (row1-row0) x cols x 3 host bytes. */
+int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, const double* weights, int m,
+                            uint8_t* out_slab);
+
 /* ---- stage intermediates for parity tests (SURVEY.md 8b "test hooks") ------------------------ */
 typedef enum {
     NLE_B200_STAGE_KA = 0,        /* p x p                                   */

@@ -4,10 +4,10 @@ lightalchemist/nonlocal-image-edit) behind the reference's own operator interfac
 Host side mirrors include/filter.hpp of the reference: class NLEFilter with trainForEnhancement /
 trainForDenoise / enhance / denoise, and the free functions computeKernel, eigenDecomposition,
 nystromApproximation, sinkhorn, orthogonalize.  All numerics run in libnle_b200.so (hand-written
-CUDA for sm_100a); Python only does what the reference does with OpenCV on the host (imread,
-BGR<->Lab, bilateralFilter)."""
-from .filter import (NLEFilter, computeKernel, eigenDecomposition, nystromApproximation,  # noqa: F401
-                     orthogonalize, sampleIndices, sinkhorn, transformEigenValues)
+CUDA for sm_100a), including the 8-bit BGR<->Lab conversion around enhance; Python only does what the
+reference does with OpenCV on the host for I/O (imread) and for the denoise variant (bilateralFilter)."""
+from .filter import (NLEFilter, bgrToLab, computeKernel, eigenDecomposition, labToBgr,  # noqa: F401
+                     nystromApproximation, orthogonalize, sampleIndices, sinkhorn, transformEigenValues)
 from ._lib import NleError, load  # noqa: F401
 
 EPS = 1e-10  # include/filter.hpp:14

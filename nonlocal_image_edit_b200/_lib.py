@@ -48,6 +48,10 @@ SYMBOLS = {
     "nle_b200_enhance_luminance_u8": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "nle_b200_enhance_luminance_u8_dev": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "nle_b200_denoise_channel_u8": (C.c_int, [_P, _P, C.c_double, _P]),
+    "nle_b200_bgr_to_lab_u8": (C.c_int, [_P, C.c_longlong, _P]),
+    "nle_b200_lab_to_bgr_u8": (C.c_int, [_P, C.c_longlong, _P]),
+    "nle_b200_train_bgr_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, ALLREDUCE_FN, _P, C.POINTER(_P)]),
+    "nle_b200_enhance_bgr_u8": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "nle_b200_get_stage": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nle_b200_set_keep_stages": (None, [C.c_int]),
     "nle_b200_launch_count": (C.c_longlong, [C.c_int]),

@@ -98,6 +98,7 @@ struct nle_b200_filter {
     std::vector<double> S;       // k eigenvalues (host copy)
     DevBuf<double> ascratch, avec;   // apply scratch
     DevBuf<uint8_t> io8_in, io8_out;
+    DevBuf<uint8_t> io_bgr, io_ab;   // BGR staging (3 bytes/pixel, in and out) and the a,b planes of the image being enhanced
     DevBuf<double> io64_in, io64_out;
     // stages
     DevBuf<double> Ka, lam, rvec_head, c, Wa, Q, la, Gram;
@@ -925,6 +926,84 @@ int nle_b200_enhance_luminance_u8(const nle_b200_filter* f, const uint8_t* lum, 
         ff->io8_out.download(out, n, f->stream);
         NLE_CUDA(cudaStreamSynchronize(f->stream));
         tr("host enhance: download");
+    });
+}
+
+// ---- image-level entry points with the colour conversion on the device (lab.cu) -----------------------------
+int nle_b200_bgr_to_lab_u8(const uint8_t* bgr, long long npix, uint8_t* lab) {
+    return guarded([&] {
+        require_device();
+        if (!bgr || !lab || npix < 0) throw InvalidArg{"null pointer"};
+        cudaStream_t s = nullptr;
+        const size_t n = (size_t)npix;
+        DevBuf<uint8_t> d_bgr(3 * n), d_L(n), d_ab(2 * n);
+        d_bgr.upload(bgr, 3 * n, s);
+        launch_bgr2lab(d_bgr.p, npix, d_L.p, d_ab.p, s);
+        // interleave on the way back: L -> lab[3j], ab -> lab[3j+1..2]
+        NLE_CUDA(cudaMemcpy2DAsync(lab, 3, d_L.p, 1, 1, n, cudaMemcpyDeviceToHost, s));
+        NLE_CUDA(cudaMemcpy2DAsync(lab + 1, 3, d_ab.p, 2, 2, n, cudaMemcpyDeviceToHost, s));
+        NLE_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int nle_b200_lab_to_bgr_u8(const uint8_t* lab, long long npix, uint8_t* bgr) {
+    return guarded([&] {
+        require_device();
+        if (!bgr || !lab || npix < 0) throw InvalidArg{"null pointer"};
+        cudaStream_t s = nullptr;
+        const size_t n = (size_t)npix;
+        DevBuf<uint8_t> d_bgr(3 * n), d_L(n), d_ab(2 * n);
+        NLE_CUDA(cudaMemcpy2DAsync(d_L.p, 1, lab, 3, 1, n, cudaMemcpyHostToDevice, s));
+        NLE_CUDA(cudaMemcpy2DAsync(d_ab.p, 2, lab + 1, 3, 2, n, cudaMemcpyHostToDevice, s));
+        launch_lab2bgr(d_L.p, d_ab.p, npix, d_bgr.p, s);
+        d_bgr.download(bgr, 3 * n, s);
+        NLE_CUDA(cudaStreamSynchronize(s));
+    });
+}
+
+int nle_b200_train_bgr_u8(const uint8_t* bgr, int rows, int cols, int row0, int row1, int nRS, int nCS, double hx,
+                          double hy, int T, int nEig, nle_b200_allreduce_fn ar, void* user, nle_b200_filter** out) {
+    return guarded([&] {
+        require_device();
+        if (!bgr || !out) throw InvalidArg{"null pointer"};
+        *out = nullptr;
+        Grid g = make_grid(rows, cols, nRS, nCS);
+        if (row0 < 0 || row1 > rows || row0 >= row1) throw InvalidArg{"invalid row slab"};
+        cudaStream_t s = nullptr;
+        const size_t nloc = (size_t)(row1 - row0) * cols;
+        // the p sample pixels (3p bytes) and this rank's slab go up as BGR; L is computed on the device
+        std::vector<uint8_t> sb((size_t)3 * g.p), ys(g.p);
+        for (int a = 0; a < g.nR; ++a)
+            for (int b = 0; b < g.nC; ++b)
+                memcpy(&sb[(size_t)3 * (a * g.nC + b)], bgr + 3 * ((size_t)g.sel_rows[a] * cols + g.sel_cols[b]), 3);
+        DevBuf<uint8_t> d_sb(sb.size()), d_ys(g.p), d_bgr(3 * nloc), d_L(nloc);
+        d_sb.upload(sb.data(), sb.size(), s);
+        d_bgr.upload(bgr + 3 * (size_t)row0 * cols, 3 * nloc, s);
+        launch_bgr2lab(d_sb.p, g.p, d_ys.p, nullptr, s);
+        launch_bgr2lab(d_bgr.p, (long long)nloc, d_L.p, nullptr, s);
+        d_ys.download(ys.data(), g.p, s);
+        NLE_CUDA(cudaStreamSynchronize(s));
+        auto f = train_core(d_L.p, rows, cols, row0, row1, ys.data(), nRS, nCS, hx, hy, T, nEig, ar, user);
+        *out = f.release();
+    });
+}
+
+int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, const double* weights, int m,
+                            uint8_t* out_slab) {
+    return guarded([&] {
+        if (!f || !bgr_slab || !weights || !out_slab) throw InvalidArg{"null pointer"};
+        if (m < 1) throw InvalidArg{"at least one weight is required"};
+        auto* ff = const_cast<nle_b200_filter*>(f);
+        const size_t n = (size_t)f->nloc;
+        if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
+        if (ff->io_bgr.n < 3 * n) { ff->io_bgr.alloc(3 * n); ff->io_ab.alloc(2 * n); }
+        ff->io_bgr.upload(bgr_slab, 3 * n, f->stream);
+        launch_bgr2lab(ff->io_bgr.p, (long long)n, ff->io8_in.p, ff->io_ab.p, f->stream);          // filter.cpp:422-426
+        auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);                            // :428
+        apply_core(f, ff->io8_in.p, nullptr, fS.data(), nullptr, ff->io8_out.p);                   // :431-436
+        launch_lab2bgr(ff->io8_out.p, ff->io_ab.p, (long long)n, ff->io_bgr.p, f->stream);          // :438-440
+        ff->io_bgr.download(out_slab, 3 * n, f->stream);
+        NLE_CUDA(cudaStreamSynchronize(f->stream));
     });
 }
 

@@ -77,6 +77,10 @@ void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, con
 void launch_recompose(long long nloc, int k, const double* V, const double* g, double* out_f64,
                       uint8_t* out_u8, cudaStream_t s);
 
+// 8-bit BGR <-> Lab, byte-exact with cv::cvtColor on CV_8UC3 (lab.cu).  bgr: npix x 3 interleaved; L: npix; ab: npix x 2.
+void launch_bgr2lab(const uint8_t* bgr, long long npix, uint8_t* L, uint8_t* ab, cudaStream_t s);
+void launch_lab2bgr(const uint8_t* L, const uint8_t* ab, long long npix, uint8_t* bgr, cudaStream_t s);
+
 // misc elementwise
 void launch_fill(double* p, long long n, double v, cudaStream_t s);
 void launch_mask_samples(const AffinityTables& t, double* x, cudaStream_t s);  // x=0 at sample pixels

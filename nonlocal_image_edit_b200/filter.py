@@ -6,8 +6,9 @@ Same names, argument meaning and error behaviour as the reference:
 Matrices cross this boundary as NumPy float64 arrays; they are handed to the library in
 column-major order (Eigen's default).  Images are BGR uint8 arrays like cv::Mat.
 
-The colour conversion (cv2.cvtColor BGR2Lab / Lab2BGR) and cv2.bilateralFilter stay on the host
-exactly where the reference calls OpenCV (filter.cpp:361-371, 423-426, 438-440, 463, 528-535).
+trainForEnhancement / enhance run the 8-bit BGR<->Lab conversion on the device (csrc/lab.cu, byte-exact with
+cv::cvtColor; `bgrToLab` / `labToBgr` expose it).  cv2.bilateralFilter, which only the denoise variant uses, stays on
+the host where the reference calls OpenCV (filter.cpp:361-371, 528-535), and so does that variant's colour conversion.
 """
 from __future__ import annotations
 
@@ -116,6 +117,26 @@ def orthogonalize(Wa, Wab, nEigVectors=5, eps=EPS):
     check(lib.nle_b200_orthogonalize(pWa, p, pWab if nrest else None, nrest, int(nEigVectors), float(eps),
                                      _ptr(V), _ptr(S), C.byref(k)))
     return np.asfortranarray(V[:, :k.value]), S[:k.value].copy()
+
+
+def bgrToLab(image):
+    """cv::cvtColor(image, COLOR_BGR2Lab) on CV_8UC3 (filter.cpp:423,463), on the device."""
+    img = np.ascontiguousarray(image, dtype=np.uint8)
+    if img.ndim != 3 or img.shape[2] != 3:
+        raise NleError(-1, "expected an H x W x 3 uint8 image")
+    out = np.empty_like(img)
+    check(_lib.load().nle_b200_bgr_to_lab_u8(_ptr(img), img.shape[0] * img.shape[1], _ptr(out)))
+    return out
+
+
+def labToBgr(lab):
+    """cv::cvtColor(lab, COLOR_Lab2BGR) on CV_8UC3 (filter.cpp:440), on the device."""
+    img = np.ascontiguousarray(lab, dtype=np.uint8)
+    if img.ndim != 3 or img.shape[2] != 3:
+        raise NleError(-1, "expected an H x W x 3 uint8 image")
+    out = np.empty_like(img)
+    check(_lib.load().nle_b200_lab_to_bgr_u8(_ptr(img), img.shape[0] * img.shape[1], _ptr(out)))
+    return out
 
 
 def transformEigenValues(eigvals, weights):
@@ -241,9 +262,18 @@ class NLEFilter:
 
     # -- public API of the reference class --------------------------------------------------
     def trainForEnhancement(self, image, nRowSamples, nColSamples, hx, hy, nSinkhornIter=10, nEigenVectors=5):
-        """filter.cpp:514-519."""
-        lum = self._lab(np.ascontiguousarray(image))[:, :, 0]          # getLuminanceChannel, :460-469
-        return self.trainFilter(lum, nRowSamples, nColSamples, hx, hy, nSinkhornIter, nEigenVectors)
+        """filter.cpp:514-519: getLuminanceChannel (:460-469, BGR2Lab on the device) + trainFilter."""
+        image = np.ascontiguousarray(image, dtype=np.uint8)
+        if image.ndim != 3 or image.shape[2] != 3:
+            raise NleError(-1, "expected an H x W x 3 uint8 image")
+        self._release()
+        h = C.c_void_p()
+        rows, cols = image.shape[:2]
+        check(self._lib.nle_b200_train_bgr_u8(_ptr(image), rows, cols, 0, rows, int(nRowSamples), int(nColSamples),
+                                              float(hx), float(hy), int(nSinkhornIter), int(nEigenVectors),
+                                              C.cast(None, _lib.ALLREDUCE_FN), None, C.byref(h)))
+        self._h = h
+        return self
 
     def trainForDenoise(self, image, nRowSamples, nColSamples, hx, hy, nSinkhornIter, nEigenVectors,
                         sigmaColor=10, sigmaSpace=10):
@@ -288,9 +318,12 @@ class NLEFilter:
         inf = self.info()
         if image.shape[0] * image.shape[1] != inf.rows * inf.cols:
             raise NleError(-1, "Cannot apply filter on image with different size from the image filter was trained on.")  # :419
-        lab = self._lab(image)
-        lab[:, :, 0] = self.enhanceLuminance(np.ascontiguousarray(lab[:, :, 0]), weights)
-        return self._bgr(lab)
+        if (inf.row0, inf.row1) != (0, inf.rows):
+            raise NleError(-1, "enhance() needs the whole image on this filter; use enhanceLuminance on a row slab")
+        w = _f64(weights)
+        out = np.empty_like(image)
+        check(self._lib.nle_b200_enhance_bgr_u8(self._h, _ptr(image), _ptr(w), w.size, _ptr(out)))   # :422-440 on the device
+        return out
 
     def denoise(self, image, k, sigmaColor=10, sigmaSpace=10):
         """NLEFilter::denoise (filter.cpp:349-410) without the imshow side effects."""

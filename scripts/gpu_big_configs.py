@@ -1,0 +1,33 @@
+"""Developer diagnostic: BASELINE.json configs[3] (full-resolution rock2, p=2500, k=100) and configs[4]
+(synthetic 4096x4096, p=2500, k=100) on one GPU: timings, ranks and size-independent invariants."""
+import os, sys, time
+import numpy as np, cv2
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import nonlocal_image_edit_b200 as nb
+from bench import synth_luminance
+
+def run(name, L, a, weights):
+    f = None
+    for rep in range(2):
+        t0 = time.time()
+        f = nb.NLEFilter().trainFilter(L, *a)
+        out = f.enhanceLuminance(L, weights)
+        dt = time.time() - t0
+    inf = f.info()
+    S = f.eigvals
+    z = L.astype(np.float64)
+    ones = np.ones(S.size)
+    p1 = f.apply(z, ones); p2 = f.apply(p1, ones)
+    print(f"{name}: {L.shape} p={inf.p} r={inf.r} r2={inf.r2} k={inf.k} wall {dt*1e3:.1f} ms ({L.size/1e6/dt:.2f} MP/s) stage ms {np.round(f.stage(8), 1)}")
+    print(f"   S[0]={S[0]:.6f} S[-1]={S[-1]:.3e} sorted={bool(np.all(np.diff(S) <= 1e-12))} projector idempotence {np.abs(p2-p1).max()/np.abs(p1).max():.2e} "
+          f"out range {out.min()}..{out.max()} mean|out-L| {np.abs(out.astype(int)-L.astype(int)).mean():.2f}", flush=True)
+
+which = sys.argv[1:] or ["c4", "c5"]
+if "c4" in which:
+    img = cv2.imread(os.path.join(ROOT, "tests/golden/rock2_input.png"))
+    L = np.ascontiguousarray(cv2.cvtColor(img, cv2.COLOR_BGR2Lab)[:, :, 0])
+    run("C4 rock2 p=2500 k=100 T=50", L, (50, 50, 500.0, 10.0, 50, 100), [4.0, 3.0, 4.0, 1.0])
+if "c5" in which:
+    L = synth_luminance(4096, 4096)
+    run("C5 synthetic 4096^2 p=2500 k=100 T=20", L, (50, 50, 500.0, 30.0, 20, 100), [2.0, 3.0, 4.0, 1.0])
