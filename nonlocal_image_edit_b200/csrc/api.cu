@@ -294,6 +294,12 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     const bool sk_cells = !sk_rows_env && sinkhorn_cells_supported(tb);
     TmpBuf<double> spart(sk_cells ? 1 : ((size_t)nrows + cdiv(nrows, 32) + 1) * p);
     TmpBuf<double> skscratch(sk_cells ? sinkhorn_cells_scratch_doubles(tb) : 1);
+    TmpBuf<double> ciscratch(sk_cells ? cell_index_scratch_doubles(tb) : 1);
+    CellIndex cidx{};
+    if (sk_cells) {
+        cidx = build_cell_index(tb, ciscratch.p, s);
+        sinkhorn_cells_prepare(tb, skscratch.p, s);
+    }
     copy_dd(inv_lam.p, lam.p, p, s);
     guarded_reciprocal(inv_lam.p, r, kEps, s);            // filter.cpp:265-266
     // t = phi^T x = U_r^T x_sel + Lam^-1 U_r^T (Kab x_rest)
@@ -305,14 +311,14 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         // w = U_r t (rest pixels: k_j^T w) and, for the samples, recip(U[s,:] Lam t) in one pass over U
         sk_sample_step(p, r, U.p, p, tvec.p, lam.p, kEps, wvec.p, x_sel_out, s);
         if (need_rest) {
-            if (sk_cells) launch_sinkhorn_cells(tb, wvec.p, xfull.p, skscratch.p, svec.p, s);
+            if (sk_cells) launch_sinkhorn_cells(tb, &cidx, wvec.p, xfull.p, skscratch.p, svec.p, s);
             else launch_pass_fused(tb, wvec.p, xfull.p, spart.p, svec.p, s);
             do_allreduce(f.get(), svec.p, p);
         }
     };
     // initial r = 1 : s0 = Kab 1
     if (sk_cells) {
-        launch_sinkhorn_cells(tb, nullptr, xfull.p, skscratch.p, svec.p, s);
+        launch_sinkhorn_cells(tb, &cidx, nullptr, xfull.p, skscratch.p, svec.p, s);
     } else {
         launch_fill(xfull.p, nloc, 1.0, s);
         launch_mask_samples(tb, xfull.p, s);

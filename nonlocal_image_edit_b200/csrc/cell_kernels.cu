@@ -707,4 +707,45 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
     }
 }
 
+// ---- cell index of a whole slab (used by the Sinkhorn pixel pass; the Gram and the extension build their own per batch)
+static void cell_index_layout(const AffinityTables& t, size_t& cells, size_t& lev_bytes, size_t& ints) {
+    const int capc = std::min(256, (t.cols + 3) & ~3);
+    cells = (size_t)capc * t.nrows;
+    lev_bytes = (cells + 7) / 8 * 8;
+    ints = 2 * ((size_t)t.nrows + 4) + 3 * cells + (size_t)t.nrows * t.cols;
+}
+
+size_t cell_index_scratch_doubles(const AffinityTables& t) {
+    size_t cells, lev_bytes, ints;
+    cell_index_layout(t, cells, lev_bytes, ints);
+    return lev_bytes / 8 + (ints * 4 + 7) / 8 + 8;
+}
+
+CellIndex build_cell_index(const AffinityTables& t, double* scratch, cudaStream_t s) {
+    size_t cells, lev_bytes, ints;
+    cell_index_layout(t, cells, lev_bytes, ints);
+    uint8_t* cell_lev = reinterpret_cast<uint8_t*>(scratch);
+    int* cnt = reinterpret_cast<int*>(cell_lev + lev_bytes);
+    int* koff = cnt + t.nrows + 4;
+    int* cell_row = koff + t.nrows + 4;
+    int* cell_pstart = cell_row + cells;
+    int* cell_pcount = cell_pstart + cells;
+    int* sorted = cell_pcount + cells;
+    const size_t ism = (size_t)(256 * 3 + 260 + 8) * sizeof(int) + ((t.cols + 15) / 16) * 16 + 16;
+    if (ism > 227 * 1024) throw Unsupported{"cell index: image too wide (cols=" + std::to_string(t.cols) + ")"};
+    static size_t conf = 0;
+    if (ism > conf) { NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism)); conf = ism; }
+    cell_count_kernel<<<std::min(t.nrows, sm_count() * 8), 256, 0, s>>>(t.lum, t.nrows, t.cols, cnt);
+    NLE_LAUNCH_CHECK();
+    cell_scan_kernel<<<1, 1024, 0, s>>>(cnt, t.nrows, koff);
+    NLE_LAUNCH_CHECK();
+    ext_index_kernel<<<std::min(t.nrows, sm_count() * 8), 256, ism, s>>>(t.lum, t.nrows, t.cols, koff, cell_lev, cell_row, cell_pstart,
+                                                                        cell_pcount, sorted);
+    NLE_LAUNCH_CHECK();
+    CellIndex ci;
+    ci.koff = koff; ci.lev = cell_lev; ci.row = cell_row; ci.pstart = cell_pstart; ci.pcount = cell_pcount; ci.sorted = sorted;
+    ci.cap_cells = (int)cells;
+    return ci;
+}
+
 }  // namespace nle

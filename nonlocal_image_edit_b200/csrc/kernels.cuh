@@ -41,12 +41,27 @@ void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart,
 void launch_pass_fused(const AffinityTables& t, const double* w, double* x, double* spart, double* s_out,
                        cudaStream_t s);
 
+// Cell index of a slab (cell_kernels.cu): the non-empty (image row, luminance level) cells, padded to a multiple of 4
+// per row, and the columns of every row ordered by (level, column).  All device pointers into `scratch`.
+struct CellIndex {
+    const int* koff;         // nrows+1: first cell of each row; koff[nrows] = number of (padded) cells
+    const uint8_t* lev;      // level of each cell (0 for padding cells)
+    const int* row;          // local image row of each cell
+    const int* pstart;       // first position of the cell in `sorted`
+    const int* pcount;       // pixels in the cell (0 for padding cells)
+    const int* sorted;       // nrows*cols: column indices, row by row, ordered by (level, column)
+    int cap_cells;           // upper bound of the number of cells (host-side grid sizing)
+};
+size_t cell_index_scratch_doubles(const AffinityTables& t);
+CellIndex build_cell_index(const AffinityTables& t, double* scratch, cudaStream_t s);
+
 // One Sinkhorn half-iteration with the sample-axis contractions as level-table GEMMs on the FP64 tensor pipe
 // (sinkhorn_cells.cu):  x = recip(k_j^T w) on the rest pixels (w == nullptr: x = 1), then s_out = Kab x.
 bool sinkhorn_cells_supported(const AffinityTables& t);
 size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t);
-void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, double* scratch, double* s_out,
-                           cudaStream_t s);
+void sinkhorn_cells_prepare(const AffinityTables& t, double* scratch, cudaStream_t s);
+void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const double* w, double* x, double* scratch,
+                           double* s_out, cudaStream_t s);
 
 // Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab.
 size_t gram_scratch_doubles(const AffinityTables& t);

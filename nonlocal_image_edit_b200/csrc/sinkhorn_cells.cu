@@ -41,7 +41,7 @@ constexpr int DG_MT = DG_ROWS / 8;   // DMMA m-tiles per warp
 // F[row][b][l] = sum_a Er[row][a] * w_ab * Gt[|l - Y_ab|].   grid (ceil(nrows/DG_ROWS), nC), 256 threads.
 // Warp w owns levels [32w, 32w+32) (4 n-tiles) for all DG_ROWS rows.
 __global__ void __launch_bounds__(256, 2)
-sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ F) {
+sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ F, int level_major) {
     extern __shared__ double dsm[];
     const int nR = t.nR, nC = t.nC;
     const int nRp = (nR + 3) & ~3;
@@ -91,9 +91,18 @@ sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __res
     for (int u = 0; u < DG_MT; ++u) {
         const int r = r0 + 8 * u + g;
         if (r >= t.nrows) continue;
-        double* o = F + ((size_t)r * nC + b) * NL + warp * 32 + 2 * tq;
+        if (!level_major) {                                   // F[row][b][l]
+            double* o = F + ((size_t)r * nC + b) * NL + warp * 32 + 2 * tq;
 #pragma unroll
-        for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+            for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+        } else {                                              // F[row][l][b]: a cell's nC values are contiguous
+            double* o = F + ((size_t)r * NL + warp * 32 + 2 * tq) * nC + b;
+#pragma unroll
+            for (int v = 0; v < 4; ++v) {
+                o[(size_t)(8 * v) * nC] = acc[u][v][0];
+                o[(size_t)(8 * v + 1) * nC] = acc[u][v][1];
+            }
+        }
     }
 }
 
@@ -291,6 +300,73 @@ sk_pix_fused_kernel(AffinityTables t, int w_given, double* __restrict__ x, doubl
     }
 }
 
+// Row pass over the cell index, one WARP per cell and no shared memory or block barrier at all: the pixels of a cell
+// share the level, so its F row (nC values, contiguous in the level-major layout) lives in registers and its
+// histogram bins are register accumulators that are stored once.  Lanes = 4 pixel slots x 8 b-lanes (b = sub + 8i):
+// every Ec row is loaded once and serves both the dot (xor-shuffle tree inside the 8-lane group) and the histogram.
+//   F: [row][l][b] (read), H: [row][b][l] (written for the non-empty cells only; the rest was zeroed once per training
+//   call and is never touched), x: slab vector.
+template <int NB>
+__global__ void __launch_bounds__(256)
+sk_pix_cells_kernel(AffinityTables t, CellIndex ci, int w_given, const double* __restrict__ F, double* __restrict__ x,
+                    double* __restrict__ H) {
+    const int nC = t.nC, W = t.cols;
+    const int lane = threadIdx.x & 31, q = lane >> 3, sub = lane & 7;
+    const int K = ci.koff[t.nrows];
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < K; cell += nwarps) {
+        const int np = ci.pcount[cell];
+        if (np == 0) continue;
+        const int rl = ci.row[cell], lev = (int)ci.lev[cell];
+        const int* pix = ci.sorted + ci.pstart[cell];
+        const int a_row = t.rowa[t.row0 + rl];
+        double f[NB], acc[NB];
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            const int b = sub + 8 * i;
+            f[i] = (w_given && b < nC) ? F[((size_t)rl * NL + lev) * nC + b] : 0.0;
+            acc[i] = 0.0;
+        }
+        for (int p0 = 0; p0 < np; p0 += 4) {
+            const bool ok = p0 + q < np;
+            const int col = ok ? pix[p0 + q] : 0;
+            const double* ecr = t.Ec + (size_t)col * nC;
+            double e[NB];
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int b = sub + 8 * i;
+                e[i] = (ok && b < nC) ? ecr[b] : 0.0;
+            }
+            double xv = 1.0;
+            if (w_given) {
+                double v = 0.0;
+#pragma unroll
+                for (int i = 0; i < NB; ++i) v = fma(e[i], f[i], v);
+                v += __shfl_xor_sync(0xffffffffu, v, 4);
+                v += __shfl_xor_sync(0xffffffffu, v, 2);
+                v += __shfl_xor_sync(0xffffffffu, v, 1);
+                xv = (fabs(v) >= kEps) ? 1.0 / v : 0.0;
+            }
+            if (!ok || (a_row >= 0 && t.colb[col] >= 0)) xv = 0.0;
+            if (ok && sub == 0) x[(size_t)rl * W + col] = xv;
+#pragma unroll
+            for (int i = 0; i < NB; ++i) acc[i] = fma(e[i], xv, acc[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < NB; ++i) {
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+            acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+        }
+        if (q == 0) {
+#pragma unroll
+            for (int i = 0; i < NB; ++i) {
+                const int b = sub + 8 * i;
+                if (b < nC) H[((size_t)rl * nC + b) * NL + lev] = acc[i];
+            }
+        }
+    }
+}
+
 // Mpart[ks][b][a][l] = sum_{row in split ks} Er[row][a] * Hx[row][b][l].
 // grid (nC, nks, nab), 256 threads; warp w owns levels [32w, 32w+32) (4 n-tiles) for MT m-tiles of grid rows.
 template <int MT>
@@ -402,7 +478,20 @@ bool sinkhorn_cells_supported(const AffinityTables& t) {
 
 size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t) {
     const SkGeom g = sk_geometry(t);
-    return g.fh_doubles + g.mpart_doubles + 8;
+    return 2 * g.fh_doubles + g.mpart_doubles + 8;
+}
+
+// Zeroes the histogram table once per training call (the cell pass only ever writes the non-empty cells).
+void sinkhorn_cells_prepare(const AffinityTables& t, double* scratch, cudaStream_t s) {
+    const SkGeom g = sk_geometry(t);
+    NLE_CUDA(cudaMemsetAsync(scratch + g.fh_doubles, 0, g.fh_doubles * sizeof(double), s));
+}
+
+template <int NB>
+static void launch_pc(const AffinityTables& t, const CellIndex& ci, int w_given, const double* F, double* x, double* H,
+                      cudaStream_t s) {
+    sk_pix_cells_kernel<NB><<<sm_count() * 8, 256, 0, s>>>(t, ci, w_given, F, x, H);
+    NLE_LAUNCH_CHECK();
 }
 
 template <int MT>
@@ -412,19 +501,24 @@ static void launch_rg(const AffinityTables& t, const SkGeom& g, const double* FH
 }
 
 // One half-iteration:  x = recip(k_j^T w) on the rest pixels (w == nullptr: x = 1), then s = Kab x.
-void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, double* scratch, double* s_out,
-                           cudaStream_t s) {
+// ci != nullptr: pixel pass over the cell index (sk_pix_cells_kernel; sinkhorn_cells_prepare must have run on this
+// scratch); otherwise the staged per-row kernels.
+void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const double* w, double* x, double* scratch,
+                           double* s_out, cudaStream_t s) {
     const SkGeom g = sk_geometry(t);
-    double* FH = scratch;
-    double* Mpart = FH + g.fh_doubles;
+    static const bool staged_env = getenv("NLE_B200_SK_STAGED") != nullptr;
+    const bool cells = ci != nullptr && t.nC <= 64 && !staged_env;
+    double* FH = scratch;                              // staged path: F, overwritten in place by the histogram
+    double* Hc = scratch + g.fh_doubles;               // cell path: separate histogram table
+    double* Mpart = scratch + 2 * g.fh_doubles;
     static size_t conf_pix = 0, conf_dot = 0, conf_pixf = 0;
     static const bool unfused_env = getenv("NLE_B200_SK_UNFUSED") != nullptr;
     const bool fused = g.fused && !unfused_env;
-    if (fused && g.pixf_smem > conf_pixf) {
+    if (!cells && fused && g.pixf_smem > conf_pixf) {
         NLE_CUDA(cudaFuncSetAttribute(sk_pix_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pixf_smem));
         conf_pixf = g.pixf_smem;
     }
-    if (!fused && g.pix_smem > conf_pix) {
+    if (!cells && !fused && g.pix_smem > conf_pix) {
         NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
         conf_pix = g.pix_smem;
     }
@@ -433,18 +527,36 @@ void launch_sinkhorn_cells(const AffinityTables& t, const double* w, double* x, 
         conf_dot = g.dot_smem;
     }
     if (w) {
-        sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH);
+        sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH, cells ? 1 : 0);
         NLE_LAUNCH_CHECK();
     }
-    if (fused) sk_pix_fused_kernel<<<t.nrows, PF_THREADS, g.pixf_smem, s>>>(t, w ? 1 : 0, x, FH);
-    else sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
-    NLE_LAUNCH_CHECK();
+    const double* Hx = FH;
+    if (cells) {
+        const int nb = cdiv(t.nC, 8);
+        switch (nb) {
+            case 1: launch_pc<1>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 2: launch_pc<2>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 3: launch_pc<3>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 4: launch_pc<4>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 5: launch_pc<5>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 6: launch_pc<6>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 7: launch_pc<7>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            default: launch_pc<8>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+        }
+        Hx = Hc;
+    } else if (fused) {
+        sk_pix_fused_kernel<<<t.nrows, PF_THREADS, g.pixf_smem, s>>>(t, w ? 1 : 0, x, FH);
+        NLE_LAUNCH_CHECK();
+    } else {
+        sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
+        NLE_LAUNCH_CHECK();
+    }
     switch (g.MT) {
-        case 1: launch_rg<1>(t, g, FH, Mpart, s); break;
-        case 2: launch_rg<2>(t, g, FH, Mpart, s); break;
-        case 3: launch_rg<3>(t, g, FH, Mpart, s); break;
-        case 4: launch_rg<4>(t, g, FH, Mpart, s); break;
-        default: launch_rg<5>(t, g, FH, Mpart, s); break;
+        case 1: launch_rg<1>(t, g, Hx, Mpart, s); break;
+        case 2: launch_rg<2>(t, g, Hx, Mpart, s); break;
+        case 3: launch_rg<3>(t, g, Hx, Mpart, s); break;
+        case 4: launch_rg<4>(t, g, Hx, Mpart, s); break;
+        default: launch_rg<5>(t, g, Hx, Mpart, s); break;
     }
     sk_reduce_final_kernel<<<cdiv(t.p, 8), 256, 0, s>>>(t, Mpart, g.nks, g.nRp, s_out);
     NLE_LAUNCH_CHECK();

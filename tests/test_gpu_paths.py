@@ -49,7 +49,7 @@ def default_run(tmp_path_factory):
 
 
 @pytest.mark.parametrize("var,val", [("NLE_B200_GRAM", "pixel"), ("NLE_B200_SINKHORN", "rows"), ("NLE_B200_EXT", "pixel"),
-                                     ("NLE_B200_SK_UNFUSED", "1")])
+                                     ("NLE_B200_SK_UNFUSED", "1"), ("NLE_B200_SK_STAGED", "1")])
 def test_alternate_kernels_agree(tmp_path, default_run, var, val):
     alt = _run(tmp_path, "alt", {var: val})
     for i in range(len(CASES)):
