@@ -23,7 +23,9 @@
 //
 // scripts/proto_eig_dc.py is the NumPy prototype of exactly this structure (checked against LAPACK).
 #include <cooperative_groups.h>
+#include <cuda_pipeline.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cstdlib>
 
@@ -646,50 +648,79 @@ __global__ void reflector_dots_kernel(const double* __restrict__ A, int lda, int
     if (lane == 0) gdot[j] = acc;
 }
 
-// U = H_0 H_1 ... H_{n-3} Z in place; one warp per column, the column lives in shared memory, two reflectors
-// per pass:  z <- H_{j-1} H_j z  needs  d1 = v_j.z,  d2 = v_{j-1}.z - tau_j d1 (v_{j-1}.v_j)  -- both dots in one
-// sweep over z, one shuffle reduction, one update sweep.  Only columns the caller needs are transformed:
-// those whose eigenvalue ranks below min(vec_limit, *count).
+// collist[rank] = column whose eigenvalue has that rank (descending), for the back-transformation's work list
+__global__ void dc_collist_kernel(const int* __restrict__ order, int n, int* __restrict__ collist) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j < n) collist[order[j]] = j;
+}
+
+// U = H_0 H_1 ... H_{n-3} Z in place.  One warp per eigenvector column (the column lives in shared memory), two
+// reflectors per pass:  z <- H_{j-1} H_j z  needs  d1 = v_j.z,  d2 = v_{j-1}.z - tau_j d1 (v_{j-1}.v_j)  -- both dots in
+// one sweep over z, one shuffle reduction, one update sweep.  The reflector pair of a pass is staged ONCE per CTA in
+// shared memory (cp.async, double buffered: the next pair streams in while this one is applied) and shared by all its
+// warps; with every warp fetching the reflectors itself the kernel was bound by L2 traffic (columns x n^2 x 8 B =
+// 21 GB at n = 1600).  Only the columns the caller needs are transformed -- the work list holds the columns by
+// eigenvalue rank, the first min(vec_limit, *count) of them are taken.
 __global__ void backtransform_kernel(const double* __restrict__ A, int lda, const double* __restrict__ tau,
                                      const double* __restrict__ gdot, int n, double* __restrict__ Z, int ldz,
-                                     const int* __restrict__ order, const int* __restrict__ count, int vec_limit) {
+                                     const int* __restrict__ collist, const int* __restrict__ count, int vec_limit) {
     extern __shared__ double zsm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int wpb = blockDim.x >> 5;
-    const int col = blockIdx.x * wpb + warp;
-    if (col >= n) return;
-    if (vec_limit >= 0) {
-        const int lim = min(vec_limit, *count);
-        if (order[col] >= lim) return;
-    }
+    const int lim = vec_limit >= 0 ? min(vec_limit, *count) : n;
+    if (blockIdx.x * wpb >= lim) return;                        // whole CTA idle (uniform)
+    const int idx = blockIdx.x * wpb + warp;
+    const bool active = idx < lim;
+    const int col = active ? collist[idx] : 0;
     double* z = zsm + (size_t)warp * n;
+    double* vb = zsm + (size_t)wpb * n;                           // [2 buffers][2 reflectors][n]
     double* zc = Z + (size_t)col * ldz;
-    for (int i = lane; i < n; i += 32) z[i] = zc[i];
-    __syncwarp();
+    if (active)
+        for (int i = lane; i < n; i += 32) z[i] = zc[i];
+    // stage reflectors j (rows j+1..) and j-1 (rows j..) of a pass into buffer `buf`
+    auto stage = [&](int j, int buf) {
+        double* s1 = vb + (size_t)(2 * buf) * n;
+        double* s0 = s1 + n;
+        const double* v1 = A + (size_t)j * lda;
+        const double* v0 = A + (size_t)(j - 1) * lda;
+        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) {
+            __pipeline_memcpy_async(s1 + i, v1 + i, sizeof(double));
+            __pipeline_memcpy_async(s0 + i, v0 + i, sizeof(double));
+        }
+        __pipeline_commit();
+    };
     int j = n - 3;
-    for (; j >= 1; j -= 2) {
-        const double t1 = tau[j], t0 = tau[j - 1];
-        const double* v1 = A + (size_t)j * lda;          // rows j+1..
-        const double* v0 = A + (size_t)(j - 1) * lda;    // rows j..   (v0[j] == 1)
-        double d1 = 0.0, d0 = 0.0;
-        for (int i = j + 1 + lane; i < n; i += 32) {
-            const double zi = z[i];
-            d1 = fma(v1[i], zi, d1);
-            d0 = fma(v0[i], zi, d0);
-        }
+    int buf = 0;
+    if (j >= 1) stage(j, 0);
+    __pipeline_wait_prior(0);
+    __syncthreads();
+    for (; j >= 1; j -= 2, buf ^= 1) {
+        if (j - 2 >= 1) stage(j - 2, buf ^ 1);
+        if (active) {
+            const double t1 = tau[j], t0 = tau[j - 1];
+            const double* v1 = vb + (size_t)(2 * buf) * n;       // rows j+1..
+            const double* v0 = v1 + n;                           // rows j+1.. (v0[j] == 1 is implicit)
+            double d1 = 0.0, d0 = 0.0;
+            for (int i = j + 1 + lane; i < n; i += 32) {
+                const double zi = z[i];
+                d1 = fma(v1[i], zi, d1);
+                d0 = fma(v0[i], zi, d0);
+            }
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-            d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+            for (int o = 16; o > 0; o >>= 1) {
+                d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+                d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+            }
+            const double zj = z[j];
+            const double s1 = t1 * d1;
+            const double s0 = t0 * ((d0 + zj) - s1 * gdot[j]);
+            for (int i = j + 1 + lane; i < n; i += 32) z[i] = fma(-s0, v0[i], fma(-s1, v1[i], z[i]));
+            if (lane == 0) z[j] = zj - s0;
         }
-        const double zj = z[j];
-        const double s1 = t1 * d1;
-        const double s0 = t0 * ((d0 + zj) - s1 * gdot[j]);
-        for (int i = j + 1 + lane; i < n; i += 32) z[i] = fma(-s0, v0[i], fma(-s1, v1[i], z[i]));
-        if (lane == 0) z[j] = zj - s0;
-        __syncwarp();
+        __pipeline_wait_prior(0);
+        __syncthreads();
     }
-    if (j == 0) {
+    if (j == 0 && active) {
         const double t = tau[0];
         const double* v = A;
         double dot = 0.0;
@@ -698,7 +729,8 @@ __global__ void backtransform_kernel(const double* __restrict__ A, int lda, cons
         for (int i = 1 + lane; i < n; i += 32) z[i] = fma(-dot, v[i], z[i]);
         __syncwarp();
     }
-    for (int i = lane; i < n; i += 32) zc[i] = z[i];
+    if (active)
+        for (int i = lane; i < n; i += 32) zc[i] = z[i];
 }
 
 __global__ void dc_check_kernel(const double* __restrict__ U, int ldu, int n, int* __restrict__ fail) {
@@ -820,21 +852,33 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         int dev = 0, max_smem = 0;
         NLE_CUDA(cudaGetDevice(&dev));
         NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-        int wpb = (int)((size_t)(max_smem - 1024) / ((size_t)n * sizeof(double)));
-        if (wpb > 8) wpb = 8;
-        if (wpb < 1) throw Unsupported{"eigensolver: back-transformation column does not fit in shared memory (n=" + std::to_string(n) + ")"};
-        const size_t smem = (size_t)wpb * n * sizeof(double);
-        NLE_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         NLE_CUDA(cudaMemsetAsync(count, 0, sizeof(int), s));
         dc_rank_count_kernel<<<cdiv(n, 128), 128, 0, s>>>(dc, n, eps, order, count);
+        NLE_LAUNCH_CHECK();
+        // number of columns to transform (host copy: it sizes the CTAs so that one wave covers all SMs)
+        int count_h = 0;
+        NLE_CUDA(cudaMemcpyAsync(&count_h, count, sizeof(int), cudaMemcpyDeviceToHost, s));
+        NLE_CUDA(cudaStreamSynchronize(s));
+        const int m = vec_limit >= 0 ? std::min(vec_limit, count_h) : n;
+        // shared memory: wpb eigenvector columns + two staged reflector pairs (4 columns)
+        const int max_wpb = (int)((size_t)(max_smem - 1024) / ((size_t)n * sizeof(double))) - 4;
+        if (max_wpb < 1) throw Unsupported{"eigensolver: back-transformation column does not fit in shared memory (n=" + std::to_string(n) + ")"};
+        int wpb = std::max(2, cdiv(std::max(m, 1), sm_count()));
+        wpb = std::min(wpb, std::min(max_wpb, 16));
+        const size_t smem = (size_t)(wpb + 4) * n * sizeof(double);
+        NLE_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int* collist = a.colmap;  // the D&C column map is free again
+        dc_collist_kernel<<<cdiv(n, 128), 128, 0, s>>>(order, n, collist);
         NLE_LAUNCH_CHECK();
         double* gdot = pbuf;      // the symv exchange buffer of the tridiagonalisation is free again
         if (n >= 4) {
             reflector_dots_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(As, n, n, gdot);
             NLE_LAUNCH_CHECK();
         }
-        backtransform_kernel<<<cdiv(n, wpb), wpb * 32, smem, s>>>(As, n, tau, gdot, n, Qc, n, order, count, vec_limit);
-        NLE_LAUNCH_CHECK();
+        if (m > 0) {
+            backtransform_kernel<<<cdiv(m, wpb), wpb * 32, smem, s>>>(As, n, tau, gdot, n, Qc, n, collist, count, vec_limit);
+            NLE_LAUNCH_CHECK();
+        }
     }
     auto t_bt = tnow();
     if (prof) {
