@@ -657,7 +657,7 @@ __global__ void dc_collist_kernel(const int* __restrict__ order, int n, int* __r
 // U = H_0 H_1 ... H_{n-3} Z in place.  One warp per eigenvector column (the column lives in shared memory), two
 // reflectors per pass:  z <- H_{j-1} H_j z  needs  d1 = v_j.z,  d2 = v_{j-1}.z - tau_j d1 (v_{j-1}.v_j)  -- both dots in
 // one sweep over z, one shuffle reduction, one update sweep.  The reflector pair of a pass is staged ONCE per CTA in
-// shared memory (cp.async, double buffered: the next pair streams in while this one is applied) and shared by all its
+// shared memory (cp.async, three buffers: the next two pairs stream in while this one is applied) and shared by all its
 // warps; with every warp fetching the reflectors itself the kernel was bound by L2 traffic (columns x n^2 x 8 B =
 // 21 GB at n = 1600).  Only the columns the caller needs are transformed -- the work list holds the columns by
 // eigenvalue rank, the first min(vec_limit, *count) of them are taken.
@@ -673,29 +673,34 @@ __global__ void backtransform_kernel(const double* __restrict__ A, int lda, cons
     const bool active = idx < lim;
     const int col = active ? collist[idx] : 0;
     double* z = zsm + (size_t)warp * n;
-    double* vb = zsm + (size_t)wpb * n;                           // [2 buffers][2 reflectors][n]
+    double* vb = zsm + (size_t)wpb * n;                           // [NBUF buffers][2 reflectors][n]
     double* zc = Z + (size_t)col * ldz;
     if (active)
         for (int i = lane; i < n; i += 32) z[i] = zc[i];
-    // stage reflectors j (rows j+1..) and j-1 (rows j..) of a pass into buffer `buf`
+    // stage reflectors j (rows j+1..) and j-1 (rows j..) of a pass into buffer `buf`; always commits a group so that
+    // the wait below can count groups
     auto stage = [&](int j, int buf) {
-        double* s1 = vb + (size_t)(2 * buf) * n;
-        double* s0 = s1 + n;
-        const double* v1 = A + (size_t)j * lda;
-        const double* v0 = A + (size_t)(j - 1) * lda;
-        for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) {
-            __pipeline_memcpy_async(s1 + i, v1 + i, sizeof(double));
-            __pipeline_memcpy_async(s0 + i, v0 + i, sizeof(double));
+        if (j >= 1) {
+            double* s1 = vb + (size_t)(2 * buf) * n;
+            double* s0 = s1 + n;
+            const double* v1 = A + (size_t)j * lda;
+            const double* v0 = A + (size_t)(j - 1) * lda;
+            for (int i = j + 1 + threadIdx.x; i < n; i += blockDim.x) {
+                __pipeline_memcpy_async(s1 + i, v1 + i, sizeof(double));
+                __pipeline_memcpy_async(s0 + i, v0 + i, sizeof(double));
+            }
         }
         __pipeline_commit();
     };
+    constexpr int NBUF = 3;                                       // passes in flight: this one + two being fetched
     int j = n - 3;
     int buf = 0;
-    if (j >= 1) stage(j, 0);
-    __pipeline_wait_prior(0);
-    __syncthreads();
-    for (; j >= 1; j -= 2, buf ^= 1) {
-        if (j - 2 >= 1) stage(j - 2, buf ^ 1);
+    stage(j, 0);
+    stage(j - 2, 1);
+    for (; j >= 1; j -= 2) {
+        stage(j - 4, (buf + 2) % NBUF);
+        __pipeline_wait_prior(2);                                 // the group of pass j has landed
+        __syncthreads();
         if (active) {
             const double t1 = tau[j], t0 = tau[j - 1];
             const double* v1 = vb + (size_t)(2 * buf) * n;       // rows j+1..
@@ -717,8 +722,8 @@ __global__ void backtransform_kernel(const double* __restrict__ A, int lda, cons
             for (int i = j + 1 + lane; i < n; i += 32) z[i] = fma(-s0, v0[i], fma(-s1, v1[i], z[i]));
             if (lane == 0) z[j] = zj - s0;
         }
-        __pipeline_wait_prior(0);
-        __syncthreads();
+        __syncthreads();                                          // buffer `buf` may be refilled by the next stage()
+        buf = (buf + 1) % NBUF;
     }
     if (j == 0 && active) {
         const double t = tau[0];
@@ -860,12 +865,12 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         NLE_CUDA(cudaMemcpyAsync(&count_h, count, sizeof(int), cudaMemcpyDeviceToHost, s));
         NLE_CUDA(cudaStreamSynchronize(s));
         const int m = vec_limit >= 0 ? std::min(vec_limit, count_h) : n;
-        // shared memory: wpb eigenvector columns + two staged reflector pairs (4 columns)
-        const int max_wpb = (int)((size_t)(max_smem - 1024) / ((size_t)n * sizeof(double))) - 4;
+        // shared memory: wpb eigenvector columns + three staged reflector pairs (6 columns)
+        const int max_wpb = (int)((size_t)(max_smem - 1024) / ((size_t)n * sizeof(double))) - 6;
         if (max_wpb < 1) throw Unsupported{"eigensolver: back-transformation column does not fit in shared memory (n=" + std::to_string(n) + ")"};
         int wpb = std::max(2, cdiv(std::max(m, 1), sm_count()));
         wpb = std::min(wpb, std::min(max_wpb, 16));
-        const size_t smem = (size_t)(wpb + 4) * n * sizeof(double);
+        const size_t smem = (size_t)(wpb + 6) * n * sizeof(double);
         NLE_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int* collist = a.colmap;  // the D&C column map is free again
         dc_collist_kernel<<<cdiv(n, 128), 128, 0, s>>>(order, n, collist);

@@ -209,6 +209,23 @@ def test_train_stage_parity_small(nb, case):
     assert d.max() <= 1 and (d <= 1).mean() >= PIX_FRAC and (d == 0).mean() >= 0.99
 
 
+# hx / hy sweep (BASELINE.json configs[4] asks for one): the spatial and photometric widths move the ranks r, r2 and the
+# conditioning of every eigensolve by orders of magnitude; the rank cuts and the output must follow the FP64 oracle.
+@pytest.mark.parametrize("hx", [5.0, 100.0, 5000.0])
+@pytest.mark.parametrize("hy", [3.0, 10.0, 30.0, 100.0])
+def test_hx_hy_sweep_matches_oracle(nb, hx, hy):
+    L = synth_lum(72, 88, seed=21)
+    a = (9, 11, hx, hy, 6, 12)
+    f = nb.NLEFilter().trainFilter(L, *a)
+    fo = O.train_dense(L.astype(np.float64), *a)
+    st, inf = fo.stages, f.info()
+    assert (inf.p, inf.r, inf.r2, inf.k) == (st["p"], st["r"], st["r2"], fo.eigvals.size)
+    assert sq_close(f.eigvals, fo.eigvals)
+    w = [2.0, 3.0, 4.0, 1.0]
+    d = np.abs(f.enhanceLuminance(L, w).astype(int) - O.enhance_luminance(fo, L, w).astype(int))
+    assert d.max() <= 1 and (d <= 1).mean() >= PIX_FRAC
+
+
 def test_train_accepts_float64_channel_like_the_reference(nb):
     L = synth_lum(32, 40)
     a = (4, 5, 25.0, 20.0, 4, 5)
