@@ -86,72 +86,94 @@ int sm_count() {
 }
 
 // ------------------------------------------------------------------------------------------
-constexpr int GBM = 64, GBN = 64, GBK = 16;
+// C(m x n) = alpha * op(A) * op(B) + beta * C, column-major, on the FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS DMMA).
+// CTA tile 64 x 64 x 16, 4 warps (2 x 2), warp tile 32 x 32 = 4 x 4 DMMA tiles (32 accumulators per lane); operand tiles
+// are stored k-major in shared memory with a padded row (GLDS % 16 == 8: the four k-rows of a fragment fall into disjoint
+// bank groups) and the next chunk is prefetched into registers while the current one is multiplied.
+constexpr int GBM = 64, GBN = 64, GBK = 16, GLDS = 64 + 8;
+
+__device__ __forceinline__ void dgemm_dmma(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
 
 template <bool TA, bool TB>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
 dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
              const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc) {
-    __shared__ double As[GBK][GBM + 1];
-    __shared__ double Bs[GBK][GBN + 1];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
+    __shared__ double As[GBK][GLDS];     // As[k][i] = op(A)[i0+i][k0+k]
+    __shared__ double Bs[GBK][GLDS];     // Bs[k][j] = op(B)[k0+k][j0+j]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = warp & 1, wn = warp >> 1;
     const int i0 = blockIdx.x * GBM, j0 = blockIdx.y * GBN;
-    double acc[4][4];
+    double acc[4][4][2];
 #pragma unroll
     for (int u = 0; u < 4; ++u)
 #pragma unroll
-        for (int v = 0; v < 4; ++v) acc[u][v] = 0.0;
-
-    for (int k0 = 0; k0 < K; k0 += GBK) {
+        for (int v = 0; v < 4; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    double pa[8], pb[8];
+    auto fetch = [&](int k0) {
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            int idx = tid + l * 256;
+        for (int l = 0; l < 8; ++l) {
+            const int idx = tid + l * 128;
             int i, kk;
             if (TA) { kk = idx & 15; i = idx >> 4; } else { i = idx & 63; kk = idx >> 6; }
-            int gi = i0 + i, gk = k0 + kk;
-            double v = 0.0;
-            if (gi < M && gk < K) v = TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda];
-            As[kk][i] = v;
+            const int gi = i0 + i, gk = k0 + kk;
+            pa[l] = (gi < M && gk < K) ? (TA ? A[gk + (size_t)gi * lda] : A[gi + (size_t)gk * lda]) : 0.0;
+            int j, kb;
+            if (TB) { j = idx & 63; kb = idx >> 6; } else { kb = idx & 15; j = idx >> 4; }
+            const int gj = j0 + j, gkb = k0 + kb;
+            pb[l] = (gj < N && gkb < K) ? (TB ? B[gj + (size_t)gkb * ldb] : B[gkb + (size_t)gj * ldb]) : 0.0;
         }
+    };
+    auto commit = [&]() {
 #pragma unroll
-        for (int l = 0; l < 4; ++l) {
-            int idx = tid + l * 256;
-            int j, kk;
-            if (TB) { j = idx & 63; kk = idx >> 6; } else { kk = idx & 15; j = idx >> 4; }
-            int gj = j0 + j, gk = k0 + kk;
-            double v = 0.0;
-            if (gj < N && gk < K) v = TB ? B[gj + (size_t)gk * ldb] : B[gk + (size_t)gj * ldb];
-            Bs[kk][j] = v;
+        for (int l = 0; l < 8; ++l) {
+            const int idx = tid + l * 128;
+            int i, kk;
+            if (TA) { kk = idx & 15; i = idx >> 4; } else { i = idx & 63; kk = idx >> 6; }
+            As[kk][i] = pa[l];
+            int j, kb;
+            if (TB) { j = idx & 63; kb = idx >> 6; } else { kb = idx & 15; j = idx >> 4; }
+            Bs[kb][j] = pb[l];
         }
+    };
+    fetch(0);
+    for (int k0 = 0; k0 < K; k0 += GBK) {
+        __syncthreads();                   // previous chunk consumed
+        commit();
         __syncthreads();
+        if (k0 + GBK < K) fetch(k0 + GBK); // in flight during the DMMAs below
 #pragma unroll
-        for (int kk = 0; kk < GBK; ++kk) {
+        for (int k4 = 0; k4 < GBK / 4; ++k4) {
             double a[4], b[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) a[u] = As[kk][tx + 16 * u];
+            for (int u = 0; u < 4; ++u) a[u] = As[k4 * 4 + tq][wm * 32 + u * 8 + g];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) b[v] = Bs[kk][ty + 16 * v];
+            for (int v = 0; v < 4; ++v) b[v] = Bs[k4 * 4 + tq][wn * 32 + v * 8 + g];
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) acc[u][v] = fma(a[u], b[v], acc[u][v]);
+                for (int v = 0; v < 4; ++v) dgemm_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
-        __syncthreads();
     }
 #pragma unroll
-    for (int v = 0; v < 4; ++v) {
-        int gj = j0 + ty + 16 * v;
-        if (gj >= N) continue;
+    for (int u = 0; u < 4; ++u) {
+        const int gi = i0 + wm * 32 + u * 8 + g;
+        if (gi >= M) continue;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            int gi = i0 + tx + 16 * u;
-            if (gi >= M) continue;
-            double* c = C + gi + (size_t)gj * ldc;
-            double r = alpha * acc[u][v];
-            if (beta != 0.0) r = fma(beta, *c, r);
-            *c = r;
-        }
+        for (int v = 0; v < 4; ++v)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = j0 + wn * 32 + v * 8 + 2 * tq + e;
+                if (gj >= N) continue;
+                double* c = C + gi + (size_t)gj * ldc;
+                double r = alpha * acc[u][v][e];
+                if (beta != 0.0) r = fma(beta, *c, r);
+                *c = r;
+            }
     }
 }
 
@@ -159,10 +181,10 @@ void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const do
            const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t s) {
     if (m <= 0 || n <= 0) return;
     dim3 grid(cdiv(m, GBM), cdiv(n, GBN));
-    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else dgemm_kernel<true, true><<<grid, 256, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    else dgemm_kernel<true, true><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
     NLE_LAUNCH_CHECK();
 }
 
