@@ -432,12 +432,20 @@ sk_reduce_final_kernel(AffinityTables t, const double* __restrict__ Mpart, int n
     if (i >= t.p) return;
     const int a = i / t.nC, b = i - a * t.nC;
     const int y = (int)t.Ysel[i];
+    // the 8 level groups of a lane are independent: their loads are issued together (one L2 round trip per split)
+    double m[NL / 32];
+#pragma unroll
+    for (int q = 0; q < NL / 32; ++q) m[q] = 0.0;
+    for (int ks = 0; ks < nks; ++ks) {
+        const double* src = Mpart + (((size_t)ks * t.nC + b) * nRp + a) * NL + lane;
+#pragma unroll
+        for (int q = 0; q < NL / 32; ++q) m[q] += src[32 * q];
+    }
     double acc = 0.0;
-    for (int l = lane; l < NL; l += 32) {
-        double m = 0.0;
-        for (int ks = 0; ks < nks; ++ks) m += Mpart[(((size_t)ks * t.nC + b) * nRp + a) * NL + l];
-        const int d = l - y;
-        acc = fma(t.Gt[d < 0 ? -d : d], m, acc);
+#pragma unroll
+    for (int q = 0; q < NL / 32; ++q) {
+        const int d = lane + 32 * q - y;
+        acc = fma(t.Gt[d < 0 ? -d : d], m[q], acc);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
