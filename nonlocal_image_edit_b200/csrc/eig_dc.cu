@@ -143,8 +143,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
             acc = warp_sum(acc);
             if (lane == 0) pbuf[c] = acc;
         }
-        __threadfence();
-        grid.sync();
+        grid.sync();   // orders this step's global writes (stcg / plain stores) before every CTA's ldcg reads of the next step
     }
 
     for (int j = 0; j <= n - 3; ++j) {
@@ -235,8 +234,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
         // rotate state
         diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
         { double* t = v; v = cn; cn = t; }
-        __threadfence();
-        grid.sync();
+        grid.sync();   // orders this step's global writes (stcg / plain stores) before every CTA's ldcg reads of the next step
     }
     // epilogue: j = n-2 entries and the last diagonal
     if (b == 0 && tid == 0) {

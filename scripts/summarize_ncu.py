@@ -29,7 +29,7 @@ if os.path.exists(lp):
     for row in csv.DictReader(lines):
         if row.get("Metric Name") != "gpu__time_duration.sum":
             continue
-        name = re.sub(r"\(.*", "", row["Kernel Name"])
+        name = re.sub(r"\(.*", "", row["Kernel Name"]).replace("unnamed>::", "").replace("void ", "")
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}[row["Metric Unit"]]
         agg[name][0] += 1
@@ -59,7 +59,7 @@ if os.path.exists(rp):
                       r"l1tex__data_bank_conflicts_pipe_lsu_mem_shared\.sum|l1tex__data_pipe_lsu_wavefronts_mem_shared\.sum|lts__t_sector_hit_rate\.pct|"
                       r"lts__t_bytes\.sum|smsp__average_warps_issue_stalled_.*_per_issue_active\.ratio)$")
     for vals in rows[2:]:
-        kname = re.sub(r"\(.*", "", vals[hdr.index("Kernel Name")]).replace("void ", "").replace("nle::", "").replace("<unnamed>::", "").replace("unnamed::", "").replace("<", "_").replace(">", "")
+        kname = re.sub(r"\(.*", "", vals[hdr.index("Kernel Name")]).replace("void ", "").replace("nle::", "").replace("<unnamed>::", "").replace("unnamed>::", "").replace("unnamed::", "").replace("<", "_").replace(">", "")
         out = os.path.join(po, f"{tag}_{kname}_full.md")
         with open(out, "w") as f:
             f.write(f"# ncu --set full --clock-control none, kernel `{kname}`, tag {tag}\n\n"
