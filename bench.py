@@ -335,7 +335,12 @@ def run_b200(args, rank, world, local_rank):
     achieved = gram_flops / (st[7] * 1e-3) * 1e-12 if st[7] > 0 else None
     roofline = {"kernel": "gram_cells_kernel (register-generated affinity fragments + FP64 DMMA over (row, level) cells)",
                 "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                "frac": (achieved / peak) if (achieved and peak) else None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one gram_cells_kernel launch at this configuration
+                # (ncu --set full, profiles/r1g_gram_cells_kernel_full.md); algorithmic HBM bytes are Hh once
+                # (cells x nC(nC+1)/2 x 8 B = 1.11e9) plus the split partials: nothing is re-read.
+                "traffic": 1.2391e9 if world == 1 else None,
+                "traffic_source": "profiles/r1g_gram_cells_kernel_full.md" if world == 1 else None,
                 "launch_ms": float(st[7]),
                 "peak_source": "measured in this run by nle_b200_fp64_fma_peak_tflops (register-resident DFMA "
                                "microbenchmark); MEASURED_PEAKS.json has no FP64 figure",
