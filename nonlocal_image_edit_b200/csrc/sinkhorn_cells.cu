@@ -315,11 +315,19 @@ sk_pix_cells_kernel(AffinityTables t, CellIndex ci, int w_given, const double* _
     const int lane = threadIdx.x & 31, q = lane >> 3, sub = lane & 7;
     const int K = ci.koff[t.nrows];
     const int nwarps = gridDim.x * (blockDim.x >> 5);
-    for (int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < K; cell += nwarps) {
-        const int np = ci.pcount[cell];
+    // the metadata of the warp's NEXT cell is fetched while the current one is processed (the per-cell chain
+    // metadata -> columns -> Ec rows is three dependent L2 round trips)
+    int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    int m_np = 0, m_rl = 0, m_lev = 0, m_ps = 0;
+    if (cell < K) { m_np = ci.pcount[cell]; m_rl = ci.row[cell]; m_lev = (int)ci.lev[cell]; m_ps = ci.pstart[cell]; }
+    for (; cell < K; cell += nwarps) {
+        const int np = m_np, rl = m_rl, lev = m_lev;
+        const int* pix = ci.sorted + m_ps;
+        {
+            const int nx = cell + nwarps;
+            if (nx < K) { m_np = ci.pcount[nx]; m_rl = ci.row[nx]; m_lev = (int)ci.lev[nx]; m_ps = ci.pstart[nx]; }
+        }
         if (np == 0) continue;
-        const int rl = ci.row[cell], lev = (int)ci.lev[cell];
-        const int* pix = ci.sorted + ci.pstart[cell];
         const int a_row = t.rowa[t.row0 + rl];
         double f[NB], acc[NB];
 #pragma unroll
