@@ -226,6 +226,36 @@ def test_hx_hy_sweep_matches_oracle(nb, hx, hy):
     assert d.max() <= 1 and (d <= 1).mean() >= PIX_FRAC
 
 
+# degenerate inputs: constant image (Ka = all ones up to the spatial factor), two-level image, single-column image,
+# every pixel a sample (no rest pixels at all), one weight / five weights
+@pytest.mark.parametrize("kind", ["constant", "two_level", "single_column", "all_samples", "saturated"])
+def test_degenerate_images_follow_the_oracle(nb, kind):
+    if kind == "constant":
+        L = np.full((40, 36), 137, np.uint8); a = (4, 4, 30.0, 20.0, 5, 6)
+    elif kind == "two_level":
+        y, x = np.mgrid[0:48, 0:40]
+        L = np.where(((x // 8) + (y // 6)) % 2 == 0, 40, 210).astype(np.uint8); a = (6, 5, 25.0, 15.0, 6, 8)
+    elif kind == "single_column":
+        L = synth_lum(64, 1, seed=5); a = (8, 1, 20.0, 25.0, 4, 4)
+    elif kind == "all_samples":
+        L = synth_lum(6, 7, seed=6); a = (6, 7, 10.0, 30.0, 3, 5)
+    else:
+        L = synth_lum(40, 44, seed=8); L[:20] = 0; L[30:] = 255; a = (5, 4, 15.0, 10.0, 4, 6)
+    try:
+        fo = O.train_dense(L.astype(np.float64), *a)
+    except Exception as e:                      # the reference itself has no defined result here: the GPU path must fail loudly too
+        with pytest.raises(nb.NleError):
+            nb.NLEFilter().trainFilter(L, *a)
+        return
+    f = nb.NLEFilter().trainFilter(L, *a)
+    st, inf = fo.stages, f.info()
+    assert (inf.p, inf.r, inf.r2, inf.k) == (st["p"], st["r"], st["r2"], fo.eigvals.size)
+    assert sq_close(f.eigvals, fo.eigvals)
+    for w in ([2.0], [2.0, 3.0, 4.0, 1.0], [1.5, 2.0, 2.5, 3.0, 1.0]):
+        d = np.abs(f.enhanceLuminance(L, w).astype(int) - O.enhance_luminance(fo, L, w).astype(int))
+        assert d.max() <= 1 and (d <= 1).mean() >= PIX_FRAC
+
+
 def test_train_accepts_float64_channel_like_the_reference(nb):
     L = synth_lum(32, 40)
     a = (4, 5, 25.0, 20.0, 4, 5)
