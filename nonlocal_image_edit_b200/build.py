@@ -33,6 +33,27 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST_TEST = os.path.join(HERE, "host_mirror_test")
+
+
+def build_host_test(force=False):
+    """C++ host-side test program over include/nle_b200.hpp (g++, links the in-tree libnle_b200.so)."""
+    src = os.path.join(HERE, "..", "tests", "cpp", "host_mirror_test.cpp")
+    inc = os.path.join(HERE, "..", "include")
+    deps = [src, os.path.join(inc, "nle_b200.hpp"), os.path.join(inc, "nle_b200.h"), LIB]
+    if not force and os.path.exists(HOST_TEST) and all(os.path.getmtime(d) <= os.path.getmtime(HOST_TEST) for d in deps):
+        return HOST_TEST
+    build()
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-I", inc, src, "-o", HOST_TEST, "-L", HERE, "-lnle_b200",
+           "-Wl,-rpath,$ORIGIN"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        sys.stderr.write(res.stdout + res.stderr)
+        raise RuntimeError("g++ failed building host_mirror_test")
+    return HOST_TEST
+
+
 if __name__ == "__main__":
     build(force=True, verbose="-v" in sys.argv)
+    build_host_test(force=True)
     print(LIB)
