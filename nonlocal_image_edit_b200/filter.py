@@ -8,7 +8,7 @@ column-major order (Eigen's default).  Images are BGR uint8 arrays like cv::Mat.
 
 trainForEnhancement / enhance run the 8-bit BGR<->Lab conversion on the device (csrc/lab.cu, byte-exact with
 cv::cvtColor; `bgrToLab` / `labToBgr` expose it).  cv2.bilateralFilter, which only the denoise variant uses, stays on
-the host where the reference calls OpenCV (filter.cpp:361-371, 528-535), and so does that variant's colour conversion.
+the host where the reference calls OpenCV (filter.cpp:366-371, 535).
 """
 from __future__ import annotations
 
@@ -176,13 +176,11 @@ class NLEFilter:
     # -- helpers ---------------------------------------------------------------------------
     @staticmethod
     def _lab(image):
-        import cv2
-        return cv2.cvtColor(image, cv2.COLOR_BGR2Lab)
+        return bgrToLab(image)          # cv::cvtColor(COLOR_BGR2Lab) on the device, byte-exact (csrc/lab.cu)
 
     @staticmethod
     def _bgr(lab):
-        import cv2
-        return cv2.cvtColor(lab, cv2.COLOR_Lab2BGR)
+        return labToBgr(lab)            # cv::cvtColor(COLOR_Lab2BGR) on the device
 
     def info(self):
         self._require_trained()
