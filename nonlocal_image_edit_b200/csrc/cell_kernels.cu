@@ -229,10 +229,10 @@ constexpr int GC_WARPS = 8;
 // DMMA fragments (lane = 4g + tq): A elem (m = g, k = tq), B elem (k = tq, n = g), D elems (g, 2tq), (g, 2tq+1).
 // The 256-entry Gt table is replicated 16x in shared memory, interleaved so that lane L always reads bank pair
 // (L & 15): the 64-bit look-ups of a warp (two 16-lane phases) are conflict-free whatever the levels are.
-template <int MT>
+template <int MT, int NT, bool SKIP>
 __global__ void __launch_bounds__(GC_WARPS * 32, 1)
 gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __restrict__ cell_lev,
-                  const double* __restrict__ Hh, int ld, int nab, int ntasks, int nsplit, int accumulate,
+                  const double* __restrict__ Hh, int ld, int nabA, int nabB, int ntasks, int nsplit, int accumulate,
                   double* __restrict__ part) {
     __shared__ double Gs16[256 * 16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -241,28 +241,34 @@ gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t*
     const int task = blockIdx.x * GC_WARPS + warp;
     if (task >= ntasks) return;
     const int nC = t.nC, nR = t.nR;
-    constexpr int T = 8 * MT;
-    const int pair = task / (nab * nab);
-    const int rem = task - pair * nab * nab;
-    const int ab = rem / nab, abp = rem - ab * nab;
+    constexpr int TA = 8 * MT, TB = 8 * NT;
+    const int pair = task / (nabA * nabB);
+    const int rem = task - pair * nabA * nabB;
+    const int ab = rem / nabB, abp = rem - ab * nabB;
     int b, bp;
     pair_decode(pair, nC, b, bp);
     const int g = lane >> 2, tq = lane & 3;
     const int split = blockIdx.y;
 
-    int yA[MT], yB[MT], aA[MT], aB[MT];
+    int yA[MT], yB[NT], aA[MT], aB[NT];
+    bool okA[MT], okB[NT];          // SKIP: DMMA tiles that lie entirely in the padding of a blocked shape are not issued
 #pragma unroll
     for (int u = 0; u < MT; ++u) {
-        aA[u] = ab * T + 8 * u + g;
-        aB[u] = abp * T + 8 * u + g;
+        aA[u] = ab * TA + 8 * u + g;
+        okA[u] = ab * TA + 8 * u < nR;
         yA[u] = aA[u] < nR ? (int)t.Ysel[aA[u] * nC + b] : 0;
-        yB[u] = aB[u] < nR ? (int)t.Ysel[aB[u] * nC + bp] : 0;
     }
-    double acc[MT][MT][2];
+#pragma unroll
+    for (int v = 0; v < NT; ++v) {
+        aB[v] = abp * TB + 8 * v + g;
+        okB[v] = abp * TB + 8 * v < nR;
+        yB[v] = aB[v] < nR ? (int)t.Ysel[aB[v] * nC + bp] : 0;
+    }
+    double acc[MT][NT][2];
 #pragma unroll
     for (int u = 0; u < MT; ++u)
 #pragma unroll
-        for (int v = 0; v < MT; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+        for (int v = 0; v < NT; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
 
     const int nsteps = koff[t.nrows] >> 2;
     int k = (int)(((long long)nsteps * split) / nsplit) * 4;
@@ -278,14 +284,13 @@ gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t*
         row = lo;
     }
     int krow_end = koff[row + 1];
-    double erA[MT], erB[MT];
+    double erA[MT], erB[NT];
     auto load_er = [&]() {
         const double* er = t.Er + (size_t)(t.row0 + row) * nR;
 #pragma unroll
-        for (int u = 0; u < MT; ++u) {
-            erA[u] = aA[u] < nR ? er[aA[u]] : 0.0;
-            erB[u] = aB[u] < nR ? er[aB[u]] : 0.0;
-        }
+        for (int u = 0; u < MT; ++u) erA[u] = aA[u] < nR ? er[aA[u]] : 0.0;
+#pragma unroll
+        for (int v = 0; v < NT; ++v) erB[v] = aB[v] < nR ? er[aB[v]] : 0.0;
     };
     load_er();
     const double* gs = Gs16 + (lane & 15);
@@ -321,49 +326,54 @@ gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t*
             }
             const int lv = __shfl_sync(0xffffffffu, lv32, 4 * i + tq);
             const double hh = __shfl_sync(0xffffffffu, hh32, 4 * i + tq);
-            double a[MT], bf[MT];
+            double a[MT], bf[NT];
 #pragma unroll
             for (int u = 0; u < MT; ++u) {
-                const int dA = lv - yA[u], dB = lv - yB[u];
+                const int dA = lv - yA[u];
                 a[u] = erA[u] * gs[(dA < 0 ? -dA : dA) << 4];
-                bf[u] = (erB[u] * hh) * gs[(dB < 0 ? -dB : dB) << 4];
+            }
+#pragma unroll
+            for (int v = 0; v < NT; ++v) {
+                const int dB = lv - yB[v];
+                bf[v] = (erB[v] * hh) * gs[(dB < 0 ? -dB : dB) << 4];
             }
 #pragma unroll
             for (int u = 0; u < MT; ++u)
 #pragma unroll
-                for (int v = 0; v < MT; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], bf[v]);
+                for (int v = 0; v < NT; ++v)
+                    if (!SKIP || (okA[u] && okB[v])) dmma884(acc[u][v][0], acc[u][v][1], a[u], bf[v]);
         }
         k += 32;
     }
 
-    double* out = part + ((size_t)split * ntasks + task) * (T * T);
+    double* out = part + ((size_t)split * ntasks + task) * (TA * TB);
 #pragma unroll
     for (int u = 0; u < MT; ++u)
 #pragma unroll
-        for (int v = 0; v < MT; ++v) {
-            double2* o = reinterpret_cast<double2*>(out + (8 * u + g) * T + 8 * v + 2 * tq);
+        for (int v = 0; v < NT; ++v) {
+            double2* o = reinterpret_cast<double2*>(out + (8 * u + g) * TB + 8 * v + 2 * tq);
             double2 val = make_double2(acc[u][v][0], acc[u][v][1]);
             if (accumulate) { const double2 old = *o; val.x += old.x; val.y += old.y; }
             *o = val;
         }
 }
 
-__global__ void gram_cells_reduce_kernel(const double* __restrict__ part, int p, int nR, int nC, int T, int nab,
-                                         int ntasks, int nsplit, double* __restrict__ G) {
+__global__ void gram_cells_reduce_kernel(const double* __restrict__ part, int p, int nR, int nC, int TA, int TB, int nabA,
+                                         int nabB, int ntasks, int nsplit, double* __restrict__ G) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x, j = blockIdx.y;
     if (i >= p) return;
     int a = i / nC, b = i - a * nC, ap = j / nC, bp = j - ap * nC;
     if (b > bp || (b == bp && a > ap)) { int tmp = a; a = ap; ap = tmp; tmp = b; b = bp; bp = tmp; }
     const int pair = pair_start(b, nC) + (bp - b);
-    const int task = pair * nab * nab + (a / T) * nab + (ap / T);
-    const size_t off = (size_t)task * (T * T) + (size_t)(a % T) * T + (ap % T);
+    const int task = pair * nabA * nabB + (a / TA) * nabB + (ap / TB);
+    const size_t off = (size_t)task * (TA * TB) + (size_t)(a % TA) * TB + (ap % TB);
     double acc = 0.0;
-    for (int s = 0; s < nsplit; ++s) acc += part[(size_t)s * ntasks * (T * T) + off];
+    for (int s = 0; s < nsplit; ++s) acc += part[(size_t)s * ntasks * (TA * TB) + off];
     G[i + (size_t)j * p] = acc;
 }
 
 struct CellGeom {
-    int npairs, ld, MT, T, nab, ntasks, ncta, nsplit, capc, rows_batch;
+    int npairs, ld, MT, NT, TA, TB, nabA, nabB, ntasks, ncta, nsplit, capc, rows_batch;
     size_t hh_doubles, part_doubles, lev_bytes, int_count;
 };
 
@@ -371,12 +381,17 @@ CellGeom cell_geometry(const AffinityTables& t) {
     CellGeom g;
     g.npairs = t.nC * (t.nC + 1) / 2;
     g.ld = (g.npairs + 3) & ~3;
+    // warp tile: 8*MT grid rows (A side) x 8*NT grid rows (B side).  Up to 5 DMMA tiles per side: square; 6-7 (nR = 50 at
+    // p = 2500): 7 x 4 (28 tiles; 7 x 7 would need 196 accumulator registers); beyond: blocks of at most 7 x 4.
     const int tiles = cdiv(t.nR, 8);
-    int nab = cdiv(tiles, 5);
-    g.MT = cdiv(tiles, nab);
-    g.nab = nab;
-    g.T = 8 * g.MT;
-    g.ntasks = g.npairs * nab * nab;
+    if (tiles <= 5) {
+        g.MT = g.NT = tiles; g.nabA = g.nabB = 1;
+    } else {
+        g.nabA = cdiv(tiles, 7); g.MT = cdiv(tiles, g.nabA);
+        g.NT = 4; g.nabB = cdiv(tiles, 4);
+    }
+    g.TA = 8 * g.MT; g.TB = 8 * g.NT;
+    g.ntasks = g.npairs * g.nabA * g.nabB;
     g.ncta = cdiv(g.ntasks, GC_WARPS);
     g.nsplit = std::max(1, (7 * sm_count()) / g.ncta);
     g.nsplit = std::min(g.nsplit, std::max(1, t.nrows));
@@ -386,7 +401,7 @@ CellGeom cell_geometry(const AffinityTables& t) {
     const size_t budget = (size_t)320 << 20;   // doubles
     g.rows_batch = (int)std::max<size_t>(1, std::min<size_t>((size_t)t.nrows, budget / per_row));
     g.hh_doubles = per_row * g.rows_batch;
-    g.part_doubles = (size_t)g.nsplit * g.ntasks * g.T * g.T;
+    g.part_doubles = (size_t)g.nsplit * g.ntasks * g.TA * g.TB;
     g.lev_bytes = (size_t)g.capc * g.rows_batch;
     g.int_count = 2 * (size_t)g.rows_batch + 8;
     return g;
@@ -608,11 +623,11 @@ size_t gram_cells_scratch_doubles(const AffinityTables& t) {
     return g.hh_doubles + g.part_doubles + (g.lev_bytes + 7) / 8 + (g.int_count * 4 + 7) / 8 + 8;
 }
 
-template <int MT>
+template <int MT, int NT>
 static void launch_gc(const AffinityTables& tb, const CellGeom& g, const int* koff, const uint8_t* cell_lev,
                       const double* Hh, int accumulate, double* part, cudaStream_t s) {
-    gram_cells_kernel<MT><<<dim3(g.ncta, g.nsplit), GC_WARPS * 32, 0, s>>>(tb, koff, cell_lev, Hh, g.ld, g.nab, g.ntasks,
-                                                                            g.nsplit, accumulate, part);
+    gram_cells_kernel<MT, NT, (MT != NT)><<<dim3(g.ncta, g.nsplit), GC_WARPS * 32, 0, s>>>(tb, koff, cell_lev, Hh, g.ld, g.nabA, g.nabB,
+                                                                                g.ntasks, g.nsplit, accumulate, part);
     NLE_LAUNCH_CHECK();
 }
 
@@ -643,16 +658,19 @@ void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch
         NLE_LAUNCH_CHECK();
         cell_hist_kernel<<<tb.nrows, 256, hsm, s>>>(tb, cb, koff, g.npairs, g.ld, cell_lev, Hh);
         NLE_LAUNCH_CHECK();
-        switch (g.MT) {
-            case 1: launch_gc<1>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
-            case 2: launch_gc<2>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
-            case 3: launch_gc<3>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
-            case 4: launch_gc<4>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
-            default: launch_gc<5>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+        switch (g.MT * 10 + g.NT) {
+            case 11: launch_gc<1, 1>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 22: launch_gc<2, 2>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 33: launch_gc<3, 3>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 44: launch_gc<4, 4>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 55: launch_gc<5, 5>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 64: launch_gc<6, 4>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            case 74: launch_gc<7, 4>(tb, g, koff, cell_lev, Hh, batch > 0, part, s); break;
+            default: throw Unsupported{"gram: no kernel instance for the warp tile " + std::to_string(g.MT) + " x " + std::to_string(g.NT)};
         }
     }
-    gram_cells_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(part, t.p, t.nR, t.nC, g.T, g.nab, g.ntasks,
-                                                                       g.nsplit, G);
+    gram_cells_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(part, t.p, t.nR, t.nC, g.TA, g.TB, g.nabA, g.nabB,
+                                                                       g.ntasks, g.nsplit, G);
     NLE_LAUNCH_CHECK();
 }
 
