@@ -391,11 +391,20 @@ dc_setup_kernel(int n, int depth, const double* __restrict__ e, const double* __
                     continue;
                 }
                 if (prev >= 0) {
-                    double sv = -zsrt[prev], cv = zsrt[i];
-                    const double tt = hypot(cv, sv);
+                    // dlaed2's test |t c s| <= tol with c = z_i/tt, s = -z_prev/tt.  This scan is serial (one thread,
+                    // up to n steps per merge), so the hypot and the two divisions are only paid when the
+                    // division-free form of the same inequality, |t z_i z_prev| <= tol (z_i^2 + z_prev^2), holds
+                    // (with a hair of slack; the exact test below still decides).
+                    const double zp = zsrt[prev], zi = zsrt[i];
                     const double t = dsrt[i] - dsrt[prev];
-                    cv /= tt; sv /= tt;
-                    if (fabs(t * cv * sv) <= tol) {
+                    double sv = -zp, cv = zi, tt = 1.0;
+                    bool rot = false;
+                    if (fabs(t * zi * zp) <= 1.000001 * tol * fma(zi, zi, zp * zp)) {
+                        tt = hypot(cv, sv);
+                        cv /= tt; sv /= tt;
+                        rot = fabs(t * cv * sv) <= tol;
+                    }
+                    if (rot) {
                         // rotate (prev, i): z_prev -> 0 (deflated), z_i -> tt
                         zsrt[i] = tt;
                         a.rotA[off + nrot] = csrt[prev]; a.rotB[off + nrot] = csrt[i];
