@@ -7,15 +7,17 @@ Metric (BASELINE.json): enhance MP/s (p=1600, k=50).  A "step" = train + enhance
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-N=1 workload = BASELINE.json configs[2]: synthetic 1024x1024 8-bit luminance, 40x40=1600 samples,
+N=1 workload = BASELINE.json configs[2]: synthetic 1024x1024 gray image, 40x40=1600 samples,
 hx=500 hy=30, 20 Sinkhorn iterations, k=50, weights 2 3 4 1 (SURVEY.md 8d "S-gray-1024").
 N>1 = weak scaling: the image grows to (1024*N) x 1024 and is sharded by image rows, one slab per
 rank; NCCL carries the p-vector Sinkhorn sums, one p x p Gram and the k-vector V^T z.
 
-value : MP/s with the luminance slab already resident in HBM (nle_b200_train_u8_dev +
+The workload is a gray image in 3 equal BGR channels, as the reference's CLI would read it; the filter's input is the L
+channel of its 8-bit BGR2Lab conversion (filter.cpp:463-466).
+value : MP/s with that luminance slab already resident in HBM (nle_b200_train_u8_dev +
         nle_b200_enhance_luminance_u8_dev), timed with CUDA events, max over ranks.
-e2e   : MP/s through the host-pointer C ABI (nle_b200_train_u8_sharded + enhance_luminance_u8)
-        from pinned host memory, H2D and D2H inside the timed region.
+e2e   : MP/s through the image-level host-pointer C ABI (nle_b200_train_bgr_u8 + nle_b200_enhance_bgr_u8): BGR image
+        in pinned host memory in, BGR image out, colour conversion on the device, H2D and D2H inside the timed region.
 --impl reference : the CPU restatement of the reference (oracle/nle_oracle.py, NumPy/SciPy FP64,
         all host threads) on a bounded crop of the same workload.  The reference binary itself
         needs Eigen + OpenCV C++ which this image does not have.
@@ -28,6 +30,13 @@ import subprocess
 import sys
 import threading
 import time
+
+if "reference" in sys.argv:
+    # the CPU arm uses every host core it is allowed to: torchrun exports OMP_NUM_THREADS=1 for its children, which
+    # must be undone BEFORE NumPy / OpenBLAS load
+    _n = str(len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1))
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS"):
+        os.environ[_v] = _n
 
 import numpy as np
 
