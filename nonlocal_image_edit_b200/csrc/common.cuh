@@ -142,6 +142,7 @@ void guarded_inv_sqrt(const double* v, double* out, int n, double eps, cudaStrea
 struct EigWorkspace {
     DevBuf<double> W, As, T, lam_unsorted;
     DevBuf<double> Qa, Qb, Sb, dcd;                     // divide & conquer buffers (eig_dc.cu)
+    DevBuf<double> wyT;                                 // T factors of the blocked back-transformation
     DevBuf<int> dci;
     int dc_cap = 0;
     void reserve_dc(int n);

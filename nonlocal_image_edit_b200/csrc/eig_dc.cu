@@ -28,6 +28,7 @@
 #include <algorithm>
 #include <chrono>
 #include <cstdlib>
+#include <string>
 
 #include "common.cuh"
 
@@ -36,6 +37,13 @@ namespace cg = cooperative_groups;
 namespace nle {
 
 namespace {
+
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe: lane = 4g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
 
 constexpr double kUnitRoundoff = 1.1102230246251565e-16;
 constexpr int kLeaf = 32;
@@ -745,6 +753,168 @@ __global__ void backtransform_kernel(const double* __restrict__ A, int lda, cons
         for (int i = lane; i < n; i += 32) zc[i] = z[i];
 }
 
+// ---------------------------------------------------------------------------------------------
+// Blocked back-transformation (compact WY, LAPACK dlarft/dlarfb forward-columnwise) on the FP64 tensor pipe.
+// Reflectors are taken 32 at a time:  H_{j0} ... H_{j0+31} = I - V T V^T  with V the 32 reflector columns (unit lower
+// trapezoidal, read straight from A with a mask) and T upper triangular,
+//     T(i,i) = tau_i,   T(0:i, i) = -tau_i T(0:i,0:i) (V(:,0:i)^T v_i).
+//   bt_tfactor_kernel   one CTA per block: S = V^T V, then the T recursion (one warp)
+//   bt_wy_kernel        one CTA per 8 eigenvector columns (one DMMA n-tile), the columns live in shared memory;
+//                       per block, last to first:  W = V^T Z (DMMA, K = rows, split over the warps),  W <- T W,
+//                       Z -= V W (DMMA, K = 32).
+// Against the per-reflector kernel above (bound by shared-memory traffic: 7 accesses per element and reflector pair)
+// every reflector element is now used for 8 columns per load.
+constexpr int kWyB = 32;
+
+__global__ void __launch_bounds__(256)
+bt_tfactor_kernel(const double* __restrict__ A, int lda, int n, const double* __restrict__ tau, int nrefl,
+                  double* __restrict__ Tall) {
+    __shared__ double Vc[64][kWyB + 1];
+    __shared__ double Ss[kWyB][kWyB + 1];
+    __shared__ double Ts[kWyB][kWyB + 1];
+    const int kb = blockIdx.x, tid = threadIdx.x;
+    const int j0 = kb * kWyB;
+    const int nb = min(kWyB, nrefl - j0);
+    const int ta = tid >> 3, tb0 = (tid & 7) * 4;           // thread -> S[ta][tb0 .. tb0+3]
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    for (int r0 = j0 + 1; r0 < n; r0 += 64) {
+        __syncthreads();
+        for (int e = tid; e < 64 * kWyB; e += 256) {
+            const int r = e & 63, c = e >> 6;
+            const int row = r0 + r, j = j0 + c;
+            Vc[r][c] = (row < n && c < nb && row >= j + 1) ? A[(size_t)row + (size_t)j * lda] : 0.0;
+        }
+        __syncthreads();
+#pragma unroll 8
+        for (int r = 0; r < 64; ++r) {
+            const double va = Vc[r][ta];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) acc[q] = fma(va, Vc[r][tb0 + q], acc[q]);
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) Ss[ta][tb0 + q] = acc[q];
+    for (int e = tid; e < kWyB * (kWyB + 1); e += 256) (&Ts[0][0])[e] = 0.0;
+    __syncthreads();
+    if (tid < 32) {
+        const int r = tid;
+        for (int i = 0; i < nb; ++i) {
+            const double ti = tau[j0 + i];
+            double v = 0.0;
+            if (r < i) {
+                for (int q = r; q < i; ++q) v = fma(Ts[r][q], Ss[q][i], v);
+                v *= -ti;
+            } else if (r == i) {
+                v = ti;
+            }
+            __syncwarp();
+            if (r <= i) Ts[r][i] = v;
+            __syncwarp();
+        }
+    }
+    __syncthreads();
+    double* out = Tall + (size_t)kb * kWyB * kWyB;
+    for (int e = tid; e < kWyB * kWyB; e += 256) out[e] = Ts[e >> 5][e & 31];
+}
+
+__global__ void __launch_bounds__(256, 1)
+bt_wy_kernel(const double* __restrict__ A, int lda, int n, const double* __restrict__ Tall, int nblocks, int nrefl,
+             double* __restrict__ Z, int ldz, const int* __restrict__ collist, const int* __restrict__ count, int vec_limit) {
+    extern __shared__ double wsm[];
+    double* Zs = wsm;                         // n x 8, row-major
+    double* Wp = Zs + (size_t)n * 8;          // 8 warps x 32 x 8 partials of V^T Z
+    double* Ws = Wp + 8 * kWyB * 8;           // 32 x 8
+    double* W2 = Ws + kWyB * 8;               // 32 x 8   (T W)
+    double* Ts = W2 + kWyB * 8;               // 32 x 33
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int lim = vec_limit >= 0 ? min(vec_limit, *count) : n;
+    if (blockIdx.x * 8 >= lim) return;
+    int cols[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+        const int idx = blockIdx.x * 8 + c;
+        cols[c] = idx < lim ? collist[idx] : -1;
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        for (int row = tid; row < n; row += 256) Zs[(size_t)row * 8 + c] = cols[c] >= 0 ? Z[(size_t)row + (size_t)cols[c] * ldz] : 0.0;
+    __syncthreads();
+    for (int kb = nblocks - 1; kb >= 0; --kb) {
+        const int j0 = kb * kWyB;
+        const int nb = min(kWyB, nrefl - j0);
+        const int r_lo = j0 + 1;                                   // first row any reflector of the block touches
+        for (int e = tid; e < kWyB * kWyB; e += 256) Ts[(e >> 5) * (kWyB + 1) + (e & 31)] = Tall[(size_t)kb * kWyB * kWyB + e];
+        // ---- phase 1: W = V^T Z, k-steps of 4 rows (aligned to 4) dealt round-robin to the warps
+        {
+            double acc[4][2];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
+            const int rs = r_lo & ~3;
+#pragma unroll 2
+            for (int rb = rs + 4 * warp; rb < n; rb += 32) {
+                const int row = rb + tq;
+                const bool rv = row < n && row >= r_lo;
+                const double bfr = rv ? Zs[(size_t)row * 8 + g] : 0.0;
+                double afr[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int c = 8 * u + g;
+                    afr[u] = (rv && c < nb && row >= j0 + c + 1) ? A[(size_t)row + (size_t)(j0 + c) * lda] : 0.0;
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) dmma884(acc[u][0], acc[u][1], afr[u], bfr);
+            }
+            double* wp = Wp + warp * (kWyB * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                wp[(8 * u + g) * 8 + 2 * tq] = acc[u][0];
+                wp[(8 * u + g) * 8 + 2 * tq + 1] = acc[u][1];
+            }
+        }
+        __syncthreads();
+        {
+            double w = 0.0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) w += Wp[q * (kWyB * 8) + tid];
+            Ws[tid] = w;
+        }
+        __syncthreads();
+        // ---- phase 2: W2 = -(T W)   (T upper triangular; the sign folds the subtraction of phase 3 into the DMMA)
+        {
+            const int r = tid >> 3, c = tid & 7;
+            double v = 0.0;
+            for (int q = r; q < nb; ++q) v = fma(Ts[r * (kWyB + 1) + q], Ws[q * 8 + c], v);
+            W2[tid] = -v;
+        }
+        __syncthreads();
+        // ---- phase 3: Z += V W2, m-tiles of 8 rows (aligned to 8) dealt round-robin to the warps
+        {
+            const int rs = r_lo & ~7;
+#pragma unroll 2
+            for (int rb = rs + 8 * warp; rb < n; rb += 64) {
+                const int row = rb + g;
+                const bool rv = row < n && row >= r_lo;
+                double c0 = 0.0, c1 = 0.0;
+                if (rv) { c0 = Zs[(size_t)row * 8 + 2 * tq]; c1 = Zs[(size_t)row * 8 + 2 * tq + 1]; }
+#pragma unroll
+                for (int kk = 0; kk < kWyB / 4; ++kk) {
+                    const int c = 4 * kk + tq;
+                    const double afr = (rv && c < nb && row >= j0 + c + 1) ? A[(size_t)row + (size_t)(j0 + c) * lda] : 0.0;
+                    const double bfr = W2[c * 8 + g];
+                    dmma884(c0, c1, afr, bfr);
+                }
+                if (rv) { Zs[(size_t)row * 8 + 2 * tq] = c0; Zs[(size_t)row * 8 + 2 * tq + 1] = c1; }
+            }
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int c = 0; c < 8; ++c)
+        if (cols[c] >= 0)
+            for (int row = tid; row < n; row += 256) Z[(size_t)row + (size_t)cols[c] * ldz] = Zs[(size_t)row * 8 + c];
+}
+
 __global__ void dc_check_kernel(const double* __restrict__ U, int ldu, int n, int* __restrict__ fail) {
     // column norms must be 1 to ~1e-8 and finite (cheap sanity check of the whole pipeline)
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
@@ -887,7 +1057,23 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
             reflector_dots_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(As, n, n, gdot);
             NLE_LAUNCH_CHECK();
         }
-        if (m > 0) {
+        // compact-WY blocks on DMMA when the 8-column tile fits in shared memory; NLE_B200_BT=pair keeps the per-reflector kernel
+        static const bool bt_pair_env = [] { const char* e = getenv("NLE_B200_BT"); return e && std::string(e) == "pair"; }();
+        const int nrefl = n - 2;
+        const int nblocks = cdiv(nrefl, kWyB);
+        const size_t wy_smem = ((size_t)n * 8 + 8 * kWyB * 8 + 2 * kWyB * 8 + kWyB * (kWyB + 1)) * sizeof(double);
+        if (m > 0 && !bt_pair_env && n >= 64 && wy_smem <= (size_t)max_smem) {
+            if (ws.wyT.n < (size_t)nblocks * kWyB * kWyB) ws.wyT.alloc((size_t)nblocks * kWyB * kWyB);
+            bt_tfactor_kernel<<<nblocks, 256, 0, s>>>(As, n, n, tau, nrefl, ws.wyT.p);
+            NLE_LAUNCH_CHECK();
+            static size_t conf_wy = 0;
+            if (wy_smem > conf_wy) {
+                NLE_CUDA(cudaFuncSetAttribute(bt_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wy_smem));
+                conf_wy = wy_smem;
+            }
+            bt_wy_kernel<<<cdiv(m, 8), 256, wy_smem, s>>>(As, n, n, ws.wyT.p, nblocks, nrefl, Qc, n, collist, count, vec_limit);
+            NLE_LAUNCH_CHECK();
+        } else if (m > 0) {
             backtransform_kernel<<<cdiv(m, wpb), wpb * 32, smem, s>>>(As, n, tau, gdot, n, Qc, n, collist, count, vec_limit);
             NLE_LAUNCH_CHECK();
         }
