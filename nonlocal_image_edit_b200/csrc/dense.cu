@@ -259,14 +259,14 @@ sk_sample_step_kernel(int m, int n, const double* __restrict__ A, int lda, const
     if (i < m) {
         const double* a = A + i;
         int j = slot;
-        for (; j + 3 * 32 < n; j += 4 * 32) {
-            const double a0 = a[(size_t)j * lda], a1 = a[(size_t)(j + 32) * lda];
-            const double a2 = a[(size_t)(j + 64) * lda], a3 = a[(size_t)(j + 96) * lda];
-            const double t0 = t[j], t1 = t[j + 32], t2 = t[j + 64], t3 = t[j + 96];
-            acc0 = fma(a0, t0, acc0); acc1 = fma(a0, lam[j] * t0, acc1);
-            acc0 = fma(a1, t1, acc0); acc1 = fma(a1, lam[j + 32] * t1, acc1);
-            acc0 = fma(a2, t2, acc0); acc1 = fma(a2, lam[j + 64] * t2, acc1);
-            acc0 = fma(a3, t3, acc0); acc1 = fma(a3, lam[j + 96] * t3, acc1);
+        // 8 column phases in flight per thread (the matrix is L2 resident: the pass is latency bound); summation order
+        // is the plain ascending one
+        for (; j + 7 * 32 < n; j += 8 * 32) {
+            double av[8], tv[8], lv[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { av[u] = a[(size_t)(j + 32 * u) * lda]; tv[u] = t[j + 32 * u]; lv[u] = lam[j + 32 * u]; }
+#pragma unroll
+            for (int u = 0; u < 8; ++u) { acc0 = fma(av[u], tv[u], acc0); acc1 = fma(av[u], lv[u] * tv[u], acc1); }
         }
         for (; j < n; j += 32) {
             const double a0 = a[(size_t)j * lda], t0 = t[j];
@@ -299,7 +299,15 @@ __global__ void sk_phiT_kernel(int m, int n, const double* __restrict__ A, int l
     if (warp >= n) return;
     const double* col = A + (size_t)warp * lda;
     double acc0 = 0.0, acc1 = 0.0;
-    for (int i = lane; i < m; i += 32) {
+    int i = lane;
+    for (; i + 7 * 32 < m; i += 8 * 32) {          // 8 loads in flight per lane, ascending summation order
+        double av[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) av[u] = col[i + 32 * u];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { acc0 = fma(av[u], x[i + 32 * u], acc0); acc1 = fma(av[u], sv[i + 32 * u], acc1); }
+    }
+    for (; i < m; i += 32) {
         const double a = col[i];
         acc0 = fma(a, x[i], acc0);
         acc1 = fma(a, sv[i], acc1);
