@@ -565,16 +565,19 @@ dc_gemm_kernel(int n, int depth, const double* __restrict__ Q, int ldq, const do
     const int k = a.kArr[node];
     const int i0 = blockIdx.x * DBM, j0 = blockIdx.y * DBN;
     if (i0 >= nm || j0 >= k) return;
-    __shared__ double As[DBK][DBM + 1];
-    __shared__ double Bs[DBK][DBN + 1];
+    // 64 x 64 tile on the FP64 tensor pipe: 8 warps as 4 (M) x 2 (N), warp tile 16 x 32 = 2 x 4 DMMA tiles
+    constexpr int DLD = DBM + 4;         // k-major rows, stride % 16 == 4: the fragment loads of a half-warp are conflict-free
+    __shared__ double As[DBK][DLD];
+    __shared__ double Bs[DBK][DLD];
     __shared__ int cols[DBK];
-    const int tid = threadIdx.x;
-    const int tx = tid & 15, ty = tid >> 4;
-    double acc[4][4];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int wm = warp & 3, wn = warp >> 2;
+    double acc[2][4][2];
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
+    for (int u = 0; u < 2; ++u)
 #pragma unroll
-        for (int vv = 0; vv < 4; ++vv) acc[u][vv] = 0.0;
+        for (int vv = 0; vv < 4; ++vv) acc[u][vv][0] = acc[u][vv][1] = 0.0;
     for (int k0 = 0; k0 < k; k0 += DBK) {
         if (tid < DBK) cols[tid] = (k0 + tid < k) ? a.colmap[off + k0 + tid] : -1;
         __syncthreads();
@@ -594,29 +597,30 @@ dc_gemm_kernel(int n, int depth, const double* __restrict__ Q, int ldq, const do
         }
         __syncthreads();
 #pragma unroll
-        for (int kk = 0; kk < DBK; ++kk) {
-            double av[4], bv[4];
+        for (int k4 = 0; k4 < DBK / 4; ++k4) {
+            double av[2], bv[4];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) av[u] = As[kk][tx + 16 * u];
+            for (int u = 0; u < 2; ++u) av[u] = As[k4 * 4 + tq][wm * 16 + u * 8 + g];
 #pragma unroll
-            for (int vv = 0; vv < 4; ++vv) bv[vv] = Bs[kk][ty + 16 * vv];
+            for (int vv = 0; vv < 4; ++vv) bv[vv] = Bs[k4 * 4 + tq][wn * 32 + vv * 8 + g];
 #pragma unroll
-            for (int u = 0; u < 4; ++u)
+            for (int u = 0; u < 2; ++u)
 #pragma unroll
-                for (int vv = 0; vv < 4; ++vv) acc[u][vv] = fma(av[u], bv[vv], acc[u][vv]);
+                for (int vv = 0; vv < 4; ++vv) dmma884(acc[u][vv][0], acc[u][vv][1], av[u], bv[vv]);
         }
         __syncthreads();
     }
 #pragma unroll
-    for (int vv = 0; vv < 4; ++vv) {
-        const int gj = j0 + ty + 16 * vv;
-        if (gj >= k) continue;
+    for (int u = 0; u < 2; ++u) {
+        const int gi = i0 + wm * 16 + u * 8 + g;
+        if (gi >= nm) continue;
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
-            const int gi = i0 + tx + 16 * u;
-            if (gi >= nm) continue;
-            Qn[(size_t)(off + gi) + (size_t)(off + gj) * ldq] = acc[u][vv];
-        }
+        for (int vv = 0; vv < 4; ++vv)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int gj = j0 + wn * 32 + vv * 8 + 2 * tq + e;
+                if (gj < k) Qn[(size_t)(off + gi) + (size_t)(off + gj) * ldq] = acc[u][vv][e];
+            }
     }
 }
 
