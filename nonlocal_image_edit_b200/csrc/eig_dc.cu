@@ -387,7 +387,69 @@ dc_setup_kernel(int n, int depth, const double* __restrict__ e, const double* __
     const double tol = 8.0 * kUnitRoundoff * fmax(dmax, zmax);
     __syncthreads();   // everyone has read draw[] before it is reused for the deflated list
 
-    if (tid == 0) {
+    // Fast path (the common case on these spectra): if no pair of consecutive non-deflated poles passes the rotation
+    // screen, the deflation is a pure compaction -- flags, a block scan and a parallel scatter -- and the serial scan
+    // below (one thread, up to n dependent steps) is skipped.  The serial scan decides whenever a rotation is possible.
+    __shared__ int s_fast, s_wcnt[32], s_wlast[32];
+    if (tid == 0) s_fast = 1;
+    __syncthreads();
+    {
+        const bool all_defl = rho * zmax <= tol;
+        const int per = (nm + nt - 1) / nt;
+        const int c0 = min(nm, tid * per), c1 = min(nm, c0 + per);
+        int cnt = 0, last = -1;
+        for (int i = c0; i < c1; ++i)
+            if (!all_defl && !(rho * fabs(zsrt[i]) <= tol)) { ++cnt; last = i; }
+        // block-wide exclusive scan: sum of cnt, max of last
+        const int lane = tid & 31, wid = tid >> 5, nwarp = (nt + 31) >> 5;
+        int icnt = cnt, ilast = last;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int vc = __shfl_up_sync(0xffffffffu, icnt, o);
+            const int vl = __shfl_up_sync(0xffffffffu, ilast, o);
+            if (lane >= o) { icnt += vc; ilast = max(ilast, vl); }
+        }
+        if (lane == 31) { s_wcnt[wid] = icnt; s_wlast[wid] = ilast; }
+        __syncthreads();
+        int bcnt = 0, blast = -1, total_k = 0;
+        for (int w = 0; w < nwarp; ++w) {
+            if (w < wid) { bcnt += s_wcnt[w]; blast = max(blast, s_wlast[w]); }
+            total_k += s_wcnt[w];
+        }
+        const int pc = __shfl_up_sync(0xffffffffu, icnt, 1), pl = __shfl_up_sync(0xffffffffu, ilast, 1);
+        const int excl_cnt = bcnt + (lane > 0 ? pc : 0);
+        const int excl_last = max(blast, lane > 0 ? pl : -1);
+        int prev = excl_last;
+        bool maybe_rot = false;
+        for (int i = c0; i < c1; ++i) {
+            if (all_defl || rho * fabs(zsrt[i]) <= tol) continue;
+            if (prev >= 0) {
+                const double zp = zsrt[prev], zi = zsrt[i];
+                const double t = dsrt[i] - dsrt[prev];
+                if (fabs(t * zi * zp) <= 1.000001 * tol * fma(zi, zi, zp * zp)) maybe_rot = true;
+            }
+            prev = i;
+        }
+        if (maybe_rot) s_fast = 0;
+        __syncthreads();
+        if (s_fast) {
+            int kpos = excl_cnt, dpos = c0 - excl_cnt;
+            for (int i = c0; i < c1; ++i) {
+                if (!all_defl && !(rho * fabs(zsrt[i]) <= tol)) {
+                    a.dk[off + kpos] = dsrt[i]; a.zk[off + kpos] = zsrt[i]; a.colmap[off + kpos] = csrt[i];
+                    ++kpos;
+                } else {
+                    draw[dpos] = dsrt[i]; cdef[dpos] = csrt[i];
+                    ++dpos;
+                }
+            }
+            if (tid == 0) {
+                s_k = total_k; s_ndef = nm - total_k; s_nrot = 0;
+                a.kArr[node] = total_k; a.nrotArr[node] = 0; a.rhoArr[node] = rho;
+            }
+        }
+    }
+    if (tid == 0 && !s_fast) {
         int k = 0, ndef = 0, nrot = 0;
         if (rho * zmax <= tol) {
             for (int i = 0; i < nm; ++i) { draw[ndef] = dsrt[i]; cdef[ndef] = csrt[i]; ++ndef; }
