@@ -418,7 +418,9 @@ CellGeom cell_geometry(const AffinityTables& t) {
 //                      DMMA with the cell's pixels (8 at a time) as the M tile, K = nC; FX is streamed once
 // Work: K_cells*p*k' + N*nC*k' multiply-adds instead of N*p*k' (extension_dmma_kernel).
 constexpr int XC_N = 56;          // eigenvector columns per block (7 DMMA n-tiles)
-constexpr int XC_CELLS = 256;     // cells per CTA of ext_fx_kernel (8 warps x 4 m-tiles)
+constexpr int XC_CELLS = 256;     // cells per sub-tile of ext_fx_kernel (8 warps x 4 m-tiles)
+constexpr int XC_SUB = 4;         // sub-tiles per CTA (the Y slice and the Er rows are staged once for all of them)
+constexpr int XC_ERROWS = 64;     // image rows whose Er rows fit the staging area
 
 __global__ void __launch_bounds__(256)
 ext_index_kernel(const uint8_t* __restrict__ lum, int nrows, int W, const int* __restrict__ koff,
@@ -480,11 +482,12 @@ ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __r
     double* Ys = xsm;                                  // nR4 * XC_N   slice of Y for grid column b
     double* Gs = Ys + (size_t)nR4 * XC_N;              // 256
     int* ysl = reinterpret_cast<int*>(Gs + 256);       // nR4          sample luminances of grid column b
+    double* ErS = reinterpret_cast<double*>(ysl + nR4 + (nR4 & 1));   // XC_ERROWS * nR4: Er rows of the image rows this CTA's cells span
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tq = lane & 3;
     const int b = blockIdx.y, vb = blockIdx.z;
     const int K = koff[t.nrows];
-    const int k0 = blockIdx.x * XC_CELLS;
+    const int k0 = blockIdx.x * (XC_CELLS * XC_SUB);
     if (k0 >= K) return;
     Gs[tid] = t.Gt[tid];
     for (int e = tid; e < nR4 * XC_N; e += 256) {
@@ -492,47 +495,60 @@ ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __r
         Ys[e] = a < nR ? Yt[(size_t)(a * nC + b) * kp + vb * XC_N + m] : 0.0;
     }
     for (int a = tid; a < nR4; a += 256) ysl[a] = a < nR ? (int)t.Ysel[a * nC + b] : 0;
+    // cells are ordered by image row: the CTA's cells span rows [row_first, row_last]; their Er rows are staged in shared
+    // memory when there are at most XC_ERROWS of them (ncu: 33 % of the samples sat on the Er look-up in global memory)
+    const int row_first = cell_row[k0];
+    const int row_last = cell_row[min(K, k0 + XC_CELLS * XC_SUB) - 1];
+    const bool er_smem = row_last - row_first < XC_ERROWS;
+    if (er_smem)
+        for (int e = tid; e < (row_last - row_first + 1) * nR4; e += 256) {
+            const int r = e / nR4, a = e - r * nR4;
+            ErS[e] = a < nR ? t.Er[(size_t)(t.row0 + row_first + r) * nR + a] : 0.0;
+        }
     __syncthreads();
-    const int kw = k0 + warp * 32;
-    if (kw >= K) return;
-    int crow[4], clev[4];
-    bool cok[4];
-#pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int cell = kw + 8 * u + g;
-        cok[u] = cell < K;
-        crow[u] = cok[u] ? cell_row[cell] : 0;
-        clev[u] = cok[u] ? (int)cell_lev[cell] : 0;
-    }
-    double acc[4][7][2];
-#pragma unroll
-    for (int u = 0; u < 4; ++u)
-#pragma unroll
-        for (int v = 0; v < 7; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
-    for (int kk = 0; kk < nR4; kk += 4) {
-        const int a = kk + tq;
-        const int ya = ysl[a];
-        double af[4], bf[7];
+    for (int sub = 0; sub < XC_SUB; ++sub) {
+        const int kw = k0 + sub * XC_CELLS + warp * 32;
+        if (kw >= K) break;
+        int crow[4], clev[4];
+        bool cok[4];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
-            const int d = clev[u] - ya;
-            const double er = (cok[u] && a < nR) ? t.Er[(size_t)(t.row0 + crow[u]) * nR + a] : 0.0;
-            af[u] = er * Gs[d < 0 ? -d : d];
+            const int cell = kw + 8 * u + g;
+            cok[u] = cell < K;
+            crow[u] = cok[u] ? cell_row[cell] : row_first;
+            clev[u] = cok[u] ? (int)cell_lev[cell] : 0;
         }
-#pragma unroll
-        for (int v = 0; v < 7; ++v) bf[v] = Ys[a * XC_N + 8 * v + g];
+        double acc[4][7][2];
 #pragma unroll
         for (int u = 0; u < 4; ++u)
 #pragma unroll
-            for (int v = 0; v < 7; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
-    }
+            for (int v = 0; v < 7; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+        for (int kk = 0; kk < nR4; kk += 4) {
+            const int a = kk + tq;
+            const int ya = ysl[a];
+            double af[4], bf[7];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) {
-        const int cell = kw + 8 * u + g;
-        if (cell >= K) continue;
-        double* o = FX + ((size_t)cell * nC + b) * kp + vb * XC_N + 2 * tq;
+            for (int u = 0; u < 4; ++u) {
+                const int d = clev[u] - ya;
+                double er = 0.0;
+                if (cok[u] && a < nR) er = er_smem ? ErS[(crow[u] - row_first) * nR4 + a] : t.Er[(size_t)(t.row0 + crow[u]) * nR + a];
+                af[u] = er * Gs[d < 0 ? -d : d];
+            }
 #pragma unroll
-        for (int v = 0; v < 7; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+            for (int v = 0; v < 7; ++v) bf[v] = Ys[a * XC_N + 8 * v + g];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+#pragma unroll
+                for (int v = 0; v < 7; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int cell = kw + 8 * u + g;
+            if (cell >= K) continue;
+            double* o = FX + ((size_t)cell * nC + b) * kp + vb * XC_N + 2 * tq;
+#pragma unroll
+            for (int v = 0; v < 7; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+        }
     }
 }
 
@@ -698,7 +714,7 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
     NLE_LAUNCH_CHECK();
     const size_t ism = (size_t)(256 * 3 + 260 + 8) * sizeof(int) + ((t.cols + 15) / 16) * 16 + 16;
     const int nR4 = (t.nR + 3) & ~3;
-    const size_t fsm = ((size_t)nR4 * XC_N + 256) * sizeof(double) + (size_t)nR4 * sizeof(int) + 16;
+    const size_t fsm = ((size_t)nR4 * XC_N + 256 + (size_t)XC_ERROWS * nR4) * sizeof(double) + (size_t)(nR4 + 2) * sizeof(int) + 16;
     if (ism > 227 * 1024 || fsm > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
     static size_t conf_i = 0, conf_f = 0;
     if (ism > conf_i) { NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism)); conf_i = ism; }
@@ -718,7 +734,7 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
                                                                              cell_pstart, cell_pcount, sorted);
         NLE_LAUNCH_CHECK();
         const int cap_cells = g.capc * tb.nrows;
-        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS), t.nC, g.nvb), 256, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX);
+        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), 256, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX);
         NLE_LAUNCH_CHECK();
         ext_pix_kernel<<<sm_count() * 8, 256, 0, s>>>(tb, koff, cell_row, cell_pstart, cell_pcount, sorted, cb, FX, g.kp, g.nvb, k, Vb);
         NLE_LAUNCH_CHECK();
