@@ -34,12 +34,6 @@ namespace nle {
 
 namespace {
 
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 // Distinct luminance levels of one image row (blockDim.x == 256).  levidx[l] = compact index (ascending
 // level) or -1, lev[li] = level.  Returns the number of levels.
 __device__ __forceinline__ int row_levels(const uint8_t* __restrict__ Lrow, int W, int* flags, int* levidx,

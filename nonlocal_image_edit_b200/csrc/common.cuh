@@ -113,6 +113,16 @@ struct TmpBuf {
 
 inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+#ifdef __CUDACC__
+// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe (mma.sync.m8n8k4.f64, SASS: DMMA).
+// lane = 4*g + t holds  a = A[g][t],  b = B[t][g],  d0/d1 = D[g][2t], D[g][2t+1].
+__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(d0), "+d"(d1)
+                 : "d"(a), "d"(b));
+}
+#endif
+
 int sm_count();
 
 // ---- dense.cu : column-major FP64 building blocks ------------------------------------------

@@ -92,12 +92,6 @@ int sm_count() {
 // bank groups) and the next chunk is prefetched into registers while the current one is multiplied.
 constexpr int GBM = 64, GBN = 64, GBK = 16, GLDS = 64 + 8;
 
-__device__ __forceinline__ void dgemm_dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128)
 dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
@@ -156,7 +150,7 @@ dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 4; ++v) dgemm_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+                for (int v = 0; v < 4; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
     }
 #pragma unroll

@@ -38,13 +38,6 @@ namespace nle {
 
 namespace {
 
-// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe: lane = 4g + t holds A[g][t], B[t][g], D[g][2t], D[g][2t+1]
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 constexpr double kUnitRoundoff = 1.1102230246251565e-16;
 constexpr int kLeaf = 32;
 constexpr int kTrdThreads = 512;

@@ -563,14 +563,6 @@ constexpr int GT = 128;    // tile edge (samples)
 constexpr int GKC = 16;    // pixels per chunk
 constexpr int GLD = GT + 8;   // padded row: the 4 k-rows of a DMMA fragment fall into 2 disjoint bank groups
 
-// D(8x8) += A(8x4, row) * B(4x8, col) on the FP64 tensor pipe (SASS: DMMA).
-// lane = 4*g + t :  a = A[g][t],  b = B[t][g],  d0/d1 = D[g][2t], D[g][2t+1].
-__device__ __forceinline__ void gram_dmma(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 // CE[j][b] = c_j * Ec[col_j][b] for every slab pixel j (nloc x nC): takes the per-pixel Sinkhorn weight out of
 // the tile producers' critical burst (see gram_kernel).
 __global__ void gram_ce_kernel(AffinityTables t, const double* __restrict__ cvec, double* __restrict__ CE) {
@@ -747,7 +739,7 @@ gram_kernel(AffinityTables t, const double* __restrict__ CE, int ntile, int nspl
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
 #pragma unroll
-                    for (int v = 0; v < 8; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+                    for (int v = 0; v < 8; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
             }
         }
     }
@@ -1027,7 +1019,7 @@ extension_dmma_kernel(AffinityTables t, const double* __restrict__ cvec, const d
 #pragma unroll
             for (int u = 0; u < 4; ++u)
 #pragma unroll
-                for (int v = 0; v < 7; ++v) gram_dmma(acc[u][v][0], acc[u][v][1], a[u], b[v]);
+                for (int v = 0; v < 7; ++v) dmma884(acc[u][v][0], acc[u][v][1], a[u], b[v]);
         }
     }
 #pragma unroll

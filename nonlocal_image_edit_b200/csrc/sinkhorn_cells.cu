@@ -28,12 +28,6 @@ namespace nle {
 
 namespace {
 
-__device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double b) {
-    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
-                 : "+d"(d0), "+d"(d1)
-                 : "d"(a), "d"(b));
-}
-
 constexpr int NL = 256;        // luminance levels
 constexpr int DG_ROWS = 32;    // image rows per CTA of the dot GEMM
 constexpr int DG_MT = DG_ROWS / 8;   // DMMA m-tiles per warp
