@@ -910,7 +910,7 @@ bt_wy_kernel(const double* __restrict__ A, int lda, int n, const double* __restr
 #pragma unroll
             for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = 0.0;
             const int rs = r_lo & ~3;
-#pragma unroll 2
+#pragma unroll 4
             for (int rb = rs + 4 * warp; rb < n; rb += 32) {
                 const int row = rb + tq;
                 const bool rv = row < n && row >= r_lo;
@@ -950,7 +950,7 @@ bt_wy_kernel(const double* __restrict__ A, int lda, int n, const double* __restr
         // ---- phase 3: Z += V W2, m-tiles of 8 rows (aligned to 8) dealt round-robin to the warps
         {
             const int rs = r_lo & ~7;
-#pragma unroll 2
+#pragma unroll 4
             for (int rb = rs + 8 * warp; rb < n; rb += 64) {
                 const int row = rb + g;
                 const bool rv = row < n && row >= r_lo;
