@@ -49,7 +49,7 @@ GRID = (40, 40)
 HX, HY = 500.0, 30.0
 T_SINK, K_EIG = 20, 50
 WEIGHTS = [2.0, 3.0, 4.0, 1.0]
-CPU_CROP = 256            # cpu_baseline / reference arm: CPU_CROP x CPU_CROP crop, same grid/k/T
+CPU_CROP = 384            # cpu_baseline / reference arm: CPU_CROP x CPU_CROP crop, same grid/k/T (~10 s of CPU work, ~8 GB dense)
 
 
 def synth_luminance(rows, cols, seed=1234):
@@ -343,7 +343,8 @@ def run_b200(args, rank, world, local_rank):
     peak = lib.nle_b200_fp64_fma_peak_tflops()
     achieved = gram_flops / (st[7] * 1e-3) * 1e-12 if st[7] > 0 else None
     roofline = {"kernel": "gram_cells_kernel (register-generated affinity fragments + FP64 DMMA over (row, level) cells)",
-                "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "bound": "tensor", "pipe": "FP64 tensor pipe (mma.sync m8n8k4.f64, SASS DMMA); not tcgen05: there is no FP64 tcgen05 MMA",
+                "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if (achieved and peak) else None,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one gram_cells_kernel launch at this configuration
                 # (ncu --set full, profiles/r1g_gram_cells_kernel_full.md); algorithmic HBM bytes are Hh once
