@@ -153,6 +153,7 @@ struct EigWorkspace {
     DevBuf<double> W, As, T, lam_unsorted;
     DevBuf<double> Qa, Qb, Sb, dcd;                     // divide & conquer buffers (eig_dc.cu)
     DevBuf<double> wyT;                                 // T factors of the blocked back-transformation
+    DevBuf<uint4> trdll;                                // flagged exchange cells of tridiag_resident_kernel
     DevBuf<int> dci;
     int dc_cap = 0;
     void reserve_dc(int n);

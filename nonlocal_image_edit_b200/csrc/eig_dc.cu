@@ -247,6 +247,201 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 }
 
 // ---------------------------------------------------------------------------------------------
+// Shared-memory-resident variant of tridiag_kernel (NLE_B200_TRD=resident; EXPERIMENTAL, off by default
+// until it has been run on the device -- see DESIGN.md section 6).  Same arithmetic in the same order as
+// tridiag_kernel (d, e, tau and the reflectors come out bit-identical); what changes is where the data
+// lives and how the CTAs synchronise:
+//   * CTA b keeps its columns c = b, b+G, ... of the trailing matrix in shared memory for the whole
+//     factorisation (n = 1600 on 148 SMs: 11 columns x 12.8 KB), so the rank-2 update + symv pass of a
+//     step makes no global loads or stores at all;
+//   * the two vectors every CTA needs at the start of a step -- p = A v and the next column -- are
+//     exchanged through global memory as flagged 16-byte cells {lo, tag, hi, tag} (two 8-byte halves, each
+//     written atomically together with its tag; the low-latency protocol NCCL calls LL): the consumer
+//     polls the cells themselves, so one L2 write + one L2 read replace the store-acknowledge fence,
+//     the barrier atomic, the barrier poll and the separate p / column loads of the grid.sync version;
+//   * cells are double-buffered by the parity of the tag; a CTA leaves the kernel as soon as it owns no
+//     column of the trailing matrix any more, so the CTAs that still exchange data are never more than
+//     one step apart (each waits for cells written by all the others), which is what makes two buffers
+//     enough.  The CTA that owns column n-1 lives to the end and writes d, e, tau and the reflectors.
+constexpr int kResPer = 4;   // exchange cells per thread and vector: n <= kResPer * kTrdThreads
+
+__device__ __forceinline__ void ll_store(uint4* cell, double x, unsigned tag) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
+    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)bits), "r"(tag),
+                 "r"((unsigned)(bits >> 32)), "r"(tag)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ll_load(const uint4* cell) {
+    uint4 r;
+    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(cell) : "memory");
+    return r;
+}
+__device__ __forceinline__ double ll_value(const uint4& c) {
+    return __longlong_as_double((long long)(((unsigned long long)c.z << 32) | (unsigned long long)c.x));
+}
+
+__global__ void __launch_bounds__(kTrdThreads, 1)
+tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
+                        double* __restrict__ tau, uint4* __restrict__ ll /* 4n cells, zeroed before the launch */) {
+    extern __shared__ double sm[];
+    double* v = sm;            // current reflector, global row indexing
+    double* w = sm + n;
+    double* cn = sm + 2 * (size_t)n;   // updated next column -> next reflector
+    double* red = sm + 3 * (size_t)n;  // 2*kTrdWarps
+    double* cols = red + 2 * kTrdWarps;   // owned columns, slot q holds column b + G*q (all n rows)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int q_last = (n - 1 - b) / G;          // b < G <= n
+    const int c_last = b + G * q_last;           // the largest column this CTA owns
+    const bool writer = (c_last == n - 1);
+    int phase = 0;
+    // cells of tag t: p at ll + (t&1)*2n, next column at ll + (t&1)*2n + n
+    auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n; };
+    auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n + n; };
+
+    auto make_reflector = [&](int j0, double& tau_out) -> double {     // identical to tridiag_kernel's
+        const double alpha = cn[j0 + 1];
+        double part = 0.0;
+        for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
+        const double xn2 = block_sum(part, red, phase);
+        double beta;
+        if (xn2 == 0.0) {
+            tau_out = 0.0;
+            beta = alpha;
+            __syncthreads();
+            if (tid == 0) cn[j0 + 1] = 1.0;
+        } else {
+            beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+            tau_out = (beta - alpha) / beta;
+            const double scal = 1.0 / (alpha - beta);
+            __syncthreads();
+            for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) cn[i] *= scal;
+            if (tid == 0) cn[j0 + 1] = 1.0;
+        }
+        __syncthreads();
+        return beta;
+    };
+
+    // owned columns -> shared memory; column 0 -> first reflector (every CTA, redundantly)
+    for (int q = 0; q <= q_last; ++q) {
+        const double* src = A + (size_t)(b + G * q) * lda;
+        double* dst = cols + (size_t)q * n;
+        for (int i = tid; i < n; i += kTrdThreads) dst[i] = src[i];
+    }
+    for (int i = tid; i < n; i += kTrdThreads) cn[i] = A[i];
+    __syncthreads();
+    double tau_j, beta_j, diag_j;
+    diag_j = cn[0];
+    beta_j = make_reflector(0, tau_j);
+    { double* t = v; v = cn; cn = t; }
+    // p = A v over the owned columns c >= 1 (tag 1); the owner of column 1 also publishes that column
+    for (int q = warp; q <= q_last; q += kTrdWarps) {
+        const int c = b + G * q;
+        if (c < 1) continue;
+        const double* col = cols + (size_t)q * n;
+        double acc = 0.0;
+        for (int i = 1 + lane; i < n; i += 32) acc = fma(col[i], v[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) ll_store(pcell(1) + c, acc, 1u);
+        if (c == 1)
+            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u);
+    }
+
+    for (int j = 0; j <= n - 3; ++j) {
+        if (c_last < j + 2) return;       // nothing left to update here and nobody waits for this CTA (block-uniform)
+        const unsigned T = (unsigned)(j + 1);
+        // (1) wait for p and column j+1 (rows j+1..n-1), all loads of a round in flight together
+        double part = 0.0;
+        {
+            const uint4* pc = pcell(T);
+            const uint4* cc = ccell(T);
+            uint4 P[kResPer], C[kResPer];
+            bool ok;
+            do {
+                ok = true;
+#pragma unroll
+                for (int u = 0; u < kResPer; ++u) {
+                    const int i = j + 1 + tid + u * kTrdThreads;
+                    if (i < n) { P[u] = ll_load(pc + i); C[u] = ll_load(cc + i); }
+                }
+#pragma unroll
+                for (int u = 0; u < kResPer; ++u) {
+                    const int i = j + 1 + tid + u * kTrdThreads;
+                    if (i < n) ok = ok && P[u].y == T && P[u].w == T && C[u].y == T && C[u].w == T;
+                }
+            } while (!ok);
+#pragma unroll
+            for (int u = 0; u < kResPer; ++u) {
+                const int i = j + 1 + tid + u * kTrdThreads;
+                if (i < n) {
+                    const double pi = ll_value(P[u]);
+                    w[i] = pi;
+                    cn[i] = ll_value(C[u]);
+                    part = fma(pi, v[i], part);
+                }
+            }
+        }
+        // w = tau*p - (tau^2/2)(p.v) v
+        const double dot = block_sum(part, red, phase);
+        const double kappa = 0.5 * tau_j * tau_j * dot;
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
+        __syncthreads();
+        // (2) updated column j+1 -> next diagonal and next reflector
+        {
+            const double wj1 = w[j + 1];   // v[j+1] == 1
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
+            __syncthreads();
+        }
+        const double diag_next = cn[j + 1];
+        double tau_next = 0.0, beta_next;
+        const bool has_next = (j + 1 <= n - 3);
+        if (has_next) {
+            beta_next = make_reflector(j + 1, tau_next);
+        } else {
+            beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
+        }
+        // (3) rank-2 update of the owned columns c >= j+2 (in shared memory) fused with the next symv;
+        //     the owner of column j+2 publishes the updated column as it goes
+        const unsigned Tn = (unsigned)(j + 2);
+        for (int q = warp; q <= q_last; q += kTrdWarps) {
+            const int c = b + G * q;
+            if (c < j + 2) continue;
+            double* col = cols + (size_t)q * n;
+            const double wc = w[c], vc = v[c];
+            const bool pub = has_next && c == j + 2;
+            uint4* cc = ccell(Tn);
+            double acc = 0.0;
+            for (int i = j + 2 + lane; i < n; i += 32) {
+                double a = col[i];
+                a = fma(-w[i], vc, fma(-v[i], wc, a));
+                acc = fma(a, cn[i], acc);
+                col[i] = a;
+                if (pub) ll_store(cc + i, a, Tn);
+            }
+            if (has_next) {
+                acc = warp_sum(acc);
+                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn);
+            }
+        }
+        // (0) reflector j and its scalars (off the critical path: nobody in this kernel reads them back)
+        if (writer) {
+            double* colj = A + (size_t)j * lda;
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) colj[i] = v[i];
+            if (tid == 0) { d[j] = diag_j; e[j] = beta_j; tau[j] = tau_j; }
+        }
+        diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
+        { double* t = v; v = cn; cn = t; }
+        __syncthreads();   // w and the old v are overwritten by the next step's (1)
+    }
+    if (writer && tid == 0) {
+        d[n - 2] = diag_j;
+        e[n - 2] = beta_j;
+        tau[n - 2] = 0.0;
+        d[n - 1] = cols[(size_t)q_last * n + (n - 1)];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // Leaves: symmetric tridiagonal QL with implicit Wilkinson shift (EISPACK tql2 lineage), one warp
 // per leaf; lane = row of the eigenvector matrix.  The scalar recurrence is executed redundantly by
 // all lanes on a shared copy of (d, e) -- every lane writes identical values.
@@ -1037,7 +1232,36 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     NLE_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
 
     // ---- 1. tridiagonalisation
+    // NLE_B200_TRD=resident: trailing matrix in shared memory + flagged-cell exchange (experimental, see the kernel)
+    bool trd_done = false;
     {
+        const char* env = getenv("NLE_B200_TRD");
+        int grid = std::min(sm_count(), n);
+        if (env && std::string(env) == "resident" && n >= 3 && n <= kResPer * kTrdThreads) {
+            int dev = 0, max_smem = 0;
+            NLE_CUDA(cudaGetDevice(&dev));
+            NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            const int qmax = cdiv(n, grid);
+            const size_t smem = ((3 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
+            if (smem <= (size_t)max_smem) {
+                NLE_CUDA(cudaFuncSetAttribute(tridiag_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                int per_sm = 0;
+                NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_resident_kernel, kTrdThreads, smem));
+                if (per_sm >= 1) {
+                    if (ws.trdll.n < 4 * (size_t)n) ws.trdll.alloc(4 * (size_t)n);
+                    NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, 4 * (size_t)n * sizeof(uint4), s));   // tag 0 = never written
+                    int lda = n;
+                    uint4* ll = ws.trdll.p;
+                    void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll};
+                    // cooperative launch only for its co-residency guarantee (the kernel never calls grid.sync)
+                    NLE_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_resident_kernel, dim3(grid), dim3(kTrdThreads), args, smem, s));
+                    ++g_launches;
+                    trd_done = true;
+                }
+            }
+        }
+    }
+    if (!trd_done) {
         size_t smem = (3 * (size_t)n + 2 * kTrdWarps) * sizeof(double);
         NLE_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;

@@ -1,0 +1,64 @@
+"""Opt-in GPU test of the shared-memory-resident tridiagonalisation (NLE_B200_TRD=resident, eig_dc.cu).
+
+The kernel was written while no GPU time was left, so it is OFF by default and this file is skipped unless
+NLE_B200_TEST_TRD_RESIDENT=1.  It performs the same arithmetic in the same order as tridiag_kernel, so the
+eigen-decomposition must come out BIT-identical with the switch on and off.  The kernel spins on flagged
+cells: run it under a process-level limit the first time, e.g.
+
+    NLE_B200_TEST_TRD_RESIDENT=1 timeout 300 python -m pytest tests/test_gpu_trd_resident.py -x -q
+"""
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(os.environ.get("NLE_B200_TEST_TRD_RESIDENT") != "1",
+                                 reason="experimental kernel: set NLE_B200_TEST_TRD_RESIDENT=1")]
+
+
+def both(nb, A, **kw):
+    os.environ.pop("NLE_B200_TRD", None)
+    U0, D0 = nb.eigenDecomposition(A, **kw)
+    os.environ["NLE_B200_TRD"] = "resident"
+    os.environ["NLE_B200_EIG_STRICT"] = "1"      # no silent Jacobi fallback if the sanity check trips
+    try:
+        U1, D1 = nb.eigenDecomposition(A, **kw)
+    finally:
+        os.environ.pop("NLE_B200_TRD", None)
+        os.environ.pop("NLE_B200_EIG_STRICT", None)
+    return (U0, D0), (U1, D1)
+
+
+@pytest.mark.parametrize("n", [3, 4, 5, 33, 130, 147, 148, 149, 300, 700, 1041, 1600, 1800])
+def test_resident_equals_grid_sync_bitwise(nb, n):
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, max(3, n // 2)))
+    A = B @ B.T / n + 1e-3 * np.eye(n)
+    (U0, D0), (U1, D1) = both(nb, A, eps=-1e300)
+    assert np.array_equal(D0, D1)
+    assert np.array_equal(U0, U1)
+    w = np.linalg.eigvalsh(A)[::-1]
+    assert np.abs(D1 - w).max() <= 1e-11 * max(1.0, np.abs(w).max()) * max(1, n / 16)
+
+
+def test_resident_zero_tail_and_identity(nb):
+    for A in (np.eye(70), np.zeros((70, 70)), np.ones((70, 70)), np.diag(np.arange(1.0, 41.0))):
+        (U0, D0), (U1, D1) = both(nb, A, eps=-1e300)
+        assert np.array_equal(D0, D1) and np.array_equal(U0, U1)
+
+
+def test_resident_train_equals_default(nb):
+    from nle_testlib import synth_lum
+    lum = synth_lum(160, 200, seed=3)
+    args = (12, 14, 60.0, 25.0, 8, 12)
+    os.environ.pop("NLE_B200_TRD", None)
+    f0 = nb.NLEFilter().trainFilter(lum, *args)
+    os.environ["NLE_B200_TRD"] = "resident"
+    try:
+        f1 = nb.NLEFilter().trainFilter(lum, *args)
+    finally:
+        os.environ.pop("NLE_B200_TRD", None)
+    assert np.array_equal(f0.eigvals, f1.eigvals)
+    w = [2.0, 3.0, 4.0, 1.0]
+    assert np.array_equal(f0.enhanceLuminance(lum, w), f1.enhanceLuminance(lum, w))
