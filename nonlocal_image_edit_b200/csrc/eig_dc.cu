@@ -265,24 +265,57 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 //     enough.  The CTA that owns column n-1 lives to the end and writes d, e, tau and the reflectors.
 constexpr int kResPer = 4;   // exchange cells per thread and vector: n <= kResPer * kTrdThreads
 
-__device__ __forceinline__ void ll_store(uint4* cell, double x, unsigned tag) {
+// sys = false: relaxed, gpu scope, two 8-byte elements {tag:lo, tag:hi}; sys = true: the volatile (= relaxed.sys)
+// 4 x u32 form NCCL uses.  Same bytes in memory; NLE_B200_TRD_LL=sys selects the latter for A/B timing.
+__device__ __forceinline__ void ll_store(uint4* cell, double x, unsigned tag, bool sys) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
-    asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)bits), "r"(tag),
-                 "r"((unsigned)(bits >> 32)), "r"(tag)
-                 : "memory");
+    if (sys) {
+        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)bits), "r"(tag),
+                     "r"((unsigned)(bits >> 32)), "r"(tag)
+                     : "memory");
+    } else {
+        const unsigned long long t = (unsigned long long)tag << 32;
+        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(t | (bits & 0xffffffffull)), "l"(t | (bits >> 32))
+                     : "memory");
+    }
 }
-__device__ __forceinline__ uint4 ll_load(const uint4* cell) {
+__device__ __forceinline__ uint4 ll_load(const uint4* cell, bool sys) {
     uint4 r;
-    asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(cell) : "memory");
+    if (sys) {
+        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(cell) : "memory");
+    } else {
+        unsigned long long a, b;
+        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(cell) : "memory");
+        r.x = (unsigned)a; r.y = (unsigned)(a >> 32); r.z = (unsigned)b; r.w = (unsigned)(b >> 32);
+    }
     return r;
 }
 __device__ __forceinline__ double ll_value(const uint4& c) {
     return __longlong_as_double((long long)(((unsigned long long)c.z << 32) | (unsigned long long)c.x));
 }
 
+// PROF: thread 0 of the CTA that owns column n-1 accumulates clock64() spans of the phases of a step
+//       (developer diagnostic, NLE_B200_TRD_PROF=1; results in profiles/r1l_trd_phases.md).
+// clock64 read that the compiler cannot hoist above the computation of `dep`
+__device__ __forceinline__ long long clock_after(double dep) {
+    long long t;
+    asm volatile("mov.u64 %0, %%clock64;" : "=l"(t) : "d"(dep) : "memory");
+    return t;
+}
+#define TRD_STAMP(k, dep)                                              \
+    do {                                                               \
+        if (PROF && tid == 0) {                                        \
+            const long long t_ = clock_after(dep);                     \
+            pacc[k] += t_ - tprev;                                     \
+            tprev = t_;                                                \
+        }                                                              \
+    } while (0)
+
+template <bool PROF>
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
-                        double* __restrict__ tau, uint4* __restrict__ ll /* 4n cells, zeroed before the launch */) {
+                        double* __restrict__ tau, uint4* __restrict__ ll /* 4n cells, zeroed before the launch */,
+                        long long* __restrict__ prof /* 16 counters when PROF */, int ll_sys) {
     extern __shared__ double sm[];
     double* v = sm;            // current reflector, global row indexing
     double* w = sm + n;
@@ -294,7 +327,10 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
     const int q_last = (n - 1 - b) / G;          // b < G <= n
     const int c_last = b + G * q_last;           // the largest column this CTA owns
     const bool writer = (c_last == n - 1);
+    const bool sys = ll_sys != 0;
     int phase = 0;
+    long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0, rounds = 0;
     // cells of tag t: p at ll + (t&1)*2n, next column at ll + (t&1)*2n + n
     auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n; };
     auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n + n; };
@@ -304,6 +340,7 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
         double part = 0.0;
         for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
         const double xn2 = block_sum(part, red, phase);
+        TRD_STAMP(4, xn2);
         double beta;
         if (xn2 == 0.0) {
             tau_out = 0.0;
@@ -314,6 +351,7 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
             beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
             tau_out = (beta - alpha) / beta;
             const double scal = 1.0 / (alpha - beta);
+            TRD_STAMP(5, scal + tau_out);
             __syncthreads();
             for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) cn[i] *= scal;
             if (tid == 0) cn[j0 + 1] = 1.0;
@@ -342,64 +380,73 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
         double acc = 0.0;
         for (int i = 1 + lane; i < n; i += 32) acc = fma(col[i], v[i], acc);
         acc = warp_sum(acc);
-        if (lane == 0) ll_store(pcell(1) + c, acc, 1u);
+        if (lane == 0) ll_store(pcell(1) + c, acc, 1u, sys);
         if (c == 1)
-            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u);
+            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u, sys);
+    }
+    if (PROF && tid == 0) {
+        tprev = clock64();
+#pragma unroll
+        for (int k = 0; k < 10; ++k) pacc[k] = 0;
     }
 
     for (int j = 0; j <= n - 3; ++j) {
         if (c_last < j + 2) return;       // nothing left to update here and nobody waits for this CTA (block-uniform)
         const unsigned T = (unsigned)(j + 1);
+        const bool has_next = (j + 1 <= n - 3);
+        double diag_next, tau_next = 0.0, beta_next;
         // (1) wait for p and column j+1 (rows j+1..n-1), all loads of a round in flight together
-        double part = 0.0;
+        uint4 P[kResPer], C[kResPer];
         {
             const uint4* pc = pcell(T);
             const uint4* cc = ccell(T);
-            uint4 P[kResPer], C[kResPer];
             bool ok;
             do {
                 ok = true;
 #pragma unroll
                 for (int u = 0; u < kResPer; ++u) {
                     const int i = j + 1 + tid + u * kTrdThreads;
-                    if (i < n) { P[u] = ll_load(pc + i); C[u] = ll_load(cc + i); }
+                    if (i < n) { P[u] = ll_load(pc + i, sys); C[u] = ll_load(cc + i, sys); }
                 }
 #pragma unroll
                 for (int u = 0; u < kResPer; ++u) {
                     const int i = j + 1 + tid + u * kTrdThreads;
                     if (i < n) ok = ok && P[u].y == T && P[u].w == T && C[u].y == T && C[u].w == T;
                 }
+                if (PROF) ++rounds;
             } while (!ok);
+        }
+        TRD_STAMP(0, ll_value(P[0]));
+        double part = 0.0;
 #pragma unroll
-            for (int u = 0; u < kResPer; ++u) {
-                const int i = j + 1 + tid + u * kTrdThreads;
-                if (i < n) {
-                    const double pi = ll_value(P[u]);
-                    w[i] = pi;
-                    cn[i] = ll_value(C[u]);
-                    part = fma(pi, v[i], part);
-                }
+        for (int u = 0; u < kResPer; ++u) {
+            const int i = j + 1 + tid + u * kTrdThreads;
+            if (i < n) {
+                const double pi = ll_value(P[u]);
+                w[i] = pi;
+                cn[i] = ll_value(C[u]);
+                part = fma(pi, v[i], part);
             }
         }
         // w = tau*p - (tau^2/2)(p.v) v
         const double dot = block_sum(part, red, phase);
+        TRD_STAMP(1, dot);
         const double kappa = 0.5 * tau_j * tau_j * dot;
         for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
         __syncthreads();
         // (2) updated column j+1 -> next diagonal and next reflector
-        {
-            const double wj1 = w[j + 1];   // v[j+1] == 1
-            for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
-            __syncthreads();
-        }
-        const double diag_next = cn[j + 1];
-        double tau_next = 0.0, beta_next;
-        const bool has_next = (j + 1 <= n - 3);
+        const double wj1 = w[j + 1];   // v[j+1] == 1
+        TRD_STAMP(2, wj1);
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
+        __syncthreads();
+        diag_next = cn[j + 1];
+        TRD_STAMP(3, diag_next);
         if (has_next) {
-            beta_next = make_reflector(j + 1, tau_next);
+            beta_next = make_reflector(j + 1, tau_next);     // stamps 4, 5
         } else {
             beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
         }
+        TRD_STAMP(6, beta_next);
         // (3) rank-2 update of the owned columns c >= j+2 (in shared memory) fused with the next symv;
         //     the owner of column j+2 publishes the updated column as it goes
         const unsigned Tn = (unsigned)(j + 2);
@@ -411,18 +458,20 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
             const bool pub = has_next && c == j + 2;
             uint4* cc = ccell(Tn);
             double acc = 0.0;
-            for (int i = j + 2 + lane; i < n; i += 32) {
+            int i = j + 2 + lane;
+            for (; i < n; i += 32) {
                 double a = col[i];
                 a = fma(-w[i], vc, fma(-v[i], wc, a));
                 acc = fma(a, cn[i], acc);
                 col[i] = a;
-                if (pub) ll_store(cc + i, a, Tn);
+                if (pub) ll_store(cc + i, a, Tn, sys);
             }
             if (has_next) {
                 acc = warp_sum(acc);
-                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn);
+                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn, sys);
             }
         }
+        TRD_STAMP(7, 0.0);
         // (0) reflector j and its scalars (off the critical path: nobody in this kernel reads them back)
         if (writer) {
             double* colj = A + (size_t)j * lda;
@@ -432,14 +481,22 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
         diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
         { double* t = v; v = cn; cn = t; }
         __syncthreads();   // w and the old v are overwritten by the next step's (1)
+        TRD_STAMP(8, v[j + 2]);
     }
     if (writer && tid == 0) {
         d[n - 2] = diag_j;
         e[n - 2] = beta_j;
         tau[n - 2] = 0.0;
         d[n - 1] = cols[(size_t)q_last * n + (n - 1)];
+        if (PROF) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) prof[k] = pacc[k];
+            prof[10] = rounds;
+            prof[11] = n - 2;
+        }
     }
 }
+#undef TRD_STAMP
 
 // ---------------------------------------------------------------------------------------------
 // Leaves: symmetric tridiagonal QL with implicit Wilkinson shift (EISPACK tql2 lineage), one warp
@@ -1182,6 +1239,17 @@ __global__ void dc_check_kernel(const double* __restrict__ U, int ldu, int n, in
 
 }  // namespace
 
+// CTAs of the tridiagonalisation kernels: one per SM unless NLE_B200_TRD_GRID caps it (developer knob: the
+// per-step exchange cost grows with the number of CTAs that read every cell, profiles/r1l_trd_phases.md)
+static int trd_grid_limit() {
+    int g = sm_count();
+    if (const char* e = getenv("NLE_B200_TRD_GRID")) {
+        const int v = atoi(e);
+        if (v >= 1 && v < g) g = v;
+    }
+    return g;
+}
+
 // ---------------------------------------------------------------------------------------------
 void EigWorkspace::reserve_dc(int n) {
     if (n <= dc_cap) return;
@@ -1232,31 +1300,49 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     NLE_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
 
     // ---- 1. tridiagonalisation
-    // NLE_B200_TRD=resident: trailing matrix in shared memory + flagged-cell exchange (experimental, see the kernel)
+    // NLE_B200_TRD=resident: trailing matrix in shared memory + flagged-cell exchange (see tridiag_resident_kernel);
+    // NLE_B200_TRD_PROF=1 adds the per-phase cycle counts of a step on stderr.
     bool trd_done = false;
     {
         const char* env = getenv("NLE_B200_TRD");
-        int grid = std::min(sm_count(), n);
-        if (env && std::string(env) == "resident" && n >= 3 && n <= kResPer * kTrdThreads) {
+        const std::string mode = env ? env : "";
+        int grid = std::min(trd_grid_limit(), n);
+        if (mode == "resident" && n >= 3 && n <= kResPer * kTrdThreads) {
+            const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
             int dev = 0, max_smem = 0;
             NLE_CUDA(cudaGetDevice(&dev));
             NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
             const int qmax = cdiv(n, grid);
             const size_t smem = ((3 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
+            const void* kfn = kprof ? (const void*)tridiag_resident_kernel<true> : (const void*)tridiag_resident_kernel<false>;
             if (smem <= (size_t)max_smem) {
-                NLE_CUDA(cudaFuncSetAttribute(tridiag_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
                 int per_sm = 0;
-                NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_resident_kernel, kTrdThreads, smem));
+                NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
                 if (per_sm >= 1) {
-                    if (ws.trdll.n < 4 * (size_t)n) ws.trdll.alloc(4 * (size_t)n);
-                    NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, 4 * (size_t)n * sizeof(uint4), s));   // tag 0 = never written
+                    const size_t cells = 4 * (size_t)n + 8;      // + 8 cells = 16 profile counters
+                    if (ws.trdll.n < cells) ws.trdll.alloc(cells);
+                    NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));   // tag 0 = never written
                     int lda = n;
                     uint4* ll = ws.trdll.p;
-                    void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll};
+                    long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * (size_t)n);
+                    const char* lle = getenv("NLE_B200_TRD_LL");
+                    int ll_sys = (lle && std::string(lle) == "sys") ? 1 : 0;
+                    void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp, &ll_sys};
                     // cooperative launch only for its co-residency guarantee (the kernel never calls grid.sync)
-                    NLE_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_resident_kernel, dim3(grid), dim3(kTrdThreads), args, smem, s));
+                    NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
                     ++g_launches;
                     trd_done = true;
+                    if (kprof) {
+                        long long h[16];
+                        NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
+                        NLE_CUDA(cudaStreamSynchronize(s));
+                        const double st = (double)std::max(1LL, h[11]);
+                        fprintf(stderr, "[trd %s%s n=%d] cycles/step: poll %.0f | dot-reduce %.0f | w %.0f | col %.0f | norm-reduce %.0f | "
+                                "sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; poll rounds/step %.2f\n",
+                                mode.c_str(), ll_sys ? " ll=sys" : "", n, h[0] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st, h[5] / st, h[6] / st, h[7] / st,
+                                h[8] / st, (h[0] + h[1] + h[2] + h[3] + h[4] + h[5] + h[6] + h[7] + h[8]) / st, h[10] / st);
+                    }
                 }
             }
         }
@@ -1267,8 +1353,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         int per_sm = 0;
         NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_kernel, kTrdThreads, smem));
         if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(n) + ")"};
-        int grid = sm_count();
-        if (grid > n) grid = n;
+        int grid = std::min(trd_grid_limit(), n);
         int lda = n;
         void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf};
         NLE_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(grid), dim3(kTrdThreads), args, smem, s));

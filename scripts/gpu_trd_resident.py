@@ -1,6 +1,9 @@
-"""Developer timing: grid.sync tridiagonalisation vs the shared-memory-resident one (NLE_B200_TRD=resident).
+"""Developer check + timing of the tridiagonalisation variants (eig_dc.cu):
+   gridsync (default) | NLE_B200_TRD=resident (bit-identical to gridsync) | resident:sys (volatile cells instead of relaxed.gpu).
+   The output of the round-1 runs is condensed in profiles/r1l_trd_phases.md.
 
-  NLE_B200_EIG_PROF=1 python scripts/gpu_trd_resident.py [n ...]     # per-phase ms on stderr, default n = 612 1041 1600
+  timeout 40 python scripts/gpu_trd_resident.py [n ...] [resident resident:sys ...]      # stderr: per-phase ms (NLE_B200_EIG_PROF) and, for the
+                                                             # resident kernels, cycles per step by phase (NLE_B200_TRD_PROF)
 """
 import os, sys, time
 import numpy as np
@@ -8,23 +11,65 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import nonlocal_image_edit_b200 as nb
 
-os.environ.setdefault("NLE_B200_EIG_PROF", "1")
 os.environ["NLE_B200_EIG_STRICT"] = "1"
-sizes = [int(a) for a in sys.argv[1:]] or [612, 1041, 1600]
-for n in sizes:
+sizes = [int(a) for a in sys.argv[1:] if a.isdigit()] or [1600, 300, 1041, 612, 3, 4, 5, 33, 149, 1800]
+MODES = ["gridsync"] + ([a for a in sys.argv[1:] if not a.isdigit()] or ["resident"])
+QUICK = os.environ.get("TRD_QUICK") == "1"
+
+
+def say(msg):
+    print(msg, file=sys.stderr, flush=True)
+
+
+def run(A, mode, reps=3):
+    os.environ.pop("NLE_B200_TRD", None)
+    os.environ.pop("NLE_B200_TRD_LL", None)
+    if mode != "gridsync":
+        os.environ["NLE_B200_TRD"] = mode.split(":")[0]
+        if mode.endswith(":sys"):
+            os.environ["NLE_B200_TRD_LL"] = "sys"       # volatile (sys-scope) cells instead of relaxed.gpu
+    os.environ.pop("NLE_B200_EIG_PROF", None)
+    os.environ.pop("NLE_B200_TRD_PROF", None)
+    out = nb.eigenDecomposition(A, eps=-1e300)                    # warm-up (function attributes, pool)
+    os.environ["NLE_B200_EIG_PROF"] = "1"
+    for _ in range(reps):
+        out = nb.eigenDecomposition(A, eps=-1e300)
+    os.environ.pop("NLE_B200_EIG_PROF", None)
+    if mode != "gridsync":
+        os.environ["NLE_B200_TRD_PROF"] = "1"
+        nb.eigenDecomposition(A, eps=-1e300)
+        os.environ.pop("NLE_B200_TRD_PROF", None)
+    return out
+
+
+def matrices(n):
     rng = np.random.default_rng(n)
-    B = rng.standard_normal((n, n // 2))
-    A = B @ B.T / n + 1e-3 * np.eye(n)
-    out = {}
-    for mode in ("gridsync", "resident"):
-        if mode == "resident":
-            os.environ["NLE_B200_TRD"] = "resident"
-        else:
-            os.environ.pop("NLE_B200_TRD", None)
-        nb.eigenDecomposition(A, eps=-1e300)                      # warm-up (attributes, pool)
-        t0 = time.time()
-        for _ in range(3):
-            out[mode] = nb.eigenDecomposition(A, eps=-1e300)
-        print(f"n={n} {mode}: {(time.time() - t0) / 3 * 1e3:.2f} ms per call (host clock, includes copies)", flush=True)
-    same = np.array_equal(out["gridsync"][1], out["resident"][1]) and np.array_equal(out["gridsync"][0], out["resident"][0])
-    print(f"n={n} bit-identical: {same}", flush=True)
+    B = rng.standard_normal((n, max(3, n // 2)))
+    yield "psd", B @ B.T / n + 1e-3 * np.eye(n)
+    if n <= 200 and not QUICK:
+        yield "identity", np.eye(n)
+        yield "zeros", np.zeros((n, n))
+        yield "ones", np.ones((n, n))
+        yield "diag", np.diag(np.arange(1.0, n + 1.0))
+
+
+for n in sizes:
+    for name, A in matrices(n):
+        ref = None
+        for mode in MODES:
+            say(f"## n={n} {name} mode={mode}")
+            try:
+                U, D = run(A, mode, reps=3 if name == "psd" else 1)
+            except Exception as ex:
+                say(f"   FAILED: {ex}")
+                continue
+            if ref is None:
+                ref = (U, D)
+                continue
+            scale = max(1.0, np.abs(ref[1]).max())
+            derr = np.abs(D - ref[1]).max() / scale
+            orth = np.abs(U.T @ U - np.eye(n)).max()
+            resid = np.abs(A @ U - U * D).max() / scale
+            same = np.array_equal(D, ref[1]) and np.array_equal(U, ref[0])
+            ok = derr < 1e-13 * max(1, n / 50) and orth < 1e-11 and resid < 1e-12 * max(1, n / 50)
+            say(f"   {mode}: bit-identical={same} |D-D0|/max={derr:.2e} orth={orth:.2e} resid={resid:.2e} {'ok' if ok else 'BAD'}")
