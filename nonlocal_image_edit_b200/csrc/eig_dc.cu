@@ -78,9 +78,17 @@ __device__ __forceinline__ double block_sum(double v, double* red /*>= 2*kTrdWar
 // Householder tridiagonalisation A = Q T Q^T of a symmetric matrix held in FULL storage (both
 // triangles, column-major).  On exit: d (n), e (n-1), tau (n-1); reflector j (H_j = I - tau_j v v^T,
 // v[j+1] = 1) is stored in A(j+1:n, j) including the explicit 1.
+//
+// DYN (NLE_B200_TRD_DYN=<cols>, developer experiment, off by default): the trailing columns are dealt to only
+// Geff(j) = min(G, ceil(#trailing columns / cols)) CTAs; the others just keep arriving at the grid barrier.  The
+// matrix lives in global memory and every step ends in grid.sync, so ownership may change from step to step, and a
+// column's arithmetic does not depend on which CTA performs it: the result is bit-identical for every `cols`.
+// Motivation: the cost of a step grows with the number of CTAs that read p and the next column
+// (profiles/r1l_trd_phases.md).
+template <bool DYN>
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
-               double* __restrict__ tau, double* __restrict__ pbuf) {
+               double* __restrict__ tau, double* __restrict__ pbuf, int dyn_cols) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];
     double* v = sm;            // current reflector, global row indexing
@@ -148,6 +156,14 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
     }
 
     for (int j = 0; j <= n - 3; ++j) {
+        int Ge = G;       // CTAs that own trailing columns in this step
+        if (DYN) {
+            Ge = min(G, max(1, (n - (j + 2) + dyn_cols - 1) / dyn_cols));
+            if (b >= Ge) {            // Ge never grows again: this CTA only keeps the barrier complete
+                grid.sync();
+                continue;
+            }
+        }
         const double* p = pbuf + (size_t)(j & 1) * n;
         double* pn = pbuf + (size_t)((j + 1) & 1) * n;
         // (0) publish reflector j (column j of A is no longer read by anybody in this kernel)
@@ -189,7 +205,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
         // (3) rank-2 update of the owned columns c >= j+2 fused with the next symv
         const bool has_next = (j + 1 <= n - 3);
         for (int q = warp; ; q += kTrdWarps) {
-            const int c = b + G * q;
+            const int c = b + Ge * q;
             if (c >= n) break;
             if (c < j + 2) continue;
             double* col = A + (size_t)c * lda;
@@ -1349,14 +1365,17 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     }
     if (!trd_done) {
         size_t smem = (3 * (size_t)n + 2 * kTrdWarps) * sizeof(double);
-        NLE_CUDA(cudaFuncSetAttribute(tridiag_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int dyn_cols = 0;
+        if (const char* e = getenv("NLE_B200_TRD_DYN")) dyn_cols = std::max(0, atoi(e));
+        const void* kfn = dyn_cols > 0 ? (const void*)tridiag_kernel<true> : (const void*)tridiag_kernel<false>;
+        NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
-        NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, tridiag_kernel, kTrdThreads, smem));
+        NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
         if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(n) + ")"};
         int grid = std::min(trd_grid_limit(), n);
         int lda = n;
-        void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf};
-        NLE_CUDA(cudaLaunchCooperativeKernel((void*)tridiag_kernel, dim3(grid), dim3(kTrdThreads), args, smem, s));
+        void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf, &dyn_cols};
+        NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
         ++g_launches;
     }
     auto t_trd = tnow();

@@ -1,8 +1,10 @@
 """Developer check + timing of the tridiagonalisation variants (eig_dc.cu):
-   gridsync (default) | NLE_B200_TRD=resident (bit-identical to gridsync) | resident:sys (volatile cells instead of relaxed.gpu).
+   gridsync (default) | resident (NLE_B200_TRD) | resident:sys (volatile cells) | dyn:<cols> (NLE_B200_TRD_DYN: trailing
+   columns dealt to ceil(m / cols) CTAs only) | grid:<G> (NLE_B200_TRD_GRID: at most G CTAs); join with '+', e.g. resident+grid:64.
+   All of them must be bit-identical to gridsync.
    The output of the round-1 runs is condensed in profiles/r1l_trd_phases.md.
 
-  timeout 40 python scripts/gpu_trd_resident.py [n ...] [resident resident:sys ...]      # stderr: per-phase ms (NLE_B200_EIG_PROF) and, for the
+  timeout 40 python scripts/gpu_trd_resident.py [n ...] [resident dyn:8 dyn:16 grid:64 resident+grid:74 ...]      # stderr: per-phase ms (NLE_B200_EIG_PROF) and, for the
                                                              # resident kernels, cycles per step by phase (NLE_B200_TRD_PROF)
 """
 import os, sys, time
@@ -22,12 +24,18 @@ def say(msg):
 
 
 def run(A, mode, reps=3):
-    os.environ.pop("NLE_B200_TRD", None)
-    os.environ.pop("NLE_B200_TRD_LL", None)
-    if mode != "gridsync":
-        os.environ["NLE_B200_TRD"] = mode.split(":")[0]
-        if mode.endswith(":sys"):
-            os.environ["NLE_B200_TRD_LL"] = "sys"       # volatile (sys-scope) cells instead of relaxed.gpu
+    for k in ("NLE_B200_TRD", "NLE_B200_TRD_LL", "NLE_B200_TRD_DYN", "NLE_B200_TRD_GRID"):
+        os.environ.pop(k, None)
+    # a mode is '+'-joined: gridsync | resident | resident:sys | dyn:<cols per CTA> | grid:<max CTAs>
+    for part in mode.split("+"):
+        if part.startswith("dyn:"):
+            os.environ["NLE_B200_TRD_DYN"] = part[4:]
+        elif part.startswith("grid:"):
+            os.environ["NLE_B200_TRD_GRID"] = part[5:]
+        elif part.startswith("resident"):
+            os.environ["NLE_B200_TRD"] = "resident"
+            if part.endswith(":sys"):
+                os.environ["NLE_B200_TRD_LL"] = "sys"       # volatile (sys-scope) cells instead of relaxed.gpu
     os.environ.pop("NLE_B200_EIG_PROF", None)
     os.environ.pop("NLE_B200_TRD_PROF", None)
     out = nb.eigenDecomposition(A, eps=-1e300)                    # warm-up (function attributes, pool)
@@ -35,7 +43,7 @@ def run(A, mode, reps=3):
     for _ in range(reps):
         out = nb.eigenDecomposition(A, eps=-1e300)
     os.environ.pop("NLE_B200_EIG_PROF", None)
-    if mode != "gridsync":
+    if "resident" in mode:
         os.environ["NLE_B200_TRD_PROF"] = "1"
         nb.eigenDecomposition(A, eps=-1e300)
         os.environ.pop("NLE_B200_TRD_PROF", None)

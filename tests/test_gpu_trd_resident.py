@@ -63,3 +63,24 @@ def test_resident_train_equals_default(nb):
     assert np.array_equal(f0.eigvals, f1.eigvals)
     w = [2.0, 3.0, 4.0, 1.0]
     assert np.array_equal(f0.enhanceLuminance(lum, w), f1.enhanceLuminance(lum, w))
+
+
+@pytest.mark.parametrize("env", [{"NLE_B200_TRD_DYN": "4"}, {"NLE_B200_TRD_DYN": "16"}, {"NLE_B200_TRD_GRID": "37"},
+                                 {"NLE_B200_TRD": "resident", "NLE_B200_TRD_GRID": "100"}])
+@pytest.mark.parametrize("n", [5, 149, 700, 1041])
+def test_grid_knobs_are_bit_identical(nb, env, n):
+    """NLE_B200_TRD_DYN / NLE_B200_TRD_GRID only change which CTA owns a column, never a column's arithmetic."""
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, max(3, n // 2)))
+    A = B @ B.T / n + 1e-3 * np.eye(n)
+    for k in ("NLE_B200_TRD", "NLE_B200_TRD_DYN", "NLE_B200_TRD_GRID"):
+        os.environ.pop(k, None)
+    U0, D0 = nb.eigenDecomposition(A, eps=-1e300)
+    os.environ.update(env)
+    os.environ["NLE_B200_EIG_STRICT"] = "1"
+    try:
+        U1, D1 = nb.eigenDecomposition(A, eps=-1e300)
+    finally:
+        for k in list(env) + ["NLE_B200_EIG_STRICT"]:
+            os.environ.pop(k, None)
+    assert np.array_equal(D0, D1) and np.array_equal(U0, U1)
