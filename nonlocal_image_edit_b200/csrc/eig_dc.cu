@@ -416,21 +416,26 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
         {
             const uint4* pc = pcell(T);
             const uint4* cc = ccell(T);
-            bool ok;
-            do {
-                ok = true;
+            // bit u: p cell u still missing, bit kResPer+u: column cell u still missing; a retry round re-reads only
+            // the missing cells (every read of a cell line competes with the store that is to fill it)
+            unsigned pend = 0;
+#pragma unroll
+            for (int u = 0; u < kResPer; ++u)
+                if (j + 1 + tid + u * kTrdThreads < n) pend |= (1u | (1u << kResPer)) << u;
+            while (pend) {
 #pragma unroll
                 for (int u = 0; u < kResPer; ++u) {
                     const int i = j + 1 + tid + u * kTrdThreads;
-                    if (i < n) { P[u] = ll_load(pc + i, sys); C[u] = ll_load(cc + i, sys); }
+                    if (pend & (1u << u)) P[u] = ll_load(pc + i, sys);
+                    if (pend & (1u << (kResPer + u))) C[u] = ll_load(cc + i, sys);
                 }
 #pragma unroll
                 for (int u = 0; u < kResPer; ++u) {
-                    const int i = j + 1 + tid + u * kTrdThreads;
-                    if (i < n) ok = ok && P[u].y == T && P[u].w == T && C[u].y == T && C[u].w == T;
+                    if ((pend & (1u << u)) && P[u].y == T && P[u].w == T) pend &= ~(1u << u);
+                    if ((pend & (1u << (kResPer + u))) && C[u].y == T && C[u].w == T) pend &= ~(1u << (kResPer + u));
                 }
                 if (PROF) ++rounds;
-            } while (!ok);
+            }
         }
         TRD_STAMP(0, ll_value(P[0]));
         double part = 0.0;
@@ -475,6 +480,41 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
             uint4* cc = ccell(Tn);
             double acc = 0.0;
             int i = j + 2 + lane;
+            // batches with all shared-memory loads in front: col, w, v, cn are the same address space to the compiler,
+            // so without this every iteration's loads wait behind the previous iteration's store (profiles/
+            // r1l_trd_phases.md: ~140 cycles per 32-row iteration).  Same operations in the same order per lane.
+            for (; i + 3 * 32 < n; i += 4 * 32) {
+                double a[4], wv[4], vv[4], cv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = col[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
+                    acc = fma(a[u], cv[u], acc);
+                    col[ii] = a[u];
+                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
+                }
+            }
+            for (; i + 32 < n; i += 2 * 32) {
+                double a[2], wv[2], vv[2], cv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = col[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
+                    acc = fma(a[u], cv[u], acc);
+                    col[ii] = a[u];
+                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
+                }
+            }
             for (; i < n; i += 32) {
                 double a = col[i];
                 a = fma(-w[i], vc, fma(-v[i], wc, a));
