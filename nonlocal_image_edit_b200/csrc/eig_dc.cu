@@ -11,6 +11,9 @@
 //                         grid.sync per Householder step: the rank-2 update of step j is fused with
 //                         the symmetric matrix-vector product of step j+1 (the next reflector is
 //                         derived redundantly by every CTA from the updated column j+1).
+//   tridiag_resident_kernel  experiment (NLE_B200_TRD=resident): same arithmetic, trailing matrix resident in
+//                         shared memory, flagged-cell exchange instead of grid.sync; carries the per-phase
+//                         cycle counters behind profiles/r1l_trd_phases.md.
 //   dc_leaf_kernel        implicit-shift QL on leaves of <= 32 rows, one warp per leaf.
 //   dc_setup_kernel       per merge: z vector, rank sort, LAPACK dlaed2-style deflation.
 //   dc_rotate_kernel      applies the deflation Givens rotations to the eigenvector columns.
@@ -263,8 +266,8 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory-resident variant of tridiag_kernel (NLE_B200_TRD=resident; EXPERIMENTAL, off by default
-// until it has been run on the device -- see DESIGN.md section 6).  Same arithmetic in the same order as
+// Shared-memory-resident variant of tridiag_kernel (NLE_B200_TRD=resident; experiment, off by default: measured
+// bit-identical to and within 3 % of tridiag_kernel -- see DESIGN.md section 6).  Same arithmetic in the same order as
 // tridiag_kernel (d, e, tau and the reflectors come out bit-identical); what changes is where the data
 // lives and how the CTAs synchronise:
 //   * CTA b keeps its columns c = b, b+G, ... of the trailing matrix in shared memory for the whole
