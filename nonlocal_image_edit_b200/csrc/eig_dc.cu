@@ -658,7 +658,7 @@ dc_setup_kernel(int n, int depth, const double* __restrict__ e, const double* __
     int* csrt = reinterpret_cast<int*>(smd + 3 * (size_t)nm);
     int* cdef = csrt + nm;
     __shared__ double redm[64];
-    __shared__ int s_k, s_ndef, s_nrot;
+    __shared__ int s_k, s_ndef;
 
     const double beta = e[split - 1];
     const double sgn = (beta >= 0.0) ? 1.0 : -1.0;
@@ -748,7 +748,7 @@ dc_setup_kernel(int n, int depth, const double* __restrict__ e, const double* __
                 }
             }
             if (tid == 0) {
-                s_k = total_k; s_ndef = nm - total_k; s_nrot = 0;
+                s_k = total_k; s_ndef = nm - total_k;
                 a.kArr[node] = total_k; a.nrotArr[node] = 0; a.rhoArr[node] = rho;
             }
         }
@@ -799,7 +799,7 @@ dc_setup_kernel(int n, int depth, const double* __restrict__ e, const double* __
                 ++k;
             }
         }
-        s_k = k; s_ndef = ndef; s_nrot = nrot;
+        s_k = k; s_ndef = ndef;
         a.kArr[node] = k; a.nrotArr[node] = nrot; a.rhoArr[node] = rho;
     }
     __syncthreads();

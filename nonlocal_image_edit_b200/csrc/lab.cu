@@ -16,7 +16,7 @@ namespace {
 #undef NLE_LAB_TAB
 
 constexpr int kGammaN = 256, kCbrtN = 3072, kInvGammaN = 4096;
-constexpr int kLabShift = 12, kLabShift2 = 15, kBase = 1 << 14, kMinAB = -8145;
+constexpr int kLabShift = 12, kLabShift2 = 15, kBase = 1 << 14;
 
 __device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
 __device__ __forceinline__ int sat_u8(int v) { return v < 0 ? 0 : (v > 255 ? 255 : v); }
