@@ -555,6 +555,254 @@ tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restri
         }
     }
 }
+// Cluster variant of the resident kernel (NLE_B200_TRD=cluster, NLE_B200_TRD_CLUSTER=<S>; prepared for the next round,
+// NOT yet run on a device).  The resident kernel's counters show the step is bound by 148 CTAs reading every cell
+// (profiles/r1l_trd_phases.md).  Here the CTAs of a thread-block cluster share the polling: CTA `rank` polls every S-th
+// cell and forwards what it receives to its peers through distributed shared memory, one cluster barrier per step makes the
+// vectors complete everywhere.  Readers per cell: G/S.  Everything behind the barrier is the resident kernel's arithmetic
+// in the same order (bit-identical results expected).
+template <bool PROF>
+__global__ void __launch_bounds__(kTrdThreads, 1)
+tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
+                        double* __restrict__ tau, uint4* __restrict__ ll /* 4n cells, zeroed before the launch */,
+                        long long* __restrict__ prof /* 16 counters when PROF */, int ll_sys) {
+    cg::cluster_group cluster = cg::this_cluster();
+    const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    extern __shared__ double sm[];
+    // Peers write p and the next column straight into this CTA's vectors, possibly one step ahead of it: w has two
+    // buffers (step parity) and the reflector / next-column vectors rotate through three, so a buffer is written
+    // again only behind the cluster barrier of the step after its last reader.
+    double* Wb = sm;                       // 2 n
+    double* Vb = sm + 2 * (size_t)n;       // 3 n
+    double* red = sm + 5 * (size_t)n;      // 2*kTrdWarps
+    double* cols = red + 2 * kTrdWarps;    // owned columns, slot q holds column b + G*q (all n rows)
+    double* v = Vb;            // current reflector, global row indexing
+    double* w = Wb;
+    double* cn = Vb;           // updated next column -> next reflector (first reflector is built here, then becomes v)
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = gridDim.x, b = blockIdx.x;
+    const int q_last = (n - 1 - b) / G;          // b < G <= n
+    const int c_last = b + G * q_last;           // the largest column this CTA owns
+    const bool writer = (c_last == n - 1);
+    int cl_last = 0;                             // the largest column any CTA of this cluster owns
+    for (int r = 0; r < S; ++r) {
+        const int br = b - rank + r;
+        cl_last = max(cl_last, br + G * ((n - 1 - br) / G));
+    }
+    const bool sys = ll_sys != 0;
+    cluster.sync();            // no CTA touches a peer's shared memory before that peer is running
+    int phase = 0;
+    long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tprev = 0, rounds = 0;
+    // cells of tag t: p at ll + (t&1)*2n, next column at ll + (t&1)*2n + n
+    auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n; };
+    auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n + n; };
+
+    auto make_reflector = [&](int j0, double& tau_out) -> double {     // identical to tridiag_kernel's
+        const double alpha = cn[j0 + 1];
+        double part = 0.0;
+        for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
+        const double xn2 = block_sum(part, red, phase);
+        TRD_STAMP(4, xn2);
+        double beta;
+        if (xn2 == 0.0) {
+            tau_out = 0.0;
+            beta = alpha;
+            __syncthreads();
+            if (tid == 0) cn[j0 + 1] = 1.0;
+        } else {
+            beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+            tau_out = (beta - alpha) / beta;
+            const double scal = 1.0 / (alpha - beta);
+            TRD_STAMP(5, scal + tau_out);
+            __syncthreads();
+            for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) cn[i] *= scal;
+            if (tid == 0) cn[j0 + 1] = 1.0;
+        }
+        __syncthreads();
+        return beta;
+    };
+
+    // owned columns -> shared memory; column 0 -> first reflector (every CTA, redundantly)
+    for (int q = 0; q <= q_last; ++q) {
+        const double* src = A + (size_t)(b + G * q) * lda;
+        double* dst = cols + (size_t)q * n;
+        for (int i = tid; i < n; i += kTrdThreads) dst[i] = src[i];
+    }
+    for (int i = tid; i < n; i += kTrdThreads) cn[i] = A[i];
+    __syncthreads();
+    double tau_j, beta_j, diag_j;
+    diag_j = cn[0];
+    beta_j = make_reflector(0, tau_j);
+    v = Vb;                    // step j: v = Vb[j % 3], cn = Vb[(j + 1) % 3], w = Wb[j & 1]
+    // p = A v over the owned columns c >= 1 (tag 1); the owner of column 1 also publishes that column
+    for (int q = warp; q <= q_last; q += kTrdWarps) {
+        const int c = b + G * q;
+        if (c < 1) continue;
+        const double* col = cols + (size_t)q * n;
+        double acc = 0.0;
+        for (int i = 1 + lane; i < n; i += 32) acc = fma(col[i], v[i], acc);
+        acc = warp_sum(acc);
+        if (lane == 0) ll_store(pcell(1) + c, acc, 1u, sys);
+        if (c == 1)
+            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u, sys);
+    }
+    if (PROF && tid == 0) {
+        tprev = clock64();
+#pragma unroll
+        for (int k = 0; k < 10; ++k) pacc[k] = 0;
+    }
+
+    for (int j = 0; j <= n - 3; ++j) {
+        if (cl_last < j + 2) return;      // cluster-uniform: the whole cluster leaves together, after its last barrier
+        v = Vb + (size_t)(j % 3) * n;
+        cn = Vb + (size_t)((j + 1) % 3) * n;
+        w = Wb + (size_t)(j & 1) * n;
+        const unsigned T = (unsigned)(j + 1);
+        const bool has_next = (j + 1 <= n - 3);
+        double diag_next, tau_next = 0.0, beta_next;
+        // (1) this CTA polls the cells of rows j+1+rank, j+1+rank+S, ... only (1/S of the readers per cell) and
+        //     writes what it received into the w / cn vectors of every CTA of the cluster (distributed shared memory)
+        {
+            const uint4* pc = pcell(T);
+            const uint4* cc = ccell(T);
+            uint4 P[kResPer], C[kResPer];
+            unsigned pend = 0;
+#pragma unroll
+            for (int u = 0; u < kResPer; ++u)
+                if (j + 1 + rank + S * (tid + u * kTrdThreads) < n) pend |= (1u | (1u << kResPer)) << u;
+            const unsigned mine = pend;
+            while (pend) {
+#pragma unroll
+                for (int u = 0; u < kResPer; ++u) {
+                    const int i = j + 1 + rank + S * (tid + u * kTrdThreads);
+                    if (pend & (1u << u)) P[u] = ll_load(pc + i, sys);
+                    if (pend & (1u << (kResPer + u))) C[u] = ll_load(cc + i, sys);
+                }
+#pragma unroll
+                for (int u = 0; u < kResPer; ++u) {
+                    if ((pend & (1u << u)) && P[u].y == T && P[u].w == T) pend &= ~(1u << u);
+                    if ((pend & (1u << (kResPer + u))) && C[u].y == T && C[u].w == T) pend &= ~(1u << (kResPer + u));
+                }
+                if (PROF) ++rounds;
+            }
+            TRD_STAMP(0, ll_value(P[0]));
+            for (int r = 0; r < S; ++r) {
+                double* wr = cluster.map_shared_rank(w, r);
+                double* cr = cluster.map_shared_rank(cn, r);
+#pragma unroll
+                for (int u = 0; u < kResPer; ++u) {
+                    const int i = j + 1 + rank + S * (tid + u * kTrdThreads);
+                    if (mine & (1u << u)) { wr[i] = ll_value(P[u]); cr[i] = ll_value(C[u]); }
+                }
+            }
+        }
+        cluster.sync();       // every CTA of the cluster now holds all of p (in w) and of column j+1 (in cn)
+        TRD_STAMP(9, w[j + 1]);
+        double part = 0.0;
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) part = fma(w[i], v[i], part);
+        // w = tau*p - (tau^2/2)(p.v) v
+        const double dot = block_sum(part, red, phase);
+        TRD_STAMP(1, dot);
+        const double kappa = 0.5 * tau_j * tau_j * dot;
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
+        __syncthreads();
+        // (2) updated column j+1 -> next diagonal and next reflector
+        const double wj1 = w[j + 1];   // v[j+1] == 1
+        TRD_STAMP(2, wj1);
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
+        __syncthreads();
+        diag_next = cn[j + 1];
+        TRD_STAMP(3, diag_next);
+        if (has_next) {
+            beta_next = make_reflector(j + 1, tau_next);     // stamps 4, 5
+        } else {
+            beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
+        }
+        TRD_STAMP(6, beta_next);
+        // (3) rank-2 update of the owned columns c >= j+2 (in shared memory) fused with the next symv;
+        //     the owner of column j+2 publishes the updated column as it goes
+        const unsigned Tn = (unsigned)(j + 2);
+        for (int q = warp; q <= q_last; q += kTrdWarps) {
+            const int c = b + G * q;
+            if (c < j + 2) continue;
+            double* col = cols + (size_t)q * n;
+            const double wc = w[c], vc = v[c];
+            const bool pub = has_next && c == j + 2;
+            uint4* cc = ccell(Tn);
+            double acc = 0.0;
+            int i = j + 2 + lane;
+            // batches with all shared-memory loads in front: col, w, v, cn are the same address space to the compiler,
+            // so without this every iteration's loads wait behind the previous iteration's store (profiles/
+            // r1l_trd_phases.md: ~140 cycles per 32-row iteration).  Same operations in the same order per lane.
+            for (; i + 3 * 32 < n; i += 4 * 32) {
+                double a[4], wv[4], vv[4], cv[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = col[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
+                    acc = fma(a[u], cv[u], acc);
+                    col[ii] = a[u];
+                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
+                }
+            }
+            for (; i + 32 < n; i += 2 * 32) {
+                double a[2], wv[2], vv[2], cv[2];
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = col[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
+                }
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                    const int ii = i + 32 * u;
+                    a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
+                    acc = fma(a[u], cv[u], acc);
+                    col[ii] = a[u];
+                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
+                }
+            }
+            for (; i < n; i += 32) {
+                double a = col[i];
+                a = fma(-w[i], vc, fma(-v[i], wc, a));
+                acc = fma(a, cn[i], acc);
+                col[i] = a;
+                if (pub) ll_store(cc + i, a, Tn, sys);
+            }
+            if (has_next) {
+                acc = warp_sum(acc);
+                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn, sys);
+            }
+        }
+        TRD_STAMP(7, 0.0);
+        // (0) reflector j and its scalars (off the critical path: nobody in this kernel reads them back)
+        if (writer) {
+            double* colj = A + (size_t)j * lda;
+            for (int i = j + 1 + tid; i < n; i += kTrdThreads) colj[i] = v[i];
+            if (tid == 0) { d[j] = diag_j; e[j] = beta_j; tau[j] = tau_j; }
+        }
+        diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
+        __syncthreads();   // keeps the warps of a CTA together so that the poll starts once per CTA, not once per warp
+        TRD_STAMP(8, cn[j + 2]);
+    }
+    if (writer && tid == 0) {
+        d[n - 2] = diag_j;
+        e[n - 2] = beta_j;
+        tau[n - 2] = 0.0;
+        d[n - 1] = cols[(size_t)q_last * n + (n - 1)];
+        if (PROF) {
+#pragma unroll
+            for (int k = 0; k < 10; ++k) prof[k] = pacc[k];
+            prof[10] = rounds;
+            prof[11] = n - 2;
+        }
+    }
+}
 #undef TRD_STAMP
 
 // ---------------------------------------------------------------------------------------------
@@ -1366,7 +1614,74 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         const char* env = getenv("NLE_B200_TRD");
         const std::string mode = env ? env : "";
         int grid = std::min(trd_grid_limit(), n);
-        if (mode == "resident" && n >= 3 && n <= kResPer * kTrdThreads) {
+        if (mode == "cluster" && n >= 64 && n <= kResPer * kTrdThreads) {
+            // thread-block clusters share the polling (tridiag_cluster_kernel; prepared, not yet run on a device)
+            const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
+            int S = 4;
+            if (const char* e = getenv("NLE_B200_TRD_CLUSTER")) S = std::max(1, std::min(16, atoi(e)));
+            int dev = 0, max_smem = 0;
+            NLE_CUDA(cudaGetDevice(&dev));
+            NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+            const void* kfn = kprof ? (const void*)tridiag_cluster_kernel<true> : (const void*)tridiag_cluster_kernel<false>;
+            if (S > 8) NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+            // the grid depends on how many clusters fit, which depends on the shared memory, which depends on the grid:
+            // start from the cap and shrink until the launch configuration is consistent
+            int G = (std::min(grid, n) / S) * S;
+            for (int it = 0; it < 4 && G >= S; ++it) {
+                const int qmax = cdiv(n, G);
+                const size_t smem = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
+                if (smem > (size_t)max_smem) { G = 0; break; }
+                NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(G);
+                cfg.blockDim = dim3(kTrdThreads);
+                cfg.dynamicSmemBytes = smem;
+                cfg.stream = s;
+                cudaLaunchAttribute at[2];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                at[1].id = cudaLaunchAttributeCooperative;     // only for its co-residency guarantee
+                at[1].val.cooperative = 1;
+                cfg.attrs = at;
+                cfg.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &cfg) != cudaSuccess) { cudaGetLastError(); G = 0; break; }
+                if (ncl * S < G) { G = ncl * S; continue; }      // fewer clusters fit: retry with the smaller grid
+                cfg.numAttrs = 2;
+                const size_t cells = 4 * (size_t)n + 8;
+                if (ws.trdll.n < cells) ws.trdll.alloc(cells);
+                NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));
+                int lda = n;
+                uint4* ll = ws.trdll.p;
+                long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * (size_t)n);
+                const char* lle = getenv("NLE_B200_TRD_LL");
+                int ll_sys = (lle && std::string(lle) == "sys") ? 1 : 0;
+                void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp, &ll_sys};
+                cudaError_t rc = cudaLaunchKernelExC(&cfg, kfn, args);
+                if (rc != cudaSuccess) {                      // cooperative + cluster refused: the grid fits anyway
+                    cudaGetLastError();
+                    cfg.numAttrs = 1;
+                    rc = cudaLaunchKernelExC(&cfg, kfn, args);
+                }
+                NLE_CUDA(rc);
+                ++g_launches;
+                trd_done = true;
+                if (kprof) {
+                    long long h[16];
+                    NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
+                    NLE_CUDA(cudaStreamSynchronize(s));
+                    const double st = (double)std::max(1LL, h[11]);
+                    double tot = 0;
+                    for (int k = 0; k < 10; ++k) tot += (double)h[k];
+                    fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: poll %.0f | forward+cluster.sync %.0f | dot-reduce %.0f | w %.0f | "
+                            "col %.0f | norm-reduce %.0f | sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; "
+                            "poll rounds/step %.2f\n", S, G, n, h[0] / st, h[9] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st,
+                            h[5] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
+                }
+                break;
+            }
+        }
+        if (!trd_done && mode == "resident" && n >= 3 && n <= kResPer * kTrdThreads) {
             const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
             int dev = 0, max_smem = 0;
             NLE_CUDA(cudaGetDevice(&dev));

@@ -1,6 +1,6 @@
 """Developer check + timing of the tridiagonalisation variants (eig_dc.cu):
    gridsync (default) | resident (NLE_B200_TRD) | resident:sys (volatile cells) | dyn:<cols> (NLE_B200_TRD_DYN: trailing
-   columns dealt to ceil(m / cols) CTAs only) | grid:<G> (NLE_B200_TRD_GRID: at most G CTAs); join with '+', e.g. resident+grid:64.
+   columns dealt to ceil(m / cols) CTAs only) | cluster[:S] (NLE_B200_TRD=cluster: clusters of S CTAs share the polling) | grid:<G> (NLE_B200_TRD_GRID: at most G CTAs); join with '+', e.g. resident+grid:64.
    All of them must be bit-identical to gridsync.
    The output of the round-1 runs is condensed in profiles/r1l_trd_phases.md.
 
@@ -24,14 +24,18 @@ def say(msg):
 
 
 def run(A, mode, reps=3):
-    for k in ("NLE_B200_TRD", "NLE_B200_TRD_LL", "NLE_B200_TRD_DYN", "NLE_B200_TRD_GRID"):
+    for k in ("NLE_B200_TRD", "NLE_B200_TRD_LL", "NLE_B200_TRD_DYN", "NLE_B200_TRD_GRID", "NLE_B200_TRD_CLUSTER"):
         os.environ.pop(k, None)
-    # a mode is '+'-joined: gridsync | resident | resident:sys | dyn:<cols per CTA> | grid:<max CTAs>
+    # a mode is '+'-joined: gridsync | resident | resident:sys | cluster[:S] | dyn:<cols per CTA> | grid:<max CTAs>
     for part in mode.split("+"):
         if part.startswith("dyn:"):
             os.environ["NLE_B200_TRD_DYN"] = part[4:]
         elif part.startswith("grid:"):
             os.environ["NLE_B200_TRD_GRID"] = part[5:]
+        elif part.startswith("cluster"):
+            os.environ["NLE_B200_TRD"] = "cluster"
+            if ":" in part:
+                os.environ["NLE_B200_TRD_CLUSTER"] = part.split(":")[1]
         elif part.startswith("resident"):
             os.environ["NLE_B200_TRD"] = "resident"
             if part.endswith(":sys"):
@@ -43,7 +47,7 @@ def run(A, mode, reps=3):
     for _ in range(reps):
         out = nb.eigenDecomposition(A, eps=-1e300)
     os.environ.pop("NLE_B200_EIG_PROF", None)
-    if "resident" in mode:
+    if "resident" in mode or "cluster" in mode:
         os.environ["NLE_B200_TRD_PROF"] = "1"
         nb.eigenDecomposition(A, eps=-1e300)
         os.environ.pop("NLE_B200_TRD_PROF", None)

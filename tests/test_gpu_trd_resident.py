@@ -66,14 +66,17 @@ def test_resident_train_equals_default(nb):
 
 
 @pytest.mark.parametrize("env", [{"NLE_B200_TRD_DYN": "4"}, {"NLE_B200_TRD_DYN": "16"}, {"NLE_B200_TRD_GRID": "37"},
-                                 {"NLE_B200_TRD": "resident", "NLE_B200_TRD_GRID": "100"}])
-@pytest.mark.parametrize("n", [5, 149, 700, 1041])
+                                 {"NLE_B200_TRD": "resident", "NLE_B200_TRD_GRID": "100"},
+                                 {"NLE_B200_TRD": "cluster", "NLE_B200_TRD_CLUSTER": "2"},
+                                 {"NLE_B200_TRD": "cluster", "NLE_B200_TRD_CLUSTER": "4"},
+                                 {"NLE_B200_TRD": "cluster", "NLE_B200_TRD_CLUSTER": "8"}])
+@pytest.mark.parametrize("n", [5, 64, 149, 700, 1041, 1600])
 def test_grid_knobs_are_bit_identical(nb, env, n):
     """NLE_B200_TRD_DYN / NLE_B200_TRD_GRID only change which CTA owns a column, never a column's arithmetic."""
     rng = np.random.default_rng(n)
     B = rng.standard_normal((n, max(3, n // 2)))
     A = B @ B.T / n + 1e-3 * np.eye(n)
-    for k in ("NLE_B200_TRD", "NLE_B200_TRD_DYN", "NLE_B200_TRD_GRID"):
+    for k in ("NLE_B200_TRD", "NLE_B200_TRD_DYN", "NLE_B200_TRD_GRID", "NLE_B200_TRD_CLUSTER"):
         os.environ.pop(k, None)
     U0, D0 = nb.eigenDecomposition(A, eps=-1e300)
     os.environ.update(env)
