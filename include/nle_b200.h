@@ -14,7 +14,7 @@
  *   - Pointers are HOST pointers unless the function name ends in _dev.
  *   - Every function returns 0 on success, a negative nle_b200_status otherwise, and never throws;
  *     nle_b200_last_error() returns the message for the calling thread.  The reference's
- *     std::runtime_error messages (filter.cpp:118,415,419,448) are reproduced verbatim there.
+ *     std::runtime_error messages (filter.cpp:118,352,356,415,419,448) are reproduced verbatim there.
  *   - There is no CPU fallback: without a CUDA device every compute call fails with
  *     NLE_B200_ERR_CUDA.
  *   - A filter handle is not thread-safe; distinct handles are independent.
@@ -49,7 +49,9 @@ typedef struct {
     int r2;              /* #eigenvalues of Wa >= 1e-10 (filter.cpp:287)                 */
     int k;               /* eigenvectors kept: min(nEigenVectors, #eig(Q)>=1e-10)        */
     int n_row_samples_eff, n_col_samples_eff; /* grid actually produced by samplePixels  */
-    int eig_sweeps[3];   /* Jacobi sweeps used by the three eigensolves                  */
+    int eig_sweeps[3];   /* Jacobi sweeps used by the three eigensolves (0 = direct solver) */
+    int eig_fallbacks;   /* eigensolves of this training call that fell back from the direct solver to block
+                            Jacobi (also reported on stderr when it happens); 0 in normal operation */
 } nle_b200_info;
 
 /* Small all-reduce (sum) used by row-sharded training/apply.  `dev_buf` is a DEVICE pointer to
@@ -57,6 +59,17 @@ typedef struct {
  * `cuda_stream` (a cudaStream_t) or synchronously.  The host language supplies it (the Python host
  * wraps torch.distributed/NCCL).  Only p-vectors, one p x p Gram and k-vectors ever go through it. */
 typedef int (*nle_b200_allreduce_fn)(void* dev_buf, size_t count, void* cuda_stream, void* user);
+
+/* NCCL communicator owned by the library (csrc/nccl_comm.cu; libnccl is resolved with dlopen at the first call, the
+ * library itself links no NCCL).  Rank 0 calls nle_b200_comm_unique_id and the host ferries the 128 bytes to the other
+ * ranks (any transport); then EVERY rank calls nle_b200_comm_create on its own device (collective).  Pass
+ * nle_b200_comm_allreduce as `allreduce` and the communicator as `user` to the sharded training entry points: the
+ * p-vector / Gram / k-vector sums are then ncclAllReduce calls enqueued by the library on its own stream. */
+typedef struct nle_b200_comm nle_b200_comm;
+int nle_b200_comm_unique_id(unsigned char id[128]);
+int nle_b200_comm_create(const unsigned char id[128], int rank, int nranks, nle_b200_comm** out);
+int nle_b200_comm_allreduce(void* dev_buf, size_t count, void* cuda_stream, void* user /* nle_b200_comm* */);
+void nle_b200_comm_destroy(nle_b200_comm* comm);
 
 const char* nle_b200_last_error(void);
 int nle_b200_version(void);
@@ -131,16 +144,19 @@ int nle_b200_eigenvalues(const nle_b200_filter* f, double* S);
 int nle_b200_eigenvectors(const nle_b200_filter* f, double* V);
 
 /* ---- NLEFilter::apply, filter.cpp:445-458:  out = V diag(fS) V^T channel ---------------------- */
-/* channel/out: the owned slab, (row1-row0)*cols doubles. */
-int nle_b200_apply(const nle_b200_filter* f, const double* channel, const double* fS, double* out);
+/* channel/out: the owned slab, (row1-row0)*cols doubles; n_values = channel.total(): a mismatch fails with the
+ * reference's message "Number of values in channel must match that of training image." (filter.cpp:447-449). */
+int nle_b200_apply(const nle_b200_filter* f, const double* channel, long long n_values, const double* fS,
+                   double* out);
 /* enhance on the L channel (filter.cpp:426-436): u8 -> transformEigenValues -> apply ->
  * max(.,0) -> min(.,255) -> convertTo(CV_8U) (round half to even), fused on the device. */
 int nle_b200_enhance_luminance_u8(const nle_b200_filter* f, const uint8_t* lum,
                                   const double* weights, int m, uint8_t* out);
 int nle_b200_enhance_luminance_u8_dev(const nle_b200_filter* f, const uint8_t* lum_slab_dev,
                                       const double* weights, int m, uint8_t* out_slab_dev);
-/* denoise's per-channel step (filter.cpp:378-399): teig = pow(min(S,1),k); apply; clamp; round. */
-int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, double k,
+/* denoise's per-channel step (filter.cpp:378-399): teig = pow(min(S,1),k); apply; clamp; round.  rows x cols = the
+ * channel passed (owned slab); a size mismatch fails with the message of filter.cpp:355-357. */
+int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, int rows, int cols, double k,
                                 uint8_t* out);
 
 /* ---- image-level entry points with the colour conversion on the device ------------------------
@@ -154,9 +170,12 @@ int nle_b200_train_bgr_u8(const uint8_t* bgr, int rows, int cols, int row0, int 
                           int nColSamples, double hx, double hy, int nSinkhornIter, int nEigenVectors,
                           nle_b200_allreduce_fn allreduce, void* user, nle_b200_filter** out);
 /* NLEFilter::enhance, filter.cpp:412-443, on the owned slab: BGR2Lab, enhance L (transformEigenValues, apply, clamp,
- * round), merge with the untouched a,b, Lab2BGR.  bgr_slab/out_slab: (row1-row0) x cols x 3 host bytes. */
-int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, const double* weights, int m,
-                            uint8_t* out_slab);
+ * round), merge with the untouched a,b, Lab2BGR.  bgr_slab/out_slab: rows x cols x 3 host bytes, rows x cols being the
+ * image (slab) passed: channels != 3 fails with "Can only enhance RGB image." (filter.cpp:414-416) and
+ * rows*cols != (row1-row0)*cols of the handle with "Cannot apply filter on image with different size from the image
+ * filter was trained on." (filter.cpp:418-420). */
+int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, int rows, int cols, int channels,
+                            const double* weights, int m, uint8_t* out_slab);
 
 /* ---- stage intermediates for parity tests (SURVEY.md 8b "test hooks") ------------------------ */
 typedef enum {
@@ -168,7 +187,11 @@ typedef enum {
     NLE_B200_STAGE_Q = 5,         /* r x r                                   */
     NLE_B200_STAGE_LA = 6,        /* r2     eigenvalues of Wa kept           */
     NLE_B200_STAGE_GRAM = 7,      /* p x p  sum_j c_j^2 k_j k_j^T (rest)     */
-    NLE_B200_STAGE_TIMES_MS = 8   /* 8 doubles: per-stage device milliseconds */
+    NLE_B200_STAGE_TIMES_MS = 8   /* 16 doubles, device milliseconds of the training call (CUDA events recorded without
+                                     host synchronisation): 0 tables+Ka | 1 eig(Ka) | 2 Sinkhorn | 3 Gram incl. all-reduce |
+                                     4 small algebra + eig(Wa) + eig(Q) | 5 extension | 6 total | 7 Gram kernels only |
+                                     8 tridiagonalisations | 9 divide & conquer | 10 back-transformations (sums over the
+                                     three eigensolves) | 11..15 reserved */
 } nle_b200_stage;
 /* Copies min(cap, size) doubles; *size_out = full size.  Stages are kept only when the filter was
  * trained with nle_b200_set_keep_stages(1) (default 1; bench turns it off). */
@@ -181,8 +204,13 @@ long long nle_b200_launch_count(int reset);
 /* FP64 FMA throughput of this GPU measured by a register-resident microbenchmark (TFLOP/s); the
  * roofline denominator bench.py uses for the DFMA-bound Gram kernel. */
 double nle_b200_fp64_fma_peak_tflops(void);
+/* Same for the FP64 tensor pipe: back-to-back mma.sync.m8n8k4.f64 (SASS DMMA) with register operands (TFLOP/s). */
+double nle_b200_fp64_dmma_peak_tflops(void);
 
 void nle_b200_free(nle_b200_filter* f);
+/* Releases what the calling thread keeps between calls (the parked eigenvector buffer of the last freed filter and the
+ * arena of training temporaries).  Optional; a long-lived host calls it when it stops filtering. */
+void nle_b200_release_cache(void);
 
 #ifdef __cplusplus
 }

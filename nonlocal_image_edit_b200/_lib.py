@@ -16,7 +16,7 @@ class Info(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("row0", C.c_int), ("row1", C.c_int),
                 ("p", C.c_int), ("r", C.c_int), ("r2", C.c_int), ("k", C.c_int),
                 ("n_row_samples_eff", C.c_int), ("n_col_samples_eff", C.c_int),
-                ("eig_sweeps", C.c_int * 3)]
+                ("eig_sweeps", C.c_int * 3), ("eig_fallbacks", C.c_int)]
 
 
 # every symbol include/nle_b200.h declares: name -> (restype, argtypes)
@@ -44,19 +44,25 @@ SYMBOLS = {
     "nle_b200_filter_info": (C.c_int, [_P, C.POINTER(Info)]),
     "nle_b200_eigenvalues": (C.c_int, [_P, _P]),
     "nle_b200_eigenvectors": (C.c_int, [_P, _P]),
-    "nle_b200_apply": (C.c_int, [_P, _P, _P, _P]),
+    "nle_b200_apply": (C.c_int, [_P, _P, C.c_longlong, _P, _P]),
     "nle_b200_enhance_luminance_u8": (C.c_int, [_P, _P, _P, C.c_int, _P]),
     "nle_b200_enhance_luminance_u8_dev": (C.c_int, [_P, _P, _P, C.c_int, _P]),
-    "nle_b200_denoise_channel_u8": (C.c_int, [_P, _P, C.c_double, _P]),
+    "nle_b200_denoise_channel_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_double, _P]),
     "nle_b200_bgr_to_lab_u8": (C.c_int, [_P, C.c_longlong, _P]),
     "nle_b200_lab_to_bgr_u8": (C.c_int, [_P, C.c_longlong, _P]),
     "nle_b200_train_bgr_u8": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, C.c_int, C.c_int, ALLREDUCE_FN, _P, C.POINTER(_P)]),
-    "nle_b200_enhance_bgr_u8": (C.c_int, [_P, _P, _P, C.c_int, _P]),
+    "nle_b200_enhance_bgr_u8": (C.c_int, [_P, _P, C.c_int, C.c_int, C.c_int, _P, C.c_int, _P]),
     "nle_b200_get_stage": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(C.c_size_t)]),
     "nle_b200_set_keep_stages": (None, [C.c_int]),
     "nle_b200_launch_count": (C.c_longlong, [C.c_int]),
     "nle_b200_free": (None, [_P]),
+    "nle_b200_release_cache": (None, []),
+    "nle_b200_comm_unique_id": (C.c_int, [_P]),
+    "nle_b200_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
+    "nle_b200_comm_allreduce": (C.c_int, [_P, C.c_size_t, _P, _P]),
+    "nle_b200_comm_destroy": (None, [_P]),
     "nle_b200_fp64_fma_peak_tflops": (C.c_double, []),
+    "nle_b200_fp64_dmma_peak_tflops": (C.c_double, []),
 }
 
 _lib = None

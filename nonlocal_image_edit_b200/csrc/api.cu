@@ -85,6 +85,26 @@ struct Timer {
     ~Timer() { cudaEventDestroy(a); cudaEventDestroy(b); }
 };
 
+// Stage marks of one training call: events are only RECORDED while the pipeline is enqueued (no host
+// synchronisation); the elapsed times are read once, after the call's final stream synchronisation.
+struct StageClock {
+    static constexpr int kMax = 16;
+    cudaEvent_t ev[kMax];
+    bool have[kMax];
+    cudaStream_t s;
+    explicit StageClock(cudaStream_t st) : s(st) {
+        for (int i = 0; i < kMax; ++i) { cudaEventCreate(&ev[i]); have[i] = false; }
+    }
+    ~StageClock() { for (int i = 0; i < kMax; ++i) cudaEventDestroy(ev[i]); }
+    void mark(int i) { cudaEventRecord(ev[i], s); have[i] = true; }
+    double ms(int a, int b) const {
+        if (!have[a] || !have[b]) return 0.0;
+        float v = 0;
+        if (cudaEventElapsedTime(&v, ev[a], ev[b]) != cudaSuccess) { cudaGetLastError(); return 0.0; }
+        return v;
+    }
+};
+
 }  // namespace nle
 
 using namespace nle;
@@ -102,10 +122,12 @@ struct nle_b200_filter {
     DevBuf<double> io64_in, io64_out;
     // stages
     DevBuf<double> Ka, lam, rvec_head, c, Wa, Q, la, Gram;
-    double times_ms[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    double times_ms[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    int eig_fallbacks = 0;
     nle_b200_allreduce_fn allreduce = nullptr;
     void* user = nullptr;
     cudaStream_t stream = nullptr;
+    int device = 0;
 };
 
 namespace nle {
@@ -116,9 +138,16 @@ namespace nle {
 // driver for it (a fresh 400 MB mapping costs 0.1-1 s and the general pool fragments under the small I/O
 // buffers of the host-pointer path).
 static thread_local DevBuf<double> g_v_cache;
+static thread_local int g_v_cache_dev = -1;   // device the parked buffer lives on
+
+static int current_device() {
+    int dev = 0;
+    NLE_CUDA(cudaGetDevice(&dev));
+    return dev;
+}
 
 static void take_v(DevBuf<double>& V, size_t count) {
-    if (g_v_cache.p && g_v_cache.n >= count) {
+    if (g_v_cache.p && g_v_cache_dev == current_device() && g_v_cache.n >= count) {
         V = std::move(g_v_cache);
     } else {
         g_v_cache.release();
@@ -173,6 +202,37 @@ double measure_fp64_peak_tflops() {
     return best;
 }
 
+// FP64 tensor-pipe microbenchmark: back-to-back mma.sync.m8n8k4.f64 (SASS DMMA) on 8 independent accumulator
+// pairs per warp, operands in registers: the issue-rate ceiling of the DMMA-bound kernels (Gram, level GEMMs).
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+    double d[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) d[u] = threadIdx.x + u;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) dmma884(d[2 * u], d[2 * u + 1], a, b);
+    }
+    double r = 0;
+#pragma unroll
+    for (int u = 0; u < 16; ++u) r += d[u];
+    if (r == 123.456) out[0] = r;
+}
+double measure_dmma_peak_tflops() {
+    cudaStream_t s = nullptr;
+    DevBuf<double> d(1);
+    const int iters = 4096, blocks = sm_count() * 4;
+    double best = 0.0;
+    for (int rep = 0; rep < 5; ++rep) {
+        Timer t(s);
+        dmma_peak_kernel<<<blocks, 256, 0, s>>>(d.p, iters, 0.999999, 1e-9);
+        NLE_LAUNCH_CHECK();
+        double ms = t.stop();
+        double flops = 2.0 * 8 * 8 * 4 * 8.0 * iters * (256.0 / 32.0) * blocks;     // 512 flop per warp-level DMMA
+        best = std::max(best, flops / (ms * 1e-3) * 1e-12);
+    }
+    return best;
+}
+
 // small vector helpers used by the Sinkhorn loop
 __global__ void vec_axpy_kernel(double* y, const double* x, const double* scale, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -222,6 +282,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     f->nloc = (long long)(row1 - row0) * cols;
     f->p = p; f->nR = nR; f->nC = nC;
     f->allreduce = allreduce; f->user = user;
+    f->device = current_device();
     cudaStream_t s = nullptr;   // legacy default stream: ordered with the caller's work
     f->stream = s;
     const long long nloc = f->nloc;
@@ -229,8 +290,11 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
 
     thread_arena().reset();     // all temporaries below are TmpBuf views of the thread's arena
     Trace tr(s);
-    Timer t_total(s);
-    Timer t_setup(s);
+    StageClock clk(s);                          // marks: 0 start | 1 Ka | 2 eig(Ka) | 3 Sinkhorn | 4 Gram kernels | 5 Gram
+    clk.mark(0);                                //        all-reduced | 6 small algebra + 2 eigensolves | 7 extension
+    static thread_local EigWorkspace ws;        // grow-only, reused by every training call of this thread
+    ws.phase_reset();
+    const int fallbacks0 = g_eig_fallbacks;
     // V is the one large, long-lived buffer (nloc x k doubles, k <= nEig).  Take it from the pool BEFORE the
     // temporaries so that the block a previous filter released is reused for it instead of being carved up
     // (a fresh 400 MB mapping costs ~1 s on this driver).
@@ -273,33 +337,25 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     TmpBuf<double> Ka((size_t)p * p), U((size_t)p * p), lam(p);
     TmpBuf<int> d_cnt(4);
     launch_ka(p, nC, d_selrows.p, d_selcols.p, Ysel.p, hx, hy, Ka.p, s);
-    f->times_ms[0] = t_setup.stop();
+    clk.mark(1);
     tr("setup tables Ka");
-    Timer t_eig1(s);
-    static thread_local EigWorkspace ws;   // grow-only, reused by every training call of this thread
     f->eig_sweeps[0] = sym_eig(Ka.p, p, p, kEps, /*psd_hint=*/true, U.p, lam.p, d_cnt.p, ws, s, /*vec_limit=*/p);
     const int r = read_int(d_cnt.p, s);
-    f->times_ms[1] = t_eig1.stop();
+    clk.mark(2);
     tr("eig Ka");
     f->r = r;
     if (r < 1) throw Unsupported{"Ka has no eigenvalue >= 1e-10"};
 
     // ---- Sinkhorn on the factors (filter.cpp:230-245)
-    Timer t_sink(s);
     TmpBuf<double> inv_lam(p), xsel(p), ysel(p), svec(p), tvec(p), t2(p), wvec(p), lt(p);
     TmpBuf<double> xfull((size_t)nloc), cfull((size_t)nloc);
-    // Default: level-table GEMM form (sinkhorn_cells.cu).  NLE_B200_SINKHORN=rows (or a grid too wide for its
-    // shared-memory tables) selects the per-row kernels of filter_kernels.cu (same result up to FP64 re-association).
-    static const bool sk_rows_env = [] { const char* e = getenv("NLE_B200_SINKHORN"); return e && std::string(e) == "rows"; }();
-    const bool sk_cells = !sk_rows_env && sinkhorn_cells_supported(tb);
-    TmpBuf<double> spart(sk_cells ? 1 : ((size_t)nrows + cdiv(nrows, 32) + 1) * p);
-    TmpBuf<double> skscratch(sk_cells ? sinkhorn_cells_scratch_doubles(tb) : 1);
-    TmpBuf<double> ciscratch(sk_cells ? cell_index_scratch_doubles(tb) : 1);
-    CellIndex cidx{};
-    if (sk_cells) {
-        cidx = build_cell_index(tb, ciscratch.p, s);
-        sinkhorn_cells_prepare(tb, skscratch.p, s);
-    }
+    // level-table GEMM form over the (image row, luminance level) cell index (sinkhorn_cells.cu)
+    if (!sinkhorn_cells_supported(tb))
+        throw Unsupported{"sample grid too wide for the Sinkhorn level tables (nColSamples=" + std::to_string(nC) + ", nRowSamples=" + std::to_string(nR) + ")"};
+    TmpBuf<double> skscratch(sinkhorn_cells_scratch_doubles(tb));
+    TmpBuf<double> ciscratch(cell_index_scratch_doubles(tb));
+    CellIndex cidx = build_cell_index(tb, ciscratch.p, s);
+    sinkhorn_cells_prepare(tb, skscratch.p, s);
     copy_dd(inv_lam.p, lam.p, p, s);
     guarded_reciprocal(inv_lam.p, r, kEps, s);            // filter.cpp:265-266
     // t = phi^T x = U_r^T x_sel + Lam^-1 U_r^T (Kab x_rest)
@@ -311,19 +367,12 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         // w = U_r t (rest pixels: k_j^T w) and, for the samples, recip(U[s,:] Lam t) in one pass over U
         sk_sample_step(p, r, U.p, p, tvec.p, lam.p, kEps, wvec.p, x_sel_out, s);
         if (need_rest) {
-            if (sk_cells) launch_sinkhorn_cells(tb, &cidx, wvec.p, xfull.p, skscratch.p, svec.p, s);
-            else launch_pass_fused(tb, wvec.p, xfull.p, spart.p, svec.p, s);
+            launch_sinkhorn_cells(tb, &cidx, wvec.p, xfull.p, skscratch.p, svec.p, s);
             do_allreduce(f.get(), svec.p, p);
         }
     };
     // initial r = 1 : s0 = Kab 1
-    if (sk_cells) {
-        launch_sinkhorn_cells(tb, &cidx, nullptr, xfull.p, skscratch.p, svec.p, s);
-    } else {
-        launch_fill(xfull.p, nloc, 1.0, s);
-        launch_mask_samples(tb, xfull.p, s);
-        launch_pass_reduce(tb, xfull.p, spart.p, svec.p, s);
-    }
+    launch_sinkhorn_cells(tb, &cidx, nullptr, xfull.p, skscratch.p, svec.p, s);
     do_allreduce(f.get(), svec.p, p);
     launch_fill(xsel.p, p, 1.0, s);
     phiT_x(xsel.p, svec.p);
@@ -336,25 +385,21 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         half_step(rsel.p, !last);                          // r = recip(K~ c)          (:243-244)
         if (!last) phiT_x(rsel.p, svec.p);                 // the final r is only used on perm[0:r]
     }
-    f->times_ms[2] = t_sink.stop();
+    clk.mark(3);
     tr("sinkhorn");
 
     // ---- Gram of the rest pixels (filter.cpp:296 "Wab * Wab^T" in factor form, App. A.5)
-    Timer t_gram(s);
     TmpBuf<double> Gp((size_t)p * p);
     {
-        TmpBuf<double> gscratch(gram_scratch_doubles(tb));
-        Timer t_gk(s);
-        launch_gram(tb, cfull.p, gscratch.p, Gp.p, s);
-        f->times_ms[7] = t_gk.stop();                       // gram_kernel + its partial-tile reduce only
+        TmpBuf<double> gscratch(gram_cells_scratch_doubles(tb));
+        launch_gram_cells(tb, cfull.p, gscratch.p, Gp.p, s);
+        clk.mark(4);                                        // cell sort + histograms + gram_cells_kernel + reduce
         do_allreduce(f.get(), Gp.p, (size_t)p * p);
-        NLE_CUDA(cudaStreamSynchronize(s));
     }
-    f->times_ms[3] = t_gram.stop();
+    clk.mark(5);
     tr("gram");
 
     // ---- small algebra: Wa, Wab Wab^T, orthogonalisation (filter.cpp:247-250, 282-327)
-    Timer t_small(s);
     // phi_top = U[0:r,0:r] (the first r samples are the "landmarks", filter.cpp:247)
     TmpBuf<double> Lm((size_t)r * r), Ct((size_t)r * r), Wa((size_t)r * r), Bm((size_t)r * p),
         T1((size_t)r * p), WW((size_t)r * r);
@@ -420,11 +465,10 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     dgemm(false, false, r, k, r2, 1.0, Ua.p, r, Zq.p, r2, 0.0, Vq.p, r, s);          // eigenvectors of Q: U+ z
     scale_rows_cols(r, k, Vq.p, r, nullptr, irs.p, VqS.p, r, s);
     dgemm(false, false, r, k, r, 1.0, irw.p, r, VqS.p, r, 0.0, Mv.p, r, s);
-    f->times_ms[4] = t_small.stop();
+    clk.mark(6);
     tr("small: Mv");
 
     // ---- extension V = [Wa ; Wab^T] invRootWa Vq Sq^-1/2 (:324-327) and un-permute (:502)
-    Timer t_ext(s);
     TmpBuf<double> Vtop((size_t)r * k), Zr((size_t)r * k), RM((size_t)r * k), Y1((size_t)r * k),
         Y((size_t)p * k);
     dgemm(false, false, r, k, r, 1.0, Wa.p, r, Mv.p, r, 0.0, Vtop.p, r, s);          // rows of Wa
@@ -436,23 +480,24 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
         dgemm(false, false, nd, k, r, 1.0, U.p + r, p, Zr.p, r, 0.0, Vd.p, nd, s);
         scale_rows_cols(nd, k, Vd.p, nd, csel.p + r, nullptr, Vd.p, nd, s);
         launch_scatter_rows(tb, d_sel.p, r, nd, Vd.p, nd, k, f->V.p, s);
-        NLE_CUDA(cudaStreamSynchronize(s));
     }
     // Y = U_r (phi_top^T diag(rvec) Mv)   (p x k); rest pixels: V_j = c_j k_j^T Y
     scale_rows_cols(r, k, Mv.p, r, rsel.p, nullptr, RM.p, r, s);
     dgemm(true, false, r, k, r, 1.0, U.p, p, RM.p, r, 0.0, Y1.p, r, s);
     dgemm(false, false, p, k, r, 1.0, U.p, p, Y1.p, r, 0.0, Y.p, p, s);
-    static const bool ext_pixel_env = [] { const char* e = getenv("NLE_B200_EXT"); return e && std::string(e) == "pixel"; }();
-    if (ext_pixel_env) {
-        launch_extension(tb, cfull.p, Y.p, k, f->V.p, s);
-    } else {
+    {
         TmpBuf<double> xscratch(extension_cells_scratch_doubles(tb, k));
         launch_extension_cells(tb, cfull.p, Y.p, k, xscratch.p, f->V.p, s);
     }
+    clk.mark(7);
     NLE_CUDA(cudaStreamSynchronize(s));
-    f->times_ms[5] = t_ext.stop();
     tr("extension");
-    f->times_ms[6] = t_total.stop();
+    // per-stage device milliseconds (NLE_B200_STAGE_TIMES_MS); [8..10] = the three eigensolves split by phase
+    f->times_ms[0] = clk.ms(0, 1); f->times_ms[1] = clk.ms(1, 2); f->times_ms[2] = clk.ms(2, 3);
+    f->times_ms[3] = clk.ms(3, 5); f->times_ms[4] = clk.ms(5, 6); f->times_ms[5] = clk.ms(6, 7);
+    f->times_ms[6] = clk.ms(0, 7); f->times_ms[7] = clk.ms(3, 4);
+    ws.phase_ms(&f->times_ms[8]);           // tridiagonalisation, divide & conquer, back-transformation (sums)
+    f->eig_fallbacks = g_eig_fallbacks - fallbacks0;
 
     f->ascratch.alloc((size_t)apply_blocks(nloc) * k + 16);
     f->avec.alloc(4 * (size_t)k + 16);
@@ -668,7 +713,8 @@ int nle_b200_compute_kernel(const double* channel, int rows, int cols, int nRowS
             Y.upload(eye.data(), (size_t)p * p, s);
             launch_fill(ones.p, N, 1.0, s);
             Vd.zero(s);
-            launch_extension(tb, ones.p, Y.p, p, Vd.p, s);
+            DevBuf<double> xs(extension_cells_scratch_doubles(tb, p));
+            launch_extension_cells(tb, ones.p, Y.p, p, xs.p, Vd.p, s);
             std::vector<double> Vh((size_t)N * p);
             Vd.download(Vh.data(), (size_t)N * p, s);
             NLE_CUDA(cudaStreamSynchronize(s));
@@ -870,6 +916,7 @@ int nle_b200_filter_info(const nle_b200_filter* f, nle_b200_info* info) {
         info->p = f->p; info->r = f->r; info->r2 = f->r2; info->k = f->k;
         info->n_row_samples_eff = f->nR; info->n_col_samples_eff = f->nC;
         for (int i = 0; i < 3; ++i) info->eig_sweeps[i] = f->eig_sweeps[i];
+        info->eig_fallbacks = f->eig_fallbacks;
     });
 }
 
@@ -892,9 +939,10 @@ int nle_b200_eigenvectors(const nle_b200_filter* f, double* V) {
     });
 }
 
-int nle_b200_apply(const nle_b200_filter* f, const double* channel, const double* fS, double* out) {
+int nle_b200_apply(const nle_b200_filter* f, const double* channel, long long n_values, const double* fS, double* out) {
     return guarded([&] {
         if (!f || !channel || !fS || !out) throw InvalidArg{"null pointer"};
+        if (n_values != f->nloc) throw InvalidArg{"Number of values in channel must match that of training image."};   // filter.cpp:447-449
         auto* ff = const_cast<nle_b200_filter*>(f);
         const size_t n = (size_t)f->nloc;
         if (ff->io64_in.n < n) { ff->io64_in.alloc(n); ff->io64_out.alloc(n); }
@@ -994,10 +1042,13 @@ int nle_b200_train_bgr_u8(const uint8_t* bgr, int rows, int cols, int row0, int 
     });
 }
 
-int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, const double* weights, int m,
-                            uint8_t* out_slab) {
+int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, int rows, int cols, int channels,
+                            const double* weights, int m, uint8_t* out_slab) {
     return guarded([&] {
         if (!f || !bgr_slab || !weights || !out_slab) throw InvalidArg{"null pointer"};
+        if (channels != 3) throw InvalidArg{"Can only enhance RGB image."};                                      // filter.cpp:414-416
+        if ((long long)rows * cols != f->nloc)                                                                   // filter.cpp:418-420
+            throw InvalidArg{"Cannot apply filter on image with different size from the image filter was trained on."};
         if (m < 1) throw InvalidArg{"at least one weight is required"};
         auto* ff = const_cast<nle_b200_filter*>(f);
         const size_t n = (size_t)f->nloc;
@@ -1013,9 +1064,12 @@ int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, c
     });
 }
 
-int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, double kpow, uint8_t* out) {
+int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, int rows, int cols, double kpow,
+                                uint8_t* out) {
     return guarded([&] {
         if (!f || !chan || !out) throw InvalidArg{"null pointer"};
+        if ((long long)rows * cols != f->nloc)                                                                   // filter.cpp:355-357
+            throw InvalidArg{"Cannot apply filter on image with different size from the image filter was trained on."};
         auto* ff = const_cast<nle_b200_filter*>(f);
         const size_t n = (size_t)f->nloc;
         if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
@@ -1042,8 +1096,8 @@ int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t 
             case NLE_B200_STAGE_LA: b = &f->la; break;
             case NLE_B200_STAGE_GRAM: b = &f->Gram; break;
             case NLE_B200_STAGE_TIMES_MS: {
-                if (size_out) *size_out = 8;
-                if (out) for (size_t i = 0; i < std::min<size_t>(cap, 8); ++i) out[i] = f->times_ms[i];
+                if (size_out) *size_out = 16;
+                if (out) for (size_t i = 0; i < std::min<size_t>(cap, 16); ++i) out[i] = f->times_ms[i];
                 return;
             }
             default: throw InvalidArg{"unknown stage"};
@@ -1060,8 +1114,26 @@ int nle_b200_get_stage(const nle_b200_filter* f, int which, double* out, size_t 
 void nle_b200_free(nle_b200_filter* f) {
     Trace tr(nullptr);
     struct AtExit { Trace& t; ~AtExit() { t("free"); } } at_exit{tr};
-    if (f && f->V.p && f->V.n >= g_v_cache.n) g_v_cache = std::move(f->V);
+    if (f && f->V.p && f->V.n >= g_v_cache.n && f->device == current_device()) {
+        g_v_cache = std::move(f->V);
+        g_v_cache_dev = f->device;
+    }
     delete f;
+}
+
+double nle_b200_fp64_dmma_peak_tflops(void) {
+    double out = 0.0;
+    guarded([&] {
+        require_device();
+        out = nle::measure_dmma_peak_tflops();
+    });
+    return out;
+}
+
+void nle_b200_release_cache(void) {
+    g_v_cache.release();
+    g_v_cache_dev = -1;
+    thread_arena().release_all();
 }
 
 double nle_b200_fp64_fma_peak_tflops(void) {

@@ -651,11 +651,7 @@ void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch
     const size_t hsm = (size_t)2 * HS * t.nC * sizeof(double) + (size_t)(256 * 3 + 260 + 8 + t.cols) * sizeof(int) +
                        2 * (size_t)((t.cols + 15) / 16) * 16 + 64;
     if (hsm > 227 * 1024) throw Unsupported{"gram: image too wide for the per-row cell sort (cols=" + std::to_string(t.cols) + ")"};
-    static size_t configured = 0;
-    if (hsm > configured) {
-        NLE_CUDA(cudaFuncSetAttribute(cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
-        configured = hsm;
-    }
+    NLE_CUDA(cudaFuncSetAttribute(cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
     for (int r0 = 0, batch = 0; r0 < t.nrows; r0 += g.rows_batch, ++batch) {
         AffinityTables tb = t;
         tb.row0 = t.row0 + r0;
@@ -689,7 +685,7 @@ size_t extension_cells_scratch_doubles(const AffinityTables& t, int k) {
     return g.fx_doubles + g.yt_doubles + (g.lev_bytes + 7) / 8 + (g.int_count * 4 + 7) / 8 + 16;
 }
 
-// V_j = c_j k_j^T Y for the non-sample slab pixels (same contract as launch_extension).
+// V_j = c_j k_j^T Y for the non-sample slab pixels (contract in kernels.cuh).
 void launch_extension_cells(const AffinityTables& t, const double* c, const double* Y, int k, double* scratch, double* V,
                             cudaStream_t s) {
     if (k <= 0 || t.nrows <= 0) return;
@@ -710,9 +706,8 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
     const int nR4 = (t.nR + 3) & ~3;
     const size_t fsm = ((size_t)nR4 * XC_N + 256 + (size_t)XC_ERROWS * nR4) * sizeof(double) + (size_t)(nR4 + 2) * sizeof(int) + 16;
     if (ism > 227 * 1024 || fsm > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
-    static size_t conf_i = 0, conf_f = 0;
-    if (ism > conf_i) { NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism)); conf_i = ism; }
-    if (fsm > conf_f) { NLE_CUDA(cudaFuncSetAttribute(ext_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm)); conf_f = fsm; }
+    NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+    NLE_CUDA(cudaFuncSetAttribute(ext_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
     for (int r0 = 0; r0 < t.nrows; r0 += g.rows_batch) {
         AffinityTables tb = t;
         tb.row0 = t.row0 + r0;
@@ -761,8 +756,7 @@ CellIndex build_cell_index(const AffinityTables& t, double* scratch, cudaStream_
     int* sorted = cell_pcount + cells;
     const size_t ism = (size_t)(256 * 3 + 260 + 8) * sizeof(int) + ((t.cols + 15) / 16) * 16 + 16;
     if (ism > 227 * 1024) throw Unsupported{"cell index: image too wide (cols=" + std::to_string(t.cols) + ")"};
-    static size_t conf = 0;
-    if (ism > conf) { NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism)); conf = ism; }
+    NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
     cell_count_kernel<<<std::min(t.nrows, sm_count() * 8), 256, 0, s>>>(t.lum, t.nrows, t.cols, cnt);
     NLE_LAUNCH_CHECK();
     cell_scan_kernel<<<1, 1024, 0, s>>>(cnt, t.nrows, koff);

@@ -12,6 +12,7 @@ constexpr double kEps = 1e-10;  // nle::EPS, include/filter.hpp:14 of the refere
 
 void set_error(const std::string& msg);
 extern thread_local long long g_launches;  // kernels launched by this library on this thread
+extern thread_local int g_eig_fallbacks;   // direct eigensolver -> block-Jacobi fallbacks on this thread (eig.cu)
 
 struct CudaError {
     cudaError_t e;
@@ -163,6 +164,16 @@ struct EigWorkspace {
     int max_inner = 2;                                  // inner Jacobi sweeps per block-pair visit
     int cap = 0;
     void reserve(int n);
+    // Phase marks of the direct solver (eig_dc.cu): between phase_reset() and phase_ms() every solve records four
+    // events (start | tridiagonalised | divide & conquer done | back-transformed) WITHOUT synchronising; phase_ms adds
+    // the three spans up over all solves since the reset (call it after the stream has been synchronised).
+    std::vector<cudaEvent_t> pev;
+    int pev_used = 0;
+    bool phase_on = false;
+    void phase_reset() { pev_used = 0; phase_on = true; }
+    void phase_mark(cudaStream_t s);
+    void phase_ms(double out[3]);
+    ~EigWorkspace();
 };
 // Eigen-decomposition of the symmetric matrix defined by the LOWER triangle of M (n x n, ld ldm).
 // U (n x n, ld n) receives eigenvectors sorted by descending eigenvalue, D (n) the eigenvalues;

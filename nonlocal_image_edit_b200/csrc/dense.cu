@@ -75,12 +75,15 @@ Arena& thread_arena() {
 }
 
 int sm_count() {
-    static int n = 0;
+    static int cached[64] = {0};      // per device (a process may drive several GPUs, one per thread)
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int n = cached[dev];
     if (!n) {
-        int dev = 0;
-        cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
         if (n <= 0) n = 148;
+        cached[dev] = n;
     }
     return n;
 }

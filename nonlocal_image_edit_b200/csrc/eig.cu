@@ -441,6 +441,8 @@ static int sym_eig_once(const double* M, int ldm, int n, double eps, bool psd_hi
 // Tries the small (accurate) shift first -- valid whenever sym(M) is positive semi-definite up to
 // rounding, which holds for Ka, Wa and Q of the filter -- and falls back to the Gershgorin shift for
 // genuinely indefinite input (only the reference's unit tests feed such matrices).
+thread_local int g_eig_fallbacks = 0;
+
 static bool use_jacobi() {
     static int mode = -1;
     if (mode < 0) {
@@ -475,6 +477,10 @@ int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* 
     if (n > 0 && !use_jacobi()) {
         if (sym_eig_direct(M, ldm, n, eps, U, D, d_r, ws, s, vec_limit)) return 0;
         if (getenv("NLE_B200_EIG_STRICT")) throw NoConvergence{"eigensolver: direct solver failed its sanity check (n=" + std::to_string(n) + ")"};
+        // never silent: the block-Jacobi solver below is ~10x slower.  nle_b200_info.eig_fallbacks counts these.
+        ++g_eig_fallbacks;
+        fprintf(stderr, "[libnle_b200] warning: direct eigensolver (tridiagonalisation + divide & conquer) failed its device-side "
+                        "sanity check at n=%d; falling back to block Jacobi (about 10x slower)\n", n);
     }
     bool ok = true;
     int sweeps = sym_eig_once(M, ldm, n, eps, true, U, D, d_r, ws, s, &ok);

@@ -11,9 +11,12 @@
 //                         grid.sync per Householder step: the rank-2 update of step j is fused with
 //                         the symmetric matrix-vector product of step j+1 (the next reflector is
 //                         derived redundantly by every CTA from the updated column j+1).
-//   tridiag_resident_kernel  experiment (NLE_B200_TRD=resident): same arithmetic, trailing matrix resident in
-//                         shared memory, flagged-cell exchange instead of grid.sync; carries the per-phase
-//                         cycle counters behind profiles/r1l_trd_phases.md.
+//   tridiag_cluster_kernel   the default for 64 <= n <= 2048: same arithmetic in the same order (bit-identical d, e,
+//                         tau, reflectors), trailing matrix resident in shared memory, flagged-cell exchange instead
+//                         of grid.sync, thread-block clusters of 2 CTAs share the polling through distributed shared
+//                         memory (profiles/r2a_trd_sweep.md: 14-19 % faster than tridiag_kernel at n = 612...1600).
+//                         tridiag_kernel remains the general path (n > 2048: the matrix no longer fits in the
+//                         shared memory of 148 SMs) and the cross-check of tests/test_gpu_eig_variants.py.
 //   dc_leaf_kernel        implicit-shift QL on leaves of <= 32 rows, one warp per leaf.
 //   dc_setup_kernel       per merge: z vector, rank sort, LAPACK dlaed2-style deflation.
 //   dc_rotate_kernel      applies the deflation Givens rotations to the eigenvector columns.
@@ -82,16 +85,9 @@ __device__ __forceinline__ double block_sum(double v, double* red /*>= 2*kTrdWar
 // triangles, column-major).  On exit: d (n), e (n-1), tau (n-1); reflector j (H_j = I - tau_j v v^T,
 // v[j+1] = 1) is stored in A(j+1:n, j) including the explicit 1.
 //
-// DYN (NLE_B200_TRD_DYN=<cols>, developer experiment, off by default): the trailing columns are dealt to only
-// Geff(j) = min(G, ceil(#trailing columns / cols)) CTAs; the others just keep arriving at the grid barrier.  The
-// matrix lives in global memory and every step ends in grid.sync, so ownership may change from step to step, and a
-// column's arithmetic does not depend on which CTA performs it: the result is bit-identical for every `cols`.
-// Motivation: the cost of a step grows with the number of CTAs that read p and the next column
-// (profiles/r1l_trd_phases.md).
-template <bool DYN>
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
-               double* __restrict__ tau, double* __restrict__ pbuf, int dyn_cols) {
+               double* __restrict__ tau, double* __restrict__ pbuf) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];
     double* v = sm;            // current reflector, global row indexing
@@ -159,14 +155,6 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
     }
 
     for (int j = 0; j <= n - 3; ++j) {
-        int Ge = G;       // CTAs that own trailing columns in this step
-        if (DYN) {
-            Ge = min(G, max(1, (n - (j + 2) + dyn_cols - 1) / dyn_cols));
-            if (b >= Ge) {            // Ge never grows again: this CTA only keeps the barrier complete
-                grid.sync();
-                continue;
-            }
-        }
         const double* p = pbuf + (size_t)(j & 1) * n;
         double* pn = pbuf + (size_t)((j + 1) & 1) * n;
         // (0) publish reflector j (column j of A is no longer read by anybody in this kernel)
@@ -208,7 +196,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
         // (3) rank-2 update of the owned columns c >= j+2 fused with the next symv
         const bool has_next = (j + 1 <= n - 3);
         for (int q = warp; ; q += kTrdWarps) {
-            const int c = b + Ge * q;
+            const int c = b + G * q;
             if (c >= n) break;
             if (c < j + 2) continue;
             double* col = A + (size_t)c * lda;
@@ -266,10 +254,9 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 }
 
 // ---------------------------------------------------------------------------------------------
-// Shared-memory-resident variant of tridiag_kernel (NLE_B200_TRD=resident; experiment, off by default: measured
-// bit-identical to and within 3 % of tridiag_kernel -- see DESIGN.md section 6).  Same arithmetic in the same order as
-// tridiag_kernel (d, e, tau and the reflectors come out bit-identical); what changes is where the data
-// lives and how the CTAs synchronise:
+// Shared-memory-resident tridiagonalisation (tridiag_cluster_kernel below).  Same arithmetic in the same order as
+// tridiag_kernel (d, e, tau and the reflectors come out bit-identical); what changes is where the data lives and how
+// the CTAs synchronise:
 //   * CTA b keeps its columns c = b, b+G, ... of the trailing matrix in shared memory for the whole
 //     factorisation (n = 1600 on 148 SMs: 11 columns x 12.8 KB), so the rank-2 update + symv pass of a
 //     step makes no global loads or stores at all;
@@ -278,35 +265,25 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 //     written atomically together with its tag; the low-latency protocol NCCL calls LL): the consumer
 //     polls the cells themselves, so one L2 write + one L2 read replace the store-acknowledge fence,
 //     the barrier atomic, the barrier poll and the separate p / column loads of the grid.sync version;
-//   * cells are double-buffered by the parity of the tag; a CTA leaves the kernel as soon as it owns no
+//   * cells are double-buffered by the parity of the tag; a cluster leaves the kernel as soon as it owns no
 //     column of the trailing matrix any more, so the CTAs that still exchange data are never more than
 //     one step apart (each waits for cells written by all the others), which is what makes two buffers
 //     enough.  The CTA that owns column n-1 lives to the end and writes d, e, tau and the reflectors.
+constexpr unsigned kTrdSpinLimit = 1u << 21;   // poll rounds (~1 us each) before a waiting CTA gives up
 constexpr int kResPer = 4;   // exchange cells per thread and vector: n <= kResPer * kTrdThreads
 
-// sys = false: relaxed, gpu scope, two 8-byte elements {tag:lo, tag:hi}; sys = true: the volatile (= relaxed.sys)
-// 4 x u32 form NCCL uses.  Same bytes in memory; NLE_B200_TRD_LL=sys selects the latter for A/B timing.
-__device__ __forceinline__ void ll_store(uint4* cell, double x, unsigned tag, bool sys) {
+// relaxed, gpu scope, two 8-byte elements {tag:lo, tag:hi} (the volatile 4 x u32 form NCCL uses measured the same)
+__device__ __forceinline__ void ll_store(uint4* cell, double x, unsigned tag) {
     const unsigned long long bits = (unsigned long long)__double_as_longlong(x);
-    if (sys) {
-        asm volatile("st.volatile.global.v4.u32 [%0], {%1, %2, %3, %4};" ::"l"(cell), "r"((unsigned)bits), "r"(tag),
-                     "r"((unsigned)(bits >> 32)), "r"(tag)
-                     : "memory");
-    } else {
-        const unsigned long long t = (unsigned long long)tag << 32;
-        asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(t | (bits & 0xffffffffull)), "l"(t | (bits >> 32))
-                     : "memory");
-    }
+    const unsigned long long t = (unsigned long long)tag << 32;
+    asm volatile("st.relaxed.gpu.global.v2.u64 [%0], {%1, %2};" ::"l"(cell), "l"(t | (bits & 0xffffffffull)), "l"(t | (bits >> 32))
+                 : "memory");
 }
-__device__ __forceinline__ uint4 ll_load(const uint4* cell, bool sys) {
+__device__ __forceinline__ uint4 ll_load(const uint4* cell) {
     uint4 r;
-    if (sys) {
-        asm volatile("ld.volatile.global.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(cell) : "memory");
-    } else {
-        unsigned long long a, b;
-        asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(cell) : "memory");
-        r.x = (unsigned)a; r.y = (unsigned)(a >> 32); r.z = (unsigned)b; r.w = (unsigned)(b >> 32);
-    }
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(cell) : "memory");
+    r.x = (unsigned)a; r.y = (unsigned)(a >> 32); r.z = (unsigned)b; r.w = (unsigned)(b >> 32);
     return r;
 }
 __device__ __forceinline__ double ll_value(const uint4& c) {
@@ -330,242 +307,16 @@ __device__ __forceinline__ long long clock_after(double dep) {
         }                                                              \
     } while (0)
 
-template <bool PROF>
-__global__ void __launch_bounds__(kTrdThreads, 1)
-tridiag_resident_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
-                        double* __restrict__ tau, uint4* __restrict__ ll /* 4n cells, zeroed before the launch */,
-                        long long* __restrict__ prof /* 16 counters when PROF */, int ll_sys) {
-    extern __shared__ double sm[];
-    double* v = sm;            // current reflector, global row indexing
-    double* w = sm + n;
-    double* cn = sm + 2 * (size_t)n;   // updated next column -> next reflector
-    double* red = sm + 3 * (size_t)n;  // 2*kTrdWarps
-    double* cols = red + 2 * kTrdWarps;   // owned columns, slot q holds column b + G*q (all n rows)
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int G = gridDim.x, b = blockIdx.x;
-    const int q_last = (n - 1 - b) / G;          // b < G <= n
-    const int c_last = b + G * q_last;           // the largest column this CTA owns
-    const bool writer = (c_last == n - 1);
-    const bool sys = ll_sys != 0;
-    int phase = 0;
-    long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    long long tprev = 0, rounds = 0;
-    // cells of tag t: p at ll + (t&1)*2n, next column at ll + (t&1)*2n + n
-    auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n; };
-    auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n + n; };
-
-    auto make_reflector = [&](int j0, double& tau_out) -> double {     // identical to tridiag_kernel's
-        const double alpha = cn[j0 + 1];
-        double part = 0.0;
-        for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
-        const double xn2 = block_sum(part, red, phase);
-        TRD_STAMP(4, xn2);
-        double beta;
-        if (xn2 == 0.0) {
-            tau_out = 0.0;
-            beta = alpha;
-            __syncthreads();
-            if (tid == 0) cn[j0 + 1] = 1.0;
-        } else {
-            beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
-            tau_out = (beta - alpha) / beta;
-            const double scal = 1.0 / (alpha - beta);
-            TRD_STAMP(5, scal + tau_out);
-            __syncthreads();
-            for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) cn[i] *= scal;
-            if (tid == 0) cn[j0 + 1] = 1.0;
-        }
-        __syncthreads();
-        return beta;
-    };
-
-    // owned columns -> shared memory; column 0 -> first reflector (every CTA, redundantly)
-    for (int q = 0; q <= q_last; ++q) {
-        const double* src = A + (size_t)(b + G * q) * lda;
-        double* dst = cols + (size_t)q * n;
-        for (int i = tid; i < n; i += kTrdThreads) dst[i] = src[i];
-    }
-    for (int i = tid; i < n; i += kTrdThreads) cn[i] = A[i];
-    __syncthreads();
-    double tau_j, beta_j, diag_j;
-    diag_j = cn[0];
-    beta_j = make_reflector(0, tau_j);
-    { double* t = v; v = cn; cn = t; }
-    // p = A v over the owned columns c >= 1 (tag 1); the owner of column 1 also publishes that column
-    for (int q = warp; q <= q_last; q += kTrdWarps) {
-        const int c = b + G * q;
-        if (c < 1) continue;
-        const double* col = cols + (size_t)q * n;
-        double acc = 0.0;
-        for (int i = 1 + lane; i < n; i += 32) acc = fma(col[i], v[i], acc);
-        acc = warp_sum(acc);
-        if (lane == 0) ll_store(pcell(1) + c, acc, 1u, sys);
-        if (c == 1)
-            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u, sys);
-    }
-    if (PROF && tid == 0) {
-        tprev = clock64();
-#pragma unroll
-        for (int k = 0; k < 10; ++k) pacc[k] = 0;
-    }
-
-    for (int j = 0; j <= n - 3; ++j) {
-        if (c_last < j + 2) return;       // nothing left to update here and nobody waits for this CTA (block-uniform)
-        const unsigned T = (unsigned)(j + 1);
-        const bool has_next = (j + 1 <= n - 3);
-        double diag_next, tau_next = 0.0, beta_next;
-        // (1) wait for p and column j+1 (rows j+1..n-1), all loads of a round in flight together
-        uint4 P[kResPer], C[kResPer];
-        {
-            const uint4* pc = pcell(T);
-            const uint4* cc = ccell(T);
-            // bit u: p cell u still missing, bit kResPer+u: column cell u still missing; a retry round re-reads only
-            // the missing cells (every read of a cell line competes with the store that is to fill it)
-            unsigned pend = 0;
-#pragma unroll
-            for (int u = 0; u < kResPer; ++u)
-                if (j + 1 + tid + u * kTrdThreads < n) pend |= (1u | (1u << kResPer)) << u;
-            while (pend) {
-#pragma unroll
-                for (int u = 0; u < kResPer; ++u) {
-                    const int i = j + 1 + tid + u * kTrdThreads;
-                    if (pend & (1u << u)) P[u] = ll_load(pc + i, sys);
-                    if (pend & (1u << (kResPer + u))) C[u] = ll_load(cc + i, sys);
-                }
-#pragma unroll
-                for (int u = 0; u < kResPer; ++u) {
-                    if ((pend & (1u << u)) && P[u].y == T && P[u].w == T) pend &= ~(1u << u);
-                    if ((pend & (1u << (kResPer + u))) && C[u].y == T && C[u].w == T) pend &= ~(1u << (kResPer + u));
-                }
-                if (PROF) ++rounds;
-            }
-        }
-        TRD_STAMP(0, ll_value(P[0]));
-        double part = 0.0;
-#pragma unroll
-        for (int u = 0; u < kResPer; ++u) {
-            const int i = j + 1 + tid + u * kTrdThreads;
-            if (i < n) {
-                const double pi = ll_value(P[u]);
-                w[i] = pi;
-                cn[i] = ll_value(C[u]);
-                part = fma(pi, v[i], part);
-            }
-        }
-        // w = tau*p - (tau^2/2)(p.v) v
-        const double dot = block_sum(part, red, phase);
-        TRD_STAMP(1, dot);
-        const double kappa = 0.5 * tau_j * tau_j * dot;
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
-        __syncthreads();
-        // (2) updated column j+1 -> next diagonal and next reflector
-        const double wj1 = w[j + 1];   // v[j+1] == 1
-        TRD_STAMP(2, wj1);
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
-        __syncthreads();
-        diag_next = cn[j + 1];
-        TRD_STAMP(3, diag_next);
-        if (has_next) {
-            beta_next = make_reflector(j + 1, tau_next);     // stamps 4, 5
-        } else {
-            beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
-        }
-        TRD_STAMP(6, beta_next);
-        // (3) rank-2 update of the owned columns c >= j+2 (in shared memory) fused with the next symv;
-        //     the owner of column j+2 publishes the updated column as it goes
-        const unsigned Tn = (unsigned)(j + 2);
-        for (int q = warp; q <= q_last; q += kTrdWarps) {
-            const int c = b + G * q;
-            if (c < j + 2) continue;
-            double* col = cols + (size_t)q * n;
-            const double wc = w[c], vc = v[c];
-            const bool pub = has_next && c == j + 2;
-            uint4* cc = ccell(Tn);
-            double acc = 0.0;
-            int i = j + 2 + lane;
-            // batches with all shared-memory loads in front: col, w, v, cn are the same address space to the compiler,
-            // so without this every iteration's loads wait behind the previous iteration's store (profiles/
-            // r1l_trd_phases.md: ~140 cycles per 32-row iteration).  Same operations in the same order per lane.
-            for (; i + 3 * 32 < n; i += 4 * 32) {
-                double a[4], wv[4], vv[4], cv[4];
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int ii = i + 32 * u;
-                    a[u] = col[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
-                }
-#pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                    const int ii = i + 32 * u;
-                    a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
-                    acc = fma(a[u], cv[u], acc);
-                    col[ii] = a[u];
-                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
-                }
-            }
-            for (; i + 32 < n; i += 2 * 32) {
-                double a[2], wv[2], vv[2], cv[2];
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int ii = i + 32 * u;
-                    a[u] = col[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
-                }
-#pragma unroll
-                for (int u = 0; u < 2; ++u) {
-                    const int ii = i + 32 * u;
-                    a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
-                    acc = fma(a[u], cv[u], acc);
-                    col[ii] = a[u];
-                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
-                }
-            }
-            for (; i < n; i += 32) {
-                double a = col[i];
-                a = fma(-w[i], vc, fma(-v[i], wc, a));
-                acc = fma(a, cn[i], acc);
-                col[i] = a;
-                if (pub) ll_store(cc + i, a, Tn, sys);
-            }
-            if (has_next) {
-                acc = warp_sum(acc);
-                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn, sys);
-            }
-        }
-        TRD_STAMP(7, 0.0);
-        // (0) reflector j and its scalars (off the critical path: nobody in this kernel reads them back)
-        if (writer) {
-            double* colj = A + (size_t)j * lda;
-            for (int i = j + 1 + tid; i < n; i += kTrdThreads) colj[i] = v[i];
-            if (tid == 0) { d[j] = diag_j; e[j] = beta_j; tau[j] = tau_j; }
-        }
-        diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
-        { double* t = v; v = cn; cn = t; }
-        __syncthreads();   // w and the old v are overwritten by the next step's (1)
-        TRD_STAMP(8, v[j + 2]);
-    }
-    if (writer && tid == 0) {
-        d[n - 2] = diag_j;
-        e[n - 2] = beta_j;
-        tau[n - 2] = 0.0;
-        d[n - 1] = cols[(size_t)q_last * n + (n - 1)];
-        if (PROF) {
-#pragma unroll
-            for (int k = 0; k < 10; ++k) prof[k] = pacc[k];
-            prof[10] = rounds;
-            prof[11] = n - 2;
-        }
-    }
-}
-// Cluster variant of the resident kernel (NLE_B200_TRD=cluster, NLE_B200_TRD_CLUSTER=<S>; prepared for the next round,
-// NOT yet run on a device).  The resident kernel's counters show the step is bound by 148 CTAs reading every cell
-// (profiles/r1l_trd_phases.md).  Here the CTAs of a thread-block cluster share the polling: CTA `rank` polls every S-th
-// cell and forwards what it receives to its peers through distributed shared memory, one cluster barrier per step makes the
-// vectors complete everywhere.  Readers per cell: G/S.  Everything behind the barrier is the resident kernel's arithmetic
-// in the same order (bit-identical results expected).
+// The step is bound by every CTA reading every cell (profiles/r1l_trd_phases.md), so the CTAs of a thread-block cluster
+// share the polling: CTA `rank` polls every S-th cell and forwards what it receives to its peers through distributed
+// shared memory, one cluster barrier per step makes the vectors complete everywhere.  Readers per cell: G/S.  Measured
+// (profiles/r2a_trd_sweep.md): S = 2 is the optimum (n = 1600: 8.7 ms against 10.2 ms for tridiag_kernel, 10.1 ms for
+// S = 4, where the forwarding and the cluster barrier cost more than the polling saves).
 template <bool PROF>
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
                         double* __restrict__ tau, uint4* __restrict__ ll /* 4n cells, zeroed before the launch */,
-                        long long* __restrict__ prof /* 16 counters when PROF */, int ll_sys) {
+                        long long* __restrict__ prof /* 16 counters when PROF */) {
     cg::cluster_group cluster = cg::this_cluster();
     const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
     extern __shared__ double sm[];
@@ -589,7 +340,6 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
         const int br = b - rank + r;
         cl_last = max(cl_last, br + G * ((n - 1 - br) / G));
     }
-    const bool sys = ll_sys != 0;
     cluster.sync();            // no CTA touches a peer's shared memory before that peer is running
     int phase = 0;
     long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
@@ -643,9 +393,9 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
         double acc = 0.0;
         for (int i = 1 + lane; i < n; i += 32) acc = fma(col[i], v[i], acc);
         acc = warp_sum(acc);
-        if (lane == 0) ll_store(pcell(1) + c, acc, 1u, sys);
+        if (lane == 0) ll_store(pcell(1) + c, acc, 1u);
         if (c == 1)
-            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u, sys);
+            for (int i = 1 + lane; i < n; i += 32) ll_store(ccell(1) + i, col[i], 1u);
     }
     if (PROF && tid == 0) {
         tprev = clock64();
@@ -667,7 +417,7 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
             const uint4* pc = pcell(T);
             const uint4* cc = ccell(T);
             uint4 P[kResPer], C[kResPer];
-            unsigned pend = 0;
+            unsigned pend = 0, spins = 0;
 #pragma unroll
             for (int u = 0; u < kResPer; ++u)
                 if (j + 1 + rank + S * (tid + u * kTrdThreads) < n) pend |= (1u | (1u << kResPer)) << u;
@@ -676,8 +426,8 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
 #pragma unroll
                 for (int u = 0; u < kResPer; ++u) {
                     const int i = j + 1 + rank + S * (tid + u * kTrdThreads);
-                    if (pend & (1u << u)) P[u] = ll_load(pc + i, sys);
-                    if (pend & (1u << (kResPer + u))) C[u] = ll_load(cc + i, sys);
+                    if (pend & (1u << u)) P[u] = ll_load(pc + i);
+                    if (pend & (1u << (kResPer + u))) C[u] = ll_load(cc + i);
                 }
 #pragma unroll
                 for (int u = 0; u < kResPer; ++u) {
@@ -685,6 +435,7 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
                     if ((pend & (1u << (kResPer + u))) && C[u].y == T && C[u].w == T) pend &= ~(1u << (kResPer + u));
                 }
                 if (PROF) ++rounds;
+                if (++spins > kTrdSpinLimit) __trap();   // a lost peer must not hang the device: abort the launch loudly
             }
             TRD_STAMP(0, ll_value(P[0]));
             for (int r = 0; r < S; ++r) {
@@ -748,7 +499,7 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
                     a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
                     acc = fma(a[u], cv[u], acc);
                     col[ii] = a[u];
-                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
+                    if (pub) ll_store(cc + ii, a[u], Tn);
                 }
             }
             for (; i + 32 < n; i += 2 * 32) {
@@ -764,7 +515,7 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
                     a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
                     acc = fma(a[u], cv[u], acc);
                     col[ii] = a[u];
-                    if (pub) ll_store(cc + ii, a[u], Tn, sys);
+                    if (pub) ll_store(cc + ii, a[u], Tn);
                 }
             }
             for (; i < n; i += 32) {
@@ -772,11 +523,11 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
                 a = fma(-w[i], vc, fma(-v[i], wc, a));
                 acc = fma(a, cn[i], acc);
                 col[i] = a;
-                if (pub) ll_store(cc + i, a, Tn, sys);
+                if (pub) ll_store(cc + i, a, Tn);
             }
             if (has_next) {
                 acc = warp_sum(acc);
-                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn, sys);
+                if (lane == 0) ll_store(pcell(Tn) + c, acc, Tn);
             }
         }
         TRD_STAMP(7, 0.0);
@@ -1546,18 +1297,30 @@ __global__ void dc_check_kernel(const double* __restrict__ U, int ldu, int n, in
 
 }  // namespace
 
-// CTAs of the tridiagonalisation kernels: one per SM unless NLE_B200_TRD_GRID caps it (developer knob: the
-// per-step exchange cost grows with the number of CTAs that read every cell, profiles/r1l_trd_phases.md)
-static int trd_grid_limit() {
-    int g = sm_count();
-    if (const char* e = getenv("NLE_B200_TRD_GRID")) {
-        const int v = atoi(e);
-        if (v >= 1 && v < g) g = v;
+// ---------------------------------------------------------------------------------------------
+void EigWorkspace::phase_mark(cudaStream_t s) {
+    if (!phase_on) return;
+    if (pev_used == (int)pev.size()) {
+        cudaEvent_t e;
+        NLE_CUDA(cudaEventCreate(&e));
+        pev.push_back(e);
     }
-    return g;
+    NLE_CUDA(cudaEventRecord(pev[pev_used++], s));
+}
+void EigWorkspace::phase_ms(double out[3]) {
+    out[0] = out[1] = out[2] = 0.0;
+    for (int i = 0; i + 3 < pev_used; i += 4)
+        for (int k = 0; k < 3; ++k) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, pev[i + k], pev[i + k + 1]) == cudaSuccess) out[k] += ms; else cudaGetLastError();
+        }
+    pev_used = 0;
+    phase_on = false;
+}
+EigWorkspace::~EigWorkspace() {
+    for (cudaEvent_t e : pev) cudaEventDestroy(e);
 }
 
-// ---------------------------------------------------------------------------------------------
 void EigWorkspace::reserve_dc(int n) {
     if (n <= dc_cap) return;
     const size_t nn = (size_t)n * n;
@@ -1581,6 +1344,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     const bool prof = getenv("NLE_B200_EIG_PROF") != nullptr;
     auto tnow = [&]() { if (prof) cudaStreamSynchronize(s); return std::chrono::steady_clock::now(); };
     auto t_start = tnow();
+    ws.phase_mark(s);
     double* dd = ws.dcd.p;
     double* d0 = dd;                 // tridiagonal diagonal
     double* e0 = dd + n;             // off-diagonal
@@ -1607,136 +1371,85 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     NLE_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
 
     // ---- 1. tridiagonalisation
-    // NLE_B200_TRD=resident: trailing matrix in shared memory + flagged-cell exchange (see tridiag_resident_kernel);
-    // NLE_B200_TRD_PROF=1 adds the per-phase cycle counts of a step on stderr.
+    // Default for 64 <= n <= 2048: tridiag_cluster_kernel, clusters of 2 CTAs (falls through to tridiag_kernel when the
+    // resident columns do not fit in shared memory or the cluster launch is refused).  NLE_B200_TRD=gridsync forces
+    // tridiag_kernel (the bit-equality cross-check of tests/test_gpu_eig_variants.py); NLE_B200_TRD_PROF=1 prints the
+    // per-phase cycle counts of a step on stderr.
     bool trd_done = false;
-    {
-        const char* env = getenv("NLE_B200_TRD");
-        const std::string mode = env ? env : "";
-        int grid = std::min(trd_grid_limit(), n);
-        if (mode == "cluster" && n >= 64 && n <= kResPer * kTrdThreads) {
-            // thread-block clusters share the polling (tridiag_cluster_kernel; prepared, not yet run on a device)
-            const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
-            int S = 4;
-            if (const char* e = getenv("NLE_B200_TRD_CLUSTER")) S = std::max(1, std::min(16, atoi(e)));
-            int dev = 0, max_smem = 0;
-            NLE_CUDA(cudaGetDevice(&dev));
-            NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-            const void* kfn = kprof ? (const void*)tridiag_cluster_kernel<true> : (const void*)tridiag_cluster_kernel<false>;
-            if (S > 8) NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
-            // the grid depends on how many clusters fit, which depends on the shared memory, which depends on the grid:
-            // start from the cap and shrink until the launch configuration is consistent
-            int G = (std::min(grid, n) / S) * S;
-            for (int it = 0; it < 4 && G >= S; ++it) {
-                const int qmax = cdiv(n, G);
-                const size_t smem = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
-                if (smem > (size_t)max_smem) { G = 0; break; }
-                NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                cudaLaunchConfig_t cfg = {};
-                cfg.gridDim = dim3(G);
-                cfg.blockDim = dim3(kTrdThreads);
-                cfg.dynamicSmemBytes = smem;
-                cfg.stream = s;
-                cudaLaunchAttribute at[2];
-                at[0].id = cudaLaunchAttributeClusterDimension;
-                at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-                at[1].id = cudaLaunchAttributeCooperative;     // only for its co-residency guarantee
-                at[1].val.cooperative = 1;
-                cfg.attrs = at;
-                cfg.numAttrs = 1;
-                int ncl = 0;
-                if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &cfg) != cudaSuccess) { cudaGetLastError(); G = 0; break; }
-                if (ncl * S < G) { G = ncl * S; continue; }      // fewer clusters fit: retry with the smaller grid
-                cfg.numAttrs = 2;
-                const size_t cells = 4 * (size_t)n + 8;
-                if (ws.trdll.n < cells) ws.trdll.alloc(cells);
-                NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));
-                int lda = n;
-                uint4* ll = ws.trdll.p;
-                long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * (size_t)n);
-                const char* lle = getenv("NLE_B200_TRD_LL");
-                int ll_sys = (lle && std::string(lle) == "sys") ? 1 : 0;
-                void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp, &ll_sys};
-                cudaError_t rc = cudaLaunchKernelExC(&cfg, kfn, args);
-                if (rc != cudaSuccess) {                      // cooperative + cluster refused: the grid fits anyway
-                    cudaGetLastError();
-                    cfg.numAttrs = 1;
-                    rc = cudaLaunchKernelExC(&cfg, kfn, args);
-                }
-                NLE_CUDA(rc);
-                ++g_launches;
-                trd_done = true;
-                if (kprof) {
-                    long long h[16];
-                    NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
-                    NLE_CUDA(cudaStreamSynchronize(s));
-                    const double st = (double)std::max(1LL, h[11]);
-                    double tot = 0;
-                    for (int k = 0; k < 10; ++k) tot += (double)h[k];
-                    fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: poll %.0f | forward+cluster.sync %.0f | dot-reduce %.0f | w %.0f | "
-                            "col %.0f | norm-reduce %.0f | sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; "
-                            "poll rounds/step %.2f\n", S, G, n, h[0] / st, h[9] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st,
-                            h[5] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
-                }
-                break;
+    static const bool force_gridsync = [] { const char* e = getenv("NLE_B200_TRD"); return e && std::string(e) == "gridsync"; }();
+    if (!force_gridsync && n >= 64 && n <= kResPer * kTrdThreads) {
+        const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
+        constexpr int S = 2;
+        int dev = 0, max_smem = 0;
+        NLE_CUDA(cudaGetDevice(&dev));
+        NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+        const void* kfn = kprof ? (const void*)tridiag_cluster_kernel<true> : (const void*)tridiag_cluster_kernel<false>;
+        // the grid depends on how many clusters fit, which depends on the shared memory, which depends on the grid:
+        // start from one CTA per SM and shrink until the launch configuration is consistent
+        int G = (std::min(sm_count(), n) / S) * S;
+        for (int it = 0; it < 4 && G >= S; ++it) {
+            const int qmax = cdiv(n, G);
+            const size_t smem = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
+            if (smem > (size_t)max_smem) break;
+            NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3(G);
+            cfg.blockDim = dim3(kTrdThreads);
+            cfg.dynamicSmemBytes = smem;
+            cfg.stream = s;
+            cudaLaunchAttribute at[2];
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            at[1].id = cudaLaunchAttributeCooperative;     // only for its co-residency guarantee
+            at[1].val.cooperative = 1;
+            cfg.attrs = at;
+            cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &cfg) != cudaSuccess) { cudaGetLastError(); break; }
+            if (ncl * S < G) { G = ncl * S; continue; }      // fewer clusters fit: retry with the smaller grid
+            cfg.numAttrs = 2;
+            const size_t cells = 4 * (size_t)n + 8;          // + 8 cells = 16 profile counters
+            if (ws.trdll.n < cells) ws.trdll.alloc(cells);
+            NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));   // tag 0 = never written
+            int lda = n;
+            uint4* ll = ws.trdll.p;
+            long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * (size_t)n);
+            void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp};
+            // Without the co-residency guarantee of a cooperative launch the polling CTAs could wait for CTAs that are
+            // not running: if the launch is refused, fall through to the grid.sync kernel instead of launching anyway.
+            if (cudaLaunchKernelExC(&cfg, kfn, args) != cudaSuccess) { cudaGetLastError(); break; }
+            ++g_launches;
+            trd_done = true;
+            if (kprof) {
+                long long h[16];
+                NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
+                NLE_CUDA(cudaStreamSynchronize(s));
+                const double st = (double)std::max(1LL, h[11]);
+                double tot = 0;
+                for (int k = 0; k < 10; ++k) tot += (double)h[k];
+                fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: poll %.0f | forward+cluster.sync %.0f | dot-reduce %.0f | w %.0f | "
+                        "col %.0f | norm-reduce %.0f | sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; "
+                        "poll rounds/step %.2f\n", S, G, n, h[0] / st, h[9] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st,
+                        h[5] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
             }
-        }
-        if (!trd_done && mode == "resident" && n >= 3 && n <= kResPer * kTrdThreads) {
-            const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
-            int dev = 0, max_smem = 0;
-            NLE_CUDA(cudaGetDevice(&dev));
-            NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-            const int qmax = cdiv(n, grid);
-            const size_t smem = ((3 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
-            const void* kfn = kprof ? (const void*)tridiag_resident_kernel<true> : (const void*)tridiag_resident_kernel<false>;
-            if (smem <= (size_t)max_smem) {
-                NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-                int per_sm = 0;
-                NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
-                if (per_sm >= 1) {
-                    const size_t cells = 4 * (size_t)n + 8;      // + 8 cells = 16 profile counters
-                    if (ws.trdll.n < cells) ws.trdll.alloc(cells);
-                    NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));   // tag 0 = never written
-                    int lda = n;
-                    uint4* ll = ws.trdll.p;
-                    long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * (size_t)n);
-                    const char* lle = getenv("NLE_B200_TRD_LL");
-                    int ll_sys = (lle && std::string(lle) == "sys") ? 1 : 0;
-                    void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp, &ll_sys};
-                    // cooperative launch only for its co-residency guarantee (the kernel never calls grid.sync)
-                    NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
-                    ++g_launches;
-                    trd_done = true;
-                    if (kprof) {
-                        long long h[16];
-                        NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
-                        NLE_CUDA(cudaStreamSynchronize(s));
-                        const double st = (double)std::max(1LL, h[11]);
-                        fprintf(stderr, "[trd %s%s n=%d] cycles/step: poll %.0f | dot-reduce %.0f | w %.0f | col %.0f | norm-reduce %.0f | "
-                                "sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; poll rounds/step %.2f\n",
-                                mode.c_str(), ll_sys ? " ll=sys" : "", n, h[0] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st, h[5] / st, h[6] / st, h[7] / st,
-                                h[8] / st, (h[0] + h[1] + h[2] + h[3] + h[4] + h[5] + h[6] + h[7] + h[8]) / st, h[10] / st);
-                    }
-                }
-            }
+            break;
         }
     }
     if (!trd_done) {
         size_t smem = (3 * (size_t)n + 2 * kTrdWarps) * sizeof(double);
-        int dyn_cols = 0;
-        if (const char* e = getenv("NLE_B200_TRD_DYN")) dyn_cols = std::max(0, atoi(e));
-        const void* kfn = dyn_cols > 0 ? (const void*)tridiag_kernel<true> : (const void*)tridiag_kernel<false>;
+        const void* kfn = (const void*)tridiag_kernel;
         NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int per_sm = 0;
         NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
         if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(n) + ")"};
-        int grid = std::min(trd_grid_limit(), n);
+        int grid = std::min(sm_count(), n);
         int lda = n;
-        void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf, &dyn_cols};
+        void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf};
         NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
         ++g_launches;
     }
     auto t_trd = tnow();
+    ws.phase_mark(s);
     // ---- 2. divide & conquer on (d0, e0)
     int depth = 0;
     while (((n + (1 << depth) - 1) >> depth) > kLeaf) ++depth;
@@ -1774,6 +1487,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         std::swap(dc, dn);
     }
     auto t_dc = tnow();
+    ws.phase_mark(s);
     // ---- 3. back-transformation (in place in Qc)
     {
         int dev = 0, max_smem = 0;
@@ -1802,20 +1516,15 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
             reflector_dots_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(As, n, n, gdot);
             NLE_LAUNCH_CHECK();
         }
-        // compact-WY blocks on DMMA when the 8-column tile fits in shared memory; NLE_B200_BT=pair keeps the per-reflector kernel
-        static const bool bt_pair_env = [] { const char* e = getenv("NLE_B200_BT"); return e && std::string(e) == "pair"; }();
+        // compact-WY blocks on DMMA when the 8-column tile fits in shared memory (else the per-reflector kernel)
         const int nrefl = n - 2;
         const int nblocks = cdiv(nrefl, kWyB);
         const size_t wy_smem = ((size_t)n * 8 + 8 * kWyB * 8 + 2 * kWyB * 8 + kWyB * (kWyB + 1)) * sizeof(double);
-        if (m > 0 && !bt_pair_env && n >= 64 && wy_smem <= (size_t)max_smem) {
+        if (m > 0 && n >= 64 && wy_smem <= (size_t)max_smem) {
             if (ws.wyT.n < (size_t)nblocks * kWyB * kWyB) ws.wyT.alloc((size_t)nblocks * kWyB * kWyB);
             bt_tfactor_kernel<<<nblocks, 256, 0, s>>>(As, n, n, tau, nrefl, ws.wyT.p);
             NLE_LAUNCH_CHECK();
-            static size_t conf_wy = 0;
-            if (wy_smem > conf_wy) {
-                NLE_CUDA(cudaFuncSetAttribute(bt_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wy_smem));
-                conf_wy = wy_smem;
-            }
+            NLE_CUDA(cudaFuncSetAttribute(bt_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wy_smem));
             bt_wy_kernel<<<cdiv(m, 8), 256, wy_smem, s>>>(As, n, n, ws.wyT.p, nblocks, nrefl, Qc, n, collist, count, vec_limit);
             NLE_LAUNCH_CHECK();
         } else if (m > 0) {
@@ -1824,6 +1533,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         }
     }
     auto t_bt = tnow();
+    ws.phase_mark(s);
     if (prof) {
         auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
         fprintf(stderr, "[eig_dc n=%d] tridiag %.3f ms, divide&conquer %.3f ms, back-transform %.3f ms\n", n,

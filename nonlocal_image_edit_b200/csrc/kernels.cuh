@@ -1,4 +1,4 @@
-// Launchers of the N-scaled kernels (filter_kernels.cu).  All device pointers.
+// Launchers of the N-scaled kernels (filter_kernels.cu, cell_kernels.cu, sinkhorn_cells.cu).  All device pointers.
 #pragma once
 #include "common.cuh"
 
@@ -30,17 +30,6 @@ void launch_tables(int rows, int cols, int nR, int nC, const int* sel_rows, cons
 void launch_ka(int p, int nC, const int* sel_rows, const int* sel_cols, const uint8_t* Ysel,
                double hx, double hy, double* Ka, cudaStream_t s);
 
-// Sinkhorn pass, "dot" half:   x_j = recip( k_j^T w )  for every slab pixel (0 at sample pixels).
-void launch_pass_dot(const AffinityTables& t, const double* w, double* x, cudaStream_t s);
-// Sinkhorn pass, "reduce" half: s_i = sum_j K(i,j) x_j  over the slab (x is 0 at sample pixels).
-// spart: nrows x p scratch.  s_out: p.
-void launch_pass_reduce(const AffinityTables& t, const double* x, double* spart, double* s_out,
-                        cudaStream_t s);
-
-// Both halves in one kernel (bit-identical to launch_pass_dot followed by launch_pass_reduce).
-void launch_pass_fused(const AffinityTables& t, const double* w, double* x, double* spart, double* s_out,
-                       cudaStream_t s);
-
 // Cell index of a slab (cell_kernels.cu): the non-empty (image row, luminance level) cells, padded to a multiple of 4
 // per row, and the columns of every row ordered by (level, column).  All device pointers into `scratch`.
 struct CellIndex {
@@ -63,20 +52,13 @@ void sinkhorn_cells_prepare(const AffinityTables& t, double* scratch, cudaStream
 void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const double* w, double* x, double* scratch,
                            double* s_out, cudaStream_t s);
 
-// Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab.
-size_t gram_scratch_doubles(const AffinityTables& t);
-void launch_gram(const AffinityTables& t, const double* c, double* scratch, double* G,
-                 cudaStream_t s);
-
-// Same Gram through (image row, luminance level) cells (gram_cells.cu): K_cells*p*(p+1) flop instead of N*p*(p+1).
+// Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab, contracted over the
+// (image row, luminance level) cells (cell_kernels.cu): K_cells*p*(p+1) flop instead of N*p*(p+1).
 size_t gram_cells_scratch_doubles(const AffinityTables& t);
 void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s);
 
-// Extension  V_j = c_j * k_j^T Y   for non-sample slab pixels.  Y: p x k (column-major),
-// V: (nrows*cols) x k ROW-major (k fastest).
-void launch_extension(const AffinityTables& t, const double* c, const double* Y, int k, double* V,
-                      cudaStream_t s);
-// Same extension through (image row, luminance level) cells (cell_kernels.cu): K_cells*p*k + N*nC*k multiply-adds.
+// Extension  V_j = c_j * k_j^T Y  for the non-sample slab pixels.  Y: p x k (column-major), V: (nrows*cols) x k ROW-major
+// (k fastest).  Through the (image row, luminance level) cells (cell_kernels.cu): K_cells*p*k + N*nC*k multiply-adds.
 size_t extension_cells_scratch_doubles(const AffinityTables& t, int k);
 void launch_extension_cells(const AffinityTables& t, const double* c, const double* Y, int k, double* scratch, double* V,
                             cudaStream_t s);
@@ -98,7 +80,6 @@ void launch_lab2bgr(const uint8_t* L, const uint8_t* ab, long long npix, uint8_t
 
 // misc elementwise
 void launch_fill(double* p, long long n, double v, cudaStream_t s);
-void launch_mask_samples(const AffinityTables& t, double* x, cudaStream_t s);  // x=0 at sample pixels
 void launch_u8_from_f64(const double* in, long long n, uint8_t* out, int* bad_flag, cudaStream_t s);
 void launch_gather_c_sel(const AffinityTables& t, const int32_t* sel, const double* c_sel, double* c_full,
                          cudaStream_t s);

@@ -9,12 +9,14 @@
 //            Hx[row][b][l] = sum_{col : lum(row,col) = l} Ec[col][b] * x_j
 //
 // F (for every grid column b an (image rows x nR) * (nR x 256) product) and M (its transpose) are plain dense
-// GEMMs over ALL 256 luminance levels: they share the level-by-sample table across image rows, which the
-// per-row kernels of filter_kernels.cu (pass_fused_kernel: one table look-up per (row, level, sample) and
-// multiply-add) could not -- ncu showed those bound by shared-memory look-ups, not by arithmetic.
+// GEMMs over ALL 256 luminance levels: they share the level-by-sample table across image rows (the first
+// design, one table look-up per (row, level, sample) in a per-row kernel, was bound by shared-memory look-ups:
+// profiles/k7_pass_fused_kernel_full.md).
 //
 //   sk_dot_gemm_kernel      F  = Er * B_b,  B operand generated in registers (one look-up per 8 DMMAs)
-//   sk_pix_kernel           one CTA per image row: y, x, and the per-row histogram Hx (deterministic: every
+//   sk_pix_cells_kernel     the pixel pass: one warp per (image row, level) cell of the cell index, y, x and the
+//                           cell's histogram bins Hx in registers (sample grids up to 64 columns)
+//   sk_pix_kernel           the same pass for wider sample grids, one CTA per image row (deterministic: every
 //                           (level, b) bin is owned by one lane and filled in ascending column order);
 //                           Hx overwrites F in place
 //   sk_reduce_gemm_kernel   M partials = Er^T * Hx over row splits
@@ -167,130 +169,6 @@ sk_pix_kernel(AffinityTables t, int w_given, double* __restrict__ x, double* __r
         }
         __syncthreads();
         for (int e = tid; e < nC * NL; e += 256) fh[e] = Ts[(e & (NL - 1)) * nCp + (e >> 8)];
-    }
-}
-
-// Same row pass with the dot and the histogram fused over chunks of PF_CH consecutive pixels: the Ec rows of a
-// chunk are staged ONCE in shared memory (coalesced, prefetched one chunk ahead in registers) and serve both
-// halves, so a row costs nC*W*8 B of Ec traffic instead of twice that through the strided EcT reads of
-// sk_pix_kernel; F and the histogram live in separate shared-memory tables (2 * 256 * nC * 8 B: nC <= 47).
-// 16 warps: in the dot half 8 threads share a pixel (b = sub, sub+8, ...; xor-shuffle tree), in the
-// histogram half warp w owns the levels with (l & 15) == w (lanes over b, ascending column order).
-constexpr int PF_THREADS = 512;
-constexpr int PF_CH = 64;
-constexpr int PF_NPF = 6;       // staged doubles per thread: PF_CH * nC <= PF_THREADS * PF_NPF  (nC <= 48)
-
-__global__ void __launch_bounds__(PF_THREADS, 1)
-sk_pix_fused_kernel(AffinityTables t, int w_given, double* __restrict__ x, double* __restrict__ FH) {
-    extern __shared__ double psm[];
-    const int nC = t.nC, W = t.cols;
-    const int nCp = nC | 1;
-    double* Fs = psm;                                        // NL * nCp
-    double* Hs = Fs + (size_t)NL * nCp;                      // NL * nCp
-    double* stage = Hs + (size_t)NL * nCp;                   // PF_CH * nC
-    double* xs = stage + PF_CH * nC;                         // PF_CH
-    uint8_t* Lrow = reinterpret_cast<uint8_t*>(xs + PF_CH);  // W
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int nst = PF_CH * nC;
-    for (int rl = blockIdx.x; rl < t.nrows; rl += gridDim.x) {
-        const int row = t.row0 + rl;
-        double* fh = FH + (size_t)rl * nC * NL;
-        const uint8_t* Lg = t.lum + (size_t)rl * W;
-        const int a_row = t.rowa[row];
-        double* xo = x + (size_t)rl * W;
-        __syncthreads();
-        for (int c = tid; c < W; c += PF_THREADS) Lrow[c] = Lg[c];
-        if (w_given)
-            for (int e = tid; e < nC * NL; e += PF_THREADS) Fs[(e & (NL - 1)) * nCp + (e >> 8)] = fh[e];
-        for (int e = tid; e < NL * nCp; e += PF_THREADS) Hs[e] = 0.0;
-        double pf[PF_NPF];
-        auto fetch = [&](int c0) {
-#pragma unroll
-            for (int q = 0; q < PF_NPF; ++q) {
-                const int e = tid + PF_THREADS * q;
-                pf[q] = (e < nst && (size_t)c0 * nC + e < (size_t)W * nC) ? t.Ec[(size_t)c0 * nC + e] : 0.0;
-            }
-        };
-        fetch(0);
-        for (int c0 = 0; c0 < W; c0 += PF_CH) {
-            __syncthreads();                               // previous chunk consumed; row tables ready
-#pragma unroll
-            for (int q = 0; q < PF_NPF; ++q) {
-                const int e = tid + PF_THREADS * q;
-                if (e < nst) stage[e] = pf[q];
-            }
-            if (c0 + PF_CH < W) fetch(c0 + PF_CH);
-            __syncthreads();
-            // ---- dot half: 8 threads per pixel (b = sub, sub+8, ...), xor-shuffle tree inside the 8-lane group
-            {
-                static_assert(PF_CH * 8 == PF_THREADS, "8 threads per staged pixel");
-                const int j = tid >> 3, sub = tid & 7;
-                const int c = c0 + j;
-                double v = 0.0;
-                if (w_given && c < W) {
-                    const double* f = Fs + (size_t)Lrow[c] * nCp;
-                    const double* ec = stage + j * nC;
-                    for (int b = sub; b < nC; b += 8) v = fma(ec[b], f[b], v);
-                }
-                v += __shfl_xor_sync(0xffffffffu, v, 4);
-                v += __shfl_xor_sync(0xffffffffu, v, 2);
-                v += __shfl_xor_sync(0xffffffffu, v, 1);
-                if (sub == 0 && c < W) {
-                    double r;
-                    if (a_row >= 0 && t.colb[c] >= 0) r = 0.0;
-                    else if (!w_given) r = 1.0;
-                    else r = (fabs(v) >= kEps) ? 1.0 / v : 0.0;
-                    xs[j] = r;
-                }
-            }
-            __syncthreads();
-            if (tid < PF_CH && c0 + tid < W) xo[c0 + tid] = xs[tid];
-            // ---- histogram half
-#pragma unroll
-            for (int half = 0; half < PF_CH / 32; ++half) {
-                const int jl = half * 32 + lane;
-                const int c = c0 + jl;
-                const int lv_l = (c < W) ? (int)Lrow[c] : 0;
-                const bool mine = (c < W) && ((lv_l & 15) == warp) && (xs[jl] != 0.0);
-                unsigned m = __ballot_sync(0xffffffffu, mine);
-                // two pixels in flight when their levels (bins) differ: the update is a dependent LDS-DFMA-STS chain
-                while (m) {
-                    const int j0 = __ffs(m) - 1;
-                    m &= m - 1;
-                    const int lv0 = __shfl_sync(0xffffffffu, lv_l, j0);
-                    int j1 = -1, lv1 = 0;
-                    if (m) {
-                        j1 = __ffs(m) - 1;
-                        lv1 = __shfl_sync(0xffffffffu, lv_l, j1);
-                        if (lv1 != lv0) m &= m - 1; else j1 = -1;
-                    }
-                    const double xv0 = xs[half * 32 + j0];
-                    const double* ec0 = stage + (half * 32 + j0) * nC;
-                    double* h0 = Hs + (size_t)lv0 * nCp;
-                    const bool tail = lane + 32 < nC;
-                    if (j1 >= 0) {
-                        const double xv1 = xs[half * 32 + j1];
-                        const double* ec1 = stage + (half * 32 + j1) * nC;
-                        double* h1 = Hs + (size_t)lv1 * nCp;
-                        if (lane < nC) {
-                            const double e0 = ec0[lane], g0 = h0[lane], e1 = ec1[lane], g1 = h1[lane];
-                            h0[lane] = fma(e0, xv0, g0);
-                            h1[lane] = fma(e1, xv1, g1);
-                        }
-                        if (tail) {
-                            const double e0 = ec0[lane + 32], g0 = h0[lane + 32], e1 = ec1[lane + 32], g1 = h1[lane + 32];
-                            h0[lane + 32] = fma(e0, xv0, g0);
-                            h1[lane + 32] = fma(e1, xv1, g1);
-                        }
-                    } else {
-                        if (lane < nC) h0[lane] = fma(ec0[lane], xv0, h0[lane]);
-                        if (tail) h0[lane + 32] = fma(ec0[lane + 32], xv0, h0[lane + 32]);
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        for (int e = tid; e < nC * NL; e += PF_THREADS) fh[e] = Hs[(e & (NL - 1)) * nCp + (e >> 8)];
     }
 }
 
@@ -456,8 +334,7 @@ sk_reduce_final_kernel(AffinityTables t, const double* __restrict__ Mpart, int n
 
 struct SkGeom {
     int nRp, MT, nab, nks;
-    size_t fh_doubles, mpart_doubles, pix_smem, pixf_smem, dot_smem;
-    bool fused;
+    size_t fh_doubles, mpart_doubles, pix_smem, dot_smem;
 };
 
 SkGeom sk_geometry(const AffinityTables& t) {
@@ -472,8 +349,6 @@ SkGeom sk_geometry(const AffinityTables& t) {
     g.mpart_doubles = (size_t)g.nks * t.nC * g.nRp * NL;
     const int nCp = t.nC | 1;
     g.pix_smem = ((size_t)NL * nCp + 32 * (size_t)t.nC + t.cols) * sizeof(double) + ((t.cols + 15) / 16) * 16 + 64;
-    g.pixf_smem = ((size_t)2 * NL * nCp + (size_t)PF_CH * t.nC + PF_CH) * sizeof(double) + ((t.cols + 15) / 16) * 16 + 64;
-    g.fused = g.pixf_smem <= 227 * 1024 && PF_CH * t.nC <= PF_THREADS * PF_NPF && t.nC <= 64;
     const int nR4 = (t.nR + 3) & ~3;
     const int lda = nR4 + ((12 - (nR4 & 15)) & 15);
     g.dot_smem = ((size_t)DG_ROWS * lda + NL + nR4) * sizeof(double) + (size_t)nR4 * sizeof(int) + 64;
@@ -484,7 +359,7 @@ SkGeom sk_geometry(const AffinityTables& t) {
 
 bool sinkhorn_cells_supported(const AffinityTables& t) {
     const SkGeom g = sk_geometry(t);
-    return (g.fused || g.pix_smem <= 227 * 1024) && g.dot_smem <= 227 * 1024;
+    return (t.nC <= 64 || g.pix_smem <= 227 * 1024) && g.dot_smem <= 227 * 1024;
 }
 
 size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t) {
@@ -517,26 +392,12 @@ static void launch_rg(const AffinityTables& t, const SkGeom& g, const double* FH
 void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const double* w, double* x, double* scratch,
                            double* s_out, cudaStream_t s) {
     const SkGeom g = sk_geometry(t);
-    static const bool staged_env = getenv("NLE_B200_SK_STAGED") != nullptr;
-    const bool cells = ci != nullptr && t.nC <= 64 && !staged_env;
+    const bool cells = ci != nullptr && t.nC <= 64;    // wider sample grids: the per-row staged kernel
     double* FH = scratch;                              // staged path: F, overwritten in place by the histogram
     double* Hc = scratch + g.fh_doubles;               // cell path: separate histogram table
     double* Mpart = scratch + 2 * g.fh_doubles;
-    static size_t conf_pix = 0, conf_dot = 0, conf_pixf = 0;
-    static const bool unfused_env = getenv("NLE_B200_SK_UNFUSED") != nullptr;
-    const bool fused = g.fused && !unfused_env;
-    if (!cells && fused && g.pixf_smem > conf_pixf) {
-        NLE_CUDA(cudaFuncSetAttribute(sk_pix_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pixf_smem));
-        conf_pixf = g.pixf_smem;
-    }
-    if (!cells && !fused && g.pix_smem > conf_pix) {
-        NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
-        conf_pix = g.pix_smem;
-    }
-    if (g.dot_smem > conf_dot) {
-        NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_smem));
-        conf_dot = g.dot_smem;
-    }
+    if (!cells) NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
+    NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_smem));
     if (w) {
         sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH, 0);
         NLE_LAUNCH_CHECK();
@@ -555,9 +416,6 @@ void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const d
             default: launch_pc<8>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
         }
         Hx = Hc;
-    } else if (fused) {
-        sk_pix_fused_kernel<<<t.nrows, PF_THREADS, g.pixf_smem, s>>>(t, w ? 1 : 0, x, FH);
-        NLE_LAUNCH_CHECK();
     } else {
         sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
         NLE_LAUNCH_CHECK();

@@ -119,9 +119,17 @@ def orthogonalize(Wa, Wab, nEigVectors=5, eps=EPS):
     return np.asfortranarray(V[:, :k.value]), S[:k.value].copy()
 
 
+def _image_u8(image, what):
+    """The reference's images are CV_8UC3 cv::Mat (enhance.cpp:33 imread): anything else is refused, never reinterpreted."""
+    img = np.asarray(image)
+    if img.dtype != np.uint8:
+        raise NleError(-1, f"{what}: expected a uint8 (CV_8U) image, got dtype {img.dtype}")
+    return np.ascontiguousarray(img)
+
+
 def bgrToLab(image):
     """cv::cvtColor(image, COLOR_BGR2Lab) on CV_8UC3 (filter.cpp:423,463), on the device."""
-    img = np.ascontiguousarray(image, dtype=np.uint8)
+    img = _image_u8(image, "bgrToLab")
     if img.ndim != 3 or img.shape[2] != 3:
         raise NleError(-1, "expected an H x W x 3 uint8 image")
     out = np.empty_like(img)
@@ -131,7 +139,7 @@ def bgrToLab(image):
 
 def labToBgr(lab):
     """cv::cvtColor(lab, COLOR_Lab2BGR) on CV_8UC3 (filter.cpp:440), on the device."""
-    img = np.ascontiguousarray(lab, dtype=np.uint8)
+    img = _image_u8(lab, "labToBgr")
     if img.ndim != 3 or img.shape[2] != 3:
         raise NleError(-1, "expected an H x W x 3 uint8 image")
     out = np.empty_like(img)
@@ -261,7 +269,7 @@ class NLEFilter:
     # -- public API of the reference class --------------------------------------------------
     def trainForEnhancement(self, image, nRowSamples, nColSamples, hx, hy, nSinkhornIter=10, nEigenVectors=5):
         """filter.cpp:514-519: getLuminanceChannel (:460-469, BGR2Lab on the device) + trainFilter."""
-        image = np.ascontiguousarray(image, dtype=np.uint8)
+        image = _image_u8(image, "trainForEnhancement")
         if image.ndim != 3 or image.shape[2] != 3:
             raise NleError(-1, "expected an H x W x 3 uint8 image")
         self._release()
@@ -277,7 +285,7 @@ class NLEFilter:
                         sigmaColor=10, sigmaSpace=10):
         """filter.cpp:521-538."""
         import cv2
-        L = np.ascontiguousarray(self._lab(np.ascontiguousarray(image))[:, :, 0])
+        L = np.ascontiguousarray(self._lab(_image_u8(image, "trainForDenoise"))[:, :, 0])
         den = cv2.bilateralFilter(L, -1, sigmaColor, sigmaSpace, borderType=cv2.BORDER_DEFAULT)
         return self.trainFilter(den, nRowSamples, nColSamples, hx, hy, nSinkhornIter, nEigenVectors)
 
@@ -292,14 +300,14 @@ class NLEFilter:
         if fS.size != inf.k:
             raise NleError(-1, "transformed eigenvalues must have one entry per eigenvector")
         out = np.empty_like(ch)
-        check(self._lib.nle_b200_apply(self._h, _ptr(ch), _ptr(fS), _ptr(out)))
+        check(self._lib.nle_b200_apply(self._h, _ptr(ch), ch.size, _ptr(fS), _ptr(out)))
         return out
 
     def enhanceLuminance(self, lum_u8, weights):
         """filter.cpp:426-436 on the 8-bit L channel, fused on the device."""
         self._require_trained()
         inf = self.info()
-        lum = np.ascontiguousarray(lum_u8, dtype=np.uint8)
+        lum = _image_u8(lum_u8, "enhanceLuminance")
         if lum.size != (inf.row1 - inf.row0) * inf.cols:
             raise NleError(-1, "Cannot apply filter on image with different size from the image filter was trained on.")
         w = _f64(weights)
@@ -309,7 +317,7 @@ class NLEFilter:
 
     def enhance(self, image, weights):
         """NLEFilter::enhance (filter.cpp:412-443)."""
-        image = np.ascontiguousarray(image)
+        image = _image_u8(image, "enhance")
         if image.ndim != 3 or image.shape[2] != 3:
             raise NleError(-1, "Can only enhance RGB image.")                                    # :415
         self._require_trained()
@@ -320,19 +328,22 @@ class NLEFilter:
             raise NleError(-1, "enhance() needs the whole image on this filter; use enhanceLuminance on a row slab")
         w = _f64(weights)
         out = np.empty_like(image)
-        check(self._lib.nle_b200_enhance_bgr_u8(self._h, _ptr(image), _ptr(w), w.size, _ptr(out)))   # :422-440 on the device
+        check(self._lib.nle_b200_enhance_bgr_u8(self._h, _ptr(image), image.shape[0], image.shape[1], image.shape[2],
+                                                _ptr(w), w.size, _ptr(out)))                      # :422-440 on the device
         return out
 
     def denoise(self, image, k, sigmaColor=10, sigmaSpace=10):
         """NLEFilter::denoise (filter.cpp:349-410) without the imshow side effects."""
         import cv2
-        image = np.ascontiguousarray(image)
+        image = _image_u8(image, "denoise")
         if image.ndim != 3 or image.shape[2] != 3:
             raise NleError(-1, "Can only enchance RGB image.")                                   # :352 (sic)
         self._require_trained()
         inf = self.info()
         if image.shape[0] * image.shape[1] != inf.rows * inf.cols:
             raise NleError(-1, "Cannot apply filter on image with different size from the image filter was trained on.")  # :356
+        if (inf.row0, inf.row1) != (0, inf.rows):
+            raise NleError(-1, "denoise() needs the whole image on this filter (it was trained on a row slab)")
         lab = self._lab(image)
         Y = cv2.bilateralFilter(np.ascontiguousarray(lab[:, :, 0]), -1, sigmaColor, sigmaSpace,
                                 borderType=cv2.BORDER_DEFAULT)                                   # :371
@@ -341,6 +352,6 @@ class NLEFilter:
         for c in (1, 2):                                                                         # :388-389
             src = np.ascontiguousarray(lab[:, :, c])
             dst = np.empty_like(src)
-            check(self._lib.nle_b200_denoise_channel_u8(self._h, _ptr(src), float(k), _ptr(dst)))
+            check(self._lib.nle_b200_denoise_channel_u8(self._h, _ptr(src), src.shape[0], src.shape[1], float(k), _ptr(dst)))
             out[:, :, c] = dst
         return self._bgr(out)

@@ -45,3 +45,35 @@ def torch_allreduce(device=None, group=None):
             t = torch.as_tensor(_DevArray(ptr, count), device=device)
         dist.all_reduce(t, group=group)
     return _fn
+
+
+class LibraryComm:
+    """The library's own NCCL communicator (csrc/nccl_comm.cu): the all-reduces of a sharded training call become
+    ncclAllReduce calls enqueued by libnle_b200.so itself -- no Python between a kernel and its collective.
+
+    torch.distributed is only the bootstrap: rank 0 draws the 128-byte NCCL unique id and it is broadcast once over the
+    already initialised process group.  `callback` / `user` are what the sharded entry points of the C ABI take
+    (nle_b200_train_bgr_u8, nle_b200_train_u8_dev, ...)."""
+
+    def __init__(self, device):
+        import torch
+        import torch.distributed as dist
+        from . import _lib
+        self._lib = _lib.load()
+        rank, world = dist.get_rank(), dist.get_world_size()
+        ident = (C.c_ubyte * 128)()
+        if rank == 0:
+            _lib.check(self._lib.nle_b200_comm_unique_id(ident))
+        t = torch.tensor(list(ident), dtype=torch.uint8, device=device)
+        dist.broadcast(t, src=0)
+        ident = (C.c_ubyte * 128)(*t.cpu().tolist())
+        h = C.c_void_p()
+        _lib.check(self._lib.nle_b200_comm_create(ident, rank, world, C.byref(h)))
+        self.handle = h
+        self.callback = C.cast(self._lib.nle_b200_comm_allreduce, _lib.ALLREDUCE_FN)
+        self.user = h
+
+    def close(self):
+        if self.handle:
+            self._lib.nle_b200_comm_destroy(self.handle)
+            self.handle = None

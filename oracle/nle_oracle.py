@@ -18,7 +18,7 @@ Third-party arithmetic the reference delegates to, and what stands in for it her
     (``filter.cpp:423,436,440``) -> Python ``cv2`` 4.13 and ``np.rint`` (cvRound is
     round-half-to-even).
 
-Parity pin: ``tests/test_oracle_golden.py`` checks this oracle against (G1) the ten README
+Parity pin: ``tests/test_oracle.py`` checks this oracle against (G1) the ten README
 parameter rows and their committed outputs ``data/*-filtered.png`` (fixtures under
 ``tests/golden/``, made by ``tests/golden/make_golden.py``), (G2) the 3x3 known-answer
 eigen-decomposition of ``test/test_filter.cpp:42-68``, (G3) the identity Sinkhorn case
@@ -108,6 +108,56 @@ def affinity_block(lum_flat, ncols, idx_a, idx_b, hx, hy):
     d2 = ((ra[:, None] - rb[None, :]) ** 2 + (ca[:, None] - cb[None, :]) ** 2).astype(np.float64)
     dy = lum_flat[idx_a][:, None] - lum_flat[idx_b][None, :]
     return np.exp(-sw * d2 - pw * (dy * dy))
+
+
+# filter.cpp:104-145 again, in C (oracle/nle_oracle_c.c): one scalar libm exp per entry, no temporaries, sample rows
+# split over a thread pool.  Same expression and evaluation order; differs from the NumPy form above only by the
+# last-ulp behaviour of the two exp implementations.  Used by train_streaming for the configurations the dense
+# reference cannot hold in RAM (tests/golden/make_oracle_big.py); tests/test_oracle.py pins it to affinity_block.
+_C = None
+
+
+def _c_lib():
+    global _C
+    if _C is None:
+        import ctypes
+        import os
+        from . import build_c
+        lib = ctypes.CDLL(build_c.build())
+        vp, i64, f64 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_double
+        lib.nle_oracle_affinity_block.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp, i64, f64, f64, vp]
+        lib.nle_oracle_affinity_block.restype = None
+        _C = lib
+    return _C
+
+
+def affinity_block_c(lum_flat, ncols, idx_a, idx_b, hx, hy, threads=None):
+    import os
+    from concurrent.futures import ThreadPoolExecutor
+    lib = _c_lib()
+    sw = 1.0 / (hx * hx)
+    pw = 1.0 / (hy * hy)
+    idx_a = np.ascontiguousarray(idx_a, dtype=np.int64)
+    idx_b = np.ascontiguousarray(idx_b, dtype=np.int64)
+    ra, ca = (np.ascontiguousarray(a) for a in np.divmod(idx_a, ncols))
+    rb, cb = (np.ascontiguousarray(a) for a in np.divmod(idx_b, ncols))
+    ya = np.ascontiguousarray(lum_flat[idx_a], dtype=np.float64)
+    yb = np.ascontiguousarray(lum_flat[idx_b], dtype=np.float64)
+    na, nb = idx_a.size, idx_b.size
+    out = np.empty((na, nb), dtype=np.float64)
+    nt = max(1, min(threads or (os.cpu_count() or 1), na))
+    cuts = [na * t // nt for t in range(nt + 1)]
+
+    def part(t):
+        lib.nle_oracle_affinity_block(ra.ctypes.data, ca.ctypes.data, ya.ctypes.data, cuts[t], cuts[t + 1],
+                                      rb.ctypes.data, cb.ctypes.data, yb.ctypes.data, nb, sw, pw, out.ctypes.data)
+
+    if nt == 1:
+        part(0)
+    else:
+        with ThreadPoolExecutor(nt) as ex:
+            list(ex.map(part, range(nt)))
+    return out
 
 
 def compute_kernel(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx: float, hy: float):
@@ -287,8 +337,9 @@ def _tiles(n, tile):
 
 def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx: float, hy: float,
                     n_sinkhorn_iter: int = 10, n_eigen_vectors: int = 5,
-                    tile: int = 16384, slab=None, allreduce=None) -> TrainedFilter:
-    """slab=(row0,row1) restricts every pixel sum to the image rows owned by one rank and
+                    tile: int = 16384, slab=None, allreduce=None, block_fn=None) -> TrainedFilter:
+    """block_fn: affinity_block (default, NumPy) or affinity_block_c (same loop in C, threaded).
+    slab=(row0,row1) restricts every pixel sum to the image rows owned by one rank and
     `allreduce(np.ndarray)` (in-place sum over ranks) completes them: the CPU model of the row-sharded
     multi-GPU path.  The returned eigvecs then cover only the slab's pixels."""
     lum = np.asarray(lum, dtype=np.float64)
@@ -306,10 +357,12 @@ def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx:
     p, nrest = sel.size, rest.size
     T = n_sinkhorn_iter
 
-    def kb(s, e):                       # p x (e-s) block of Kab for rest pixels s..e-1
-        return affinity_block(z, ncols, sel, rest[s:e], hx, hy)
+    blk = block_fn or affinity_block
 
-    Ka = affinity_block(z, ncols, sel, sel, hx, hy)
+    def kb(s, e):                       # p x (e-s) block of Kab for rest pixels s..e-1
+        return blk(z, ncols, sel, rest[s:e], hx, hy)
+
+    Ka = blk(z, ncols, sel, sel, hx, hy)
     U, lam = eigen_decomposition(Ka)                      # A.3
     r = lam.size
     inv_lam = 1.0 / lam

@@ -1,0 +1,110 @@
+"""GPU: the kernel choices that are made automatically must not change results.
+
+* Tridiagonalisation: tridiag_cluster_kernel (default for 64 <= n <= 2048: trailing matrix resident in shared memory,
+  flagged-cell exchange, clusters of 2 CTAs) performs the same FP64 operations in the same order as tridiag_kernel
+  (one grid.sync per Householder step; the path for n > 2048): d, e, tau and the reflectors -- hence the whole
+  eigen-decomposition and the enhanced image -- must be BIT-identical.  NLE_B200_TRD=gridsync (read once per process)
+  forces the latter, so each side runs in its own process.
+* Eigensolver family: the direct solver (tridiagonalisation + divide & conquer) against the block-Jacobi fallback
+  (NLE_B200_EIG=jacobi) to rounding.
+* Sinkhorn pixel pass: sample grids wider than 64 columns take the per-row staged kernel (sk_pix_kernel) instead of the
+  cell kernel; both against the oracle."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from nle_testlib import ROOT, synth_lum
+from oracle import nle_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SIZES = [3, 5, 63, 64, 65, 149, 300, 612, 1041, 1600, 2048, 2049]
+
+CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[2]); sys.path.insert(0, sys.argv[2] + '/tests')
+import nonlocal_image_edit_b200 as nb
+from nle_testlib import synth_lum
+res = {}
+for n in %r:
+    rng = np.random.default_rng(n)
+    B = rng.standard_normal((n, max(3, n // 2)))
+    A = B @ B.T / n + 1e-3 * np.eye(n)
+    U, D = nb.eigenDecomposition(A, eps=-1e300)
+    res[f'U{n}'] = U; res[f'D{n}'] = D
+for name, A in (('eye', np.eye(70)), ('zero', np.zeros((70, 70))), ('ones', np.ones((70, 70))), ('diag', np.diag(np.arange(1.0, 81.0)))):
+    U, D = nb.eigenDecomposition(A, eps=-1e300)
+    res['U' + name] = U; res['D' + name] = D
+L = synth_lum(160, 200, seed=3)
+f = nb.NLEFilter().trainFilter(L, 12, 14, 60.0, 25.0, 8, 12)
+res['S'] = f.eigvals
+res['out'] = f.enhanceLuminance(L, [2.0, 3.0, 4.0, 1.0])
+res['fallbacks'] = np.array([f.info().eig_fallbacks])
+np.savez(sys.argv[1], **res)
+""" % (SIZES,)
+
+
+def _run(tmp_path, tag, env_extra):
+    env = {k: v for k, v in os.environ.items() if not k.startswith("NLE_B200_")}
+    env.update(env_extra)
+    env["NLE_B200_EIG_STRICT"] = "1"          # no fallback to Jacobi behind the test's back
+    out = str(tmp_path / f"{tag}.npz")
+    subprocess.run([sys.executable, "-c", CHILD, out, ROOT], env=env, check=True, timeout=600)
+    return np.load(out)
+
+
+def test_cluster_tridiagonalisation_is_bit_identical_to_grid_sync(tmp_path):
+    a = _run(tmp_path, "cluster", {})
+    b = _run(tmp_path, "gridsync", {"NLE_B200_TRD": "gridsync"})
+    assert sorted(a.files) == sorted(b.files)
+    for key in a.files:
+        assert np.array_equal(a[key], b[key]), key
+    assert int(a["fallbacks"][0]) == 0
+    for n in SIZES:
+        rng = np.random.default_rng(n)
+        B = rng.standard_normal((n, max(3, n // 2)))
+        w = np.linalg.eigvalsh(B @ B.T / n + 1e-3 * np.eye(n))[::-1]
+        assert np.abs(a[f"D{n}"] - w).max() <= 1e-11 * max(1.0, np.abs(w).max()) * max(1, n / 16)
+
+
+@pytest.mark.parametrize("n", [40, 200, 700])
+def test_direct_solver_agrees_with_block_jacobi(tmp_path, n):
+    code = ("import sys, numpy as np; sys.path.insert(0, sys.argv[2]); import nonlocal_image_edit_b200 as nb;"
+            f"rng = np.random.default_rng({n}); B = rng.standard_normal(({n}, {n}));"
+            "A = B @ B.T / B.shape[0]; U, D = nb.eigenDecomposition(A, eps=-1e300); np.savez(sys.argv[1], U=U, D=D, A=A)")
+    outs = []
+    for tag, extra in (("direct", {}), ("jacobi", {"NLE_B200_EIG": "jacobi"})):
+        env = {k: v for k, v in os.environ.items() if not k.startswith("NLE_B200_")}
+        env.update(extra)
+        out = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", code, out, ROOT], env=env, check=True, timeout=300)
+        outs.append(np.load(out))
+    d, j = outs
+    scale = np.abs(d["D"]).max()
+    assert np.abs(d["D"] - j["D"]).max() <= 1e-12 * scale * max(1, n / 50)
+    for U in (d["U"], j["U"]):
+        assert np.abs(U.T @ U - np.eye(n)).max() <= 1e-11
+        assert np.abs(d["A"] @ U - U * d["D"]).max() <= 1e-11 * scale * max(1, n / 50)
+
+
+def test_wide_sample_grid_takes_the_row_kernel_and_matches_the_oracle(nb):
+    # 70 sample columns > 64: launch_sinkhorn_cells uses sk_pix_kernel (one CTA per image row) for the pixel pass
+    L = synth_lum(48, 360, seed=5)
+    args = (3, 70, 40.0, 20.0, 6, 8)
+    f = nb.NLEFilter().trainFilter(L, *args)
+    ref = O.train_dense(L.astype(np.float64), *args)
+    inf = f.info()
+    assert (inf.p, inf.r, inf.r2, inf.k) == (ref.stages["p"], ref.stages["r"], ref.stages["r2"], ref.eigvals.size)
+    cg = f.stage(3)
+    co = np.empty_like(cg)
+    co[ref.stages["perm"]] = ref.stages["c"]
+    mask = np.ones(cg.size, bool)
+    mask[ref.stages["perm"][:inf.p]] = False                  # the C stage keeps c of the rest pixels only
+    assert np.abs(cg[mask] - co[mask]).max() <= 1e-9 * np.abs(co).max()
+    assert np.allclose(f.eigvals, ref.eigvals, rtol=1e-6)
+    out = f.enhanceLuminance(L, [2.0, 3.0, 4.0, 1.0])
+    d = np.abs(out.astype(int) - O.enhance_luminance(ref, L, [2.0, 3.0, 4.0, 1.0]).astype(int))
+    assert d.max() <= 1 and (d <= 1).mean() >= 0.999

@@ -1,0 +1,63 @@
+"""GPU: parity with the FP64 streaming oracle AT THE CONFIGURATIONS THAT ARE BENCHMARKED (BASELINE.json configs[2..4]).
+
+The dense reference cannot hold these in host RAM (80 GB / 60 GB / > 2 TB), so the fixtures were produced
+once by tests/golden/make_oracle_big.py with the streaming restatement of filter.cpp:480-502 (oracle/nle_oracle.py,
+pinned to the dense restatement on small inputs and to the README goldens) and are committed as
+tests/golden/oracle_big.json + <name>_oracle_L.png:
+
+  c3      configs[2], the bench workload: 1024x1024, 40x40 samples, hx=500 hy=30, T=20, k=50
+  c4      configs[3]: full-resolution rock2 (584x876), 50x50 samples, hx=500 hy=10, T=50, k=100
+  c5crop  configs[4] on its top-left 1024x1024 crop, 50x50 samples, hx=500 hy=30, T=20, k=100
+
+Bar (north_star): identical sample indices, identical rank cuts r / r2 / k', eigenvalues within 1e-5 relative, output
+within 1 LSB on >= 99.9 % of the pixels."""
+import hashlib
+import json
+import os
+import sys
+
+import cv2
+import numpy as np
+import pytest
+
+from nle_testlib import GOLDEN, ROOT
+
+pytestmark = pytest.mark.gpu
+
+sys.path.insert(0, os.path.join(GOLDEN))
+
+
+def _fixtures():
+    path = os.path.join(GOLDEN, "oracle_big.json")
+    return json.load(open(path)) if os.path.exists(path) else {}
+
+
+FIX = _fixtures()
+
+
+@pytest.mark.parametrize("name", ["c3", "c4", "c5crop"])
+def test_cuda_path_matches_streaming_oracle(nb, name):
+    if name not in FIX:
+        pytest.fail(f"fixture {name} missing from tests/golden/oracle_big.json (run tests/golden/make_oracle_big.py)")
+    import make_oracle_big
+    fx = FIX[name]
+    lum, args, weights = make_oracle_big.config(name)
+    assert hashlib.sha1(lum.tobytes()).hexdigest() == fx["lum_sha1"], "the input generator changed since the fixture was made"
+    assert list(args) == fx["args"] and weights == fx["weights"]
+    sel, _ = nb.sampleIndices(lum.shape[0], lum.shape[1], args[0], args[1], with_rest=False)
+    assert hashlib.sha1(sel.astype(np.int32).tobytes()).hexdigest() == fx["sel_sha1"]
+    f = nb.NLEFilter().trainFilter(lum, *args)
+    inf = f.info()
+    assert (inf.p, inf.r, inf.r2, inf.k) == (fx["p"], fx["r"], fx["r2"], fx["k"]), (inf.p, inf.r, inf.r2, inf.k)
+    assert inf.eig_fallbacks == 0
+    S, So = f.eigvals, np.array(fx["Sq"])
+    rel = np.abs(S - So) / So
+    assert rel.max() <= 1e-5, (rel.max(), int(rel.argmax()), So[int(rel.argmax())])       # north_star: 1e-5 relative
+    out = f.enhanceLuminance(lum, weights)
+    ref = cv2.imread(os.path.join(GOLDEN, f"{name}_oracle_L.png"), cv2.IMREAD_GRAYSCALE)
+    assert ref is not None and ref.shape == lum.shape
+    assert hashlib.sha1(ref.tobytes()).hexdigest() == fx["L_sha1"]
+    d = np.abs(out.astype(int) - ref.astype(int))
+    assert (d <= 1).mean() >= 0.999, ((d <= 1).mean(), int(d.max()))
+    print(f"{name}: max|dL|={int(d.max())} identical={float((d == 0).mean()):.5f} within1={float((d <= 1).mean()):.5f} "
+          f"max rel dSq={rel.max():.2e}")

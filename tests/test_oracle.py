@@ -111,6 +111,57 @@ def test_compute_kernel_errors_and_shapes():
     assert np.allclose(np.diag(Ka), 1.0) and np.allclose(Ka, Ka.T)
 
 
+# ---- the C affinity loop (oracle/nle_oracle_c.c) == the NumPy affinity loop ------------------------
+def test_c_affinity_block_matches_numpy():
+    L = synth_lum(60, 90).astype(float)
+    z = L.ravel()
+    sel, rest = O.sample_pixels(60, 90, 5, 7)
+    for hx, hy in ((20.0, 25.0), (500.0, 10.0), (3.0, 200.0)):
+        A = O.affinity_block(z, 90, sel, rest, hx, hy)
+        B = O.affinity_block_c(z, 90, sel, rest, hx, hy)
+        assert A.shape == B.shape
+        # same expression, same evaluation order; libm's exp and NumPy's exp may differ in the last ulp
+        assert np.all(np.abs(A - B) <= 4 * np.finfo(float).eps * A)
+        assert np.array_equal(O.affinity_block_c(z, 90, sel, rest, hx, hy, threads=1), B)
+    Ka = O.affinity_block_c(z, 90, sel, sel, 20.0, 25.0)
+    assert np.array_equal(Ka, Ka.T) and np.all(np.diag(Ka) == 1.0)
+
+
+def test_streaming_with_c_block_equals_dense():
+    L = synth_lum(48, 64).astype(float)
+    a = (6, 8, 20.0, 25.0, 5, 6)
+    fd = O.train_dense(L, *a)
+    fs = O.train_streaming(L, *a, tile=700, block_fn=O.affinity_block_c)
+    assert (fd.stages["r"], fd.stages["r2"], fd.eigvals.size) == (fs.stages["r"], fs.stages["r2"], fs.eigvals.size)
+    assert np.allclose(fd.eigvals, fs.eigvals, rtol=1e-9, atol=1e-13)
+    w = [2, 3, 4, 1]
+    assert np.array_equal(O.enhance_luminance(fd, L.astype(np.uint8), w), O.enhance_luminance(fs, L.astype(np.uint8), w))
+
+
+def test_big_oracle_fixtures_are_consistent():
+    """tests/golden/oracle_big.json (made by make_oracle_big.py with the streaming oracle): inputs regenerate to the recorded
+    checksums and the recorded rank cuts sit on the recorded side of 1e-10."""
+    import hashlib
+    import json
+    import sys
+    import cv2
+    from nle_testlib import GOLDEN
+    sys.path.insert(0, GOLDEN)
+    import make_oracle_big
+    fx = json.load(open(os.path.join(GOLDEN, "oracle_big.json")))
+    assert {"c3", "c4", "c5crop"} <= set(fx)
+    for name, f in fx.items():
+        lum, args, weights = make_oracle_big.config(name)
+        assert hashlib.sha1(lum.tobytes()).hexdigest() == f["lum_sha1"], name
+        assert list(args) == f["args"] and (lum.shape[0], lum.shape[1]) == (f["rows"], f["cols"])
+        sel, _ = O.sample_pixels(lum.shape[0], lum.shape[1], args[0], args[1])
+        assert sel.size == f["p"] and hashlib.sha1(sel.astype(np.int32).tobytes()).hexdigest() == f["sel_sha1"]
+        assert len(f["Sq"]) == f["k"] <= args[5] and f["r2"] <= f["r"] <= f["p"]
+        assert f["Ka_cut"][1] >= O.EPS > f["Ka_cut"][2] and f["Wa_cut"][1] >= O.EPS > f["Wa_cut"][2]
+        out = cv2.imread(os.path.join(GOLDEN, f"{name}_oracle_L.png"), cv2.IMREAD_GRAYSCALE)
+        assert out.shape == lum.shape and hashlib.sha1(out.tobytes()).hexdigest() == f["L_sha1"]
+
+
 # ---- streaming (factor form) == dense (literal) --------------------------------------------------
 @pytest.mark.parametrize("case", [(48, 64, 6, 8, 20.0, 25.0, 5, 6), (40, 56, 5, 7, 300.0, 12.0, 8, 40)])
 def test_streaming_equals_dense(case):
