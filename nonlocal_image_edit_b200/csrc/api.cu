@@ -118,7 +118,7 @@ struct nle_b200_filter {
     std::vector<double> S;       // k eigenvalues (host copy)
     DevBuf<double> ascratch, avec;   // apply scratch
     DevBuf<uint8_t> io8_in, io8_out;
-    DevBuf<uint8_t> io_bgr, io_ab;   // BGR staging (3 bytes/pixel, in and out) and the a,b planes of the image being enhanced
+    DevBuf<uint8_t> io_bgr, io_bgr_out, io_ab;   // BGR staging (3 bytes/pixel, in and out); a,b planes only for k > 400
     DevBuf<double> io64_in, io64_out;
     // stages
     DevBuf<double> Ka, lam, rvec_head, c, Wa, Q, la, Gram;
@@ -499,7 +499,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     ws.phase_ms(&f->times_ms[8]);           // tridiagonalisation, divide & conquer, back-transformation (sums)
     f->eig_fallbacks = g_eig_fallbacks - fallbacks0;
 
-    f->ascratch.alloc((size_t)apply_blocks(nloc) * k + 16);
+    f->ascratch.alloc((size_t)apply_blocks(nloc, k) * k + 16);
     f->avec.alloc(4 * (size_t)k + 16);
     if (g_keep_stages) {
         f->Ka.alloc((size_t)p * p); copy_dd(f->Ka.p, Ka.p, (size_t)p * p, s);
@@ -518,18 +518,22 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
 
 // ------------------------------------------------------------------------------------------
 // apply / enhance on device buffers
-static void apply_core(const nle_b200_filter* f, const uint8_t* z8, const double* z64, const double* g_host,
-                       double* out64, uint8_t* out8) {
+static void apply_core(const nle_b200_filter* f, const uint8_t* z8, const double* z64, const uint8_t* zbgr, const double* g_host,
+                       double* out64, uint8_t* out8, uint8_t* outbgr) {
     cudaStream_t s = f->stream;
     const int k = f->k;
     double* tvec = f->avec.p;
     double* gvec = f->avec.p + k;
-    double* gmul = f->avec.p + 2 * (size_t)k;
-    launch_vtz(f->nloc, k, f->V.p, z8, z64, f->ascratch.p, tvec, s);                // V^T z
-    do_allreduce(const_cast<nle_b200_filter*>(f), tvec, (size_t)k);
-    NLE_CUDA(cudaMemcpyAsync(gmul, g_host, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, s));
-    vec_mul(gvec, gmul, tvec, k, s);                                                 // diag(fS) (V^T z)
-    launch_recompose(f->nloc, k, f->V.p, gvec, out64, out8, s);
+    double* fS = f->avec.p + 2 * (size_t)k;
+    NLE_CUDA(cudaMemcpyAsync(fS, g_host, (size_t)k * sizeof(double), cudaMemcpyHostToDevice, s));
+    if (f->allreduce) {
+        launch_vtz(f->nloc, k, f->V.p, z8, z64, zbgr, nullptr, f->ascratch.p, tvec, nullptr, s);          // V^T z (this slab)
+        do_allreduce(const_cast<nle_b200_filter*>(f), tvec, (size_t)k);
+        launch_scale_t(k, tvec, fS, gvec, s);                                                            // diag(fS) (V^T z)
+    } else {
+        launch_vtz(f->nloc, k, f->V.p, z8, z64, zbgr, fS, f->ascratch.p, tvec, gvec, s);
+    }
+    launch_recompose(f->nloc, k, f->V.p, gvec, out64, out8, outbgr, zbgr, s);
 }
 
 static std::vector<double> transform_eigenvalues(const double* S, int k, const double* w, int m) {
@@ -947,7 +951,7 @@ int nle_b200_apply(const nle_b200_filter* f, const double* channel, long long n_
         const size_t n = (size_t)f->nloc;
         if (ff->io64_in.n < n) { ff->io64_in.alloc(n); ff->io64_out.alloc(n); }
         ff->io64_in.upload(channel, n, f->stream);
-        apply_core(f, nullptr, ff->io64_in.p, fS, ff->io64_out.p, nullptr);
+        apply_core(f, nullptr, ff->io64_in.p, nullptr, fS, ff->io64_out.p, nullptr, nullptr);
         ff->io64_out.download(out, n, f->stream);
         NLE_CUDA(cudaStreamSynchronize(f->stream));
     });
@@ -959,7 +963,7 @@ int nle_b200_enhance_luminance_u8_dev(const nle_b200_filter* f, const uint8_t* l
         if (!f || !lum_slab_dev || !weights || !out_slab_dev) throw InvalidArg{"null pointer"};
         if (m < 1) throw InvalidArg{"at least one weight is required"};
         auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);             // filter.cpp:428
-        apply_core(f, lum_slab_dev, nullptr, fS.data(), nullptr, out_slab_dev);     // :431-436
+        apply_core(f, lum_slab_dev, nullptr, nullptr, fS.data(), nullptr, out_slab_dev, nullptr);     // :431-436
     });
 }
 
@@ -975,7 +979,7 @@ int nle_b200_enhance_luminance_u8(const nle_b200_filter* f, const uint8_t* lum, 
         ff->io8_in.upload(lum, n, f->stream);
         tr("host enhance: upload");
         auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);
-        apply_core(f, ff->io8_in.p, nullptr, fS.data(), nullptr, ff->io8_out.p);
+        apply_core(f, ff->io8_in.p, nullptr, nullptr, fS.data(), nullptr, ff->io8_out.p, nullptr);
         tr("host enhance: apply");
         ff->io8_out.download(out, n, f->stream);
         NLE_CUDA(cudaStreamSynchronize(f->stream));
@@ -1052,14 +1056,20 @@ int nle_b200_enhance_bgr_u8(const nle_b200_filter* f, const uint8_t* bgr_slab, i
         if (m < 1) throw InvalidArg{"at least one weight is required"};
         auto* ff = const_cast<nle_b200_filter*>(f);
         const size_t n = (size_t)f->nloc;
-        if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
-        if (ff->io_bgr.n < 3 * n) { ff->io_bgr.alloc(3 * n); ff->io_ab.alloc(2 * n); }
+        if (ff->io_bgr.n < 3 * n) { ff->io_bgr.alloc(3 * n); ff->io_bgr_out.alloc(3 * n); }
         ff->io_bgr.upload(bgr_slab, 3 * n, f->stream);
-        launch_bgr2lab(ff->io_bgr.p, (long long)n, ff->io8_in.p, ff->io_ab.p, f->stream);          // filter.cpp:422-426
         auto fS = transform_eigenvalues(f->S.data(), f->k, weights, m);                            // :428
-        apply_core(f, ff->io8_in.p, nullptr, fS.data(), nullptr, ff->io8_out.p);                   // :431-436
-        launch_lab2bgr(ff->io8_out.p, ff->io_ab.p, (long long)n, ff->io_bgr.p, f->stream);          // :438-440
-        ff->io_bgr.download(out_slab, 3 * n, f->stream);
+        if (apply_tma_supported(f->k)) {
+            // BGR2Lab (:422-426) fused into the V^T z pass; clamp, round and Lab2BGR (:434-440) into the V g pass
+            apply_core(f, nullptr, nullptr, ff->io_bgr.p, fS.data(), nullptr, nullptr, ff->io_bgr_out.p);
+        } else {
+            if (ff->io8_in.n < n) { ff->io8_in.alloc(n); ff->io8_out.alloc(n); }
+            if (ff->io_ab.n < 2 * n) ff->io_ab.alloc(2 * n);
+            launch_bgr2lab(ff->io_bgr.p, (long long)n, ff->io8_in.p, ff->io_ab.p, f->stream);
+            apply_core(f, ff->io8_in.p, nullptr, nullptr, fS.data(), nullptr, ff->io8_out.p, nullptr);
+            launch_lab2bgr(ff->io8_out.p, ff->io_ab.p, (long long)n, ff->io_bgr_out.p, f->stream);
+        }
+        ff->io_bgr_out.download(out_slab, 3 * n, f->stream);
         NLE_CUDA(cudaStreamSynchronize(f->stream));
     });
 }
@@ -1076,7 +1086,7 @@ int nle_b200_denoise_channel_u8(const nle_b200_filter* f, const uint8_t* chan, i
         ff->io8_in.upload(chan, n, f->stream);
         std::vector<double> te(f->k);
         for (int i = 0; i < f->k; ++i) te[i] = std::pow(std::min(f->S[i], 1.0), kpow);   // filter.cpp:378-385
-        apply_core(f, ff->io8_in.p, nullptr, te.data(), nullptr, ff->io8_out.p);
+        apply_core(f, ff->io8_in.p, nullptr, nullptr, te.data(), nullptr, ff->io8_out.p, nullptr);
         ff->io8_out.download(out, n, f->stream);
         NLE_CUDA(cudaStreamSynchronize(f->stream));
     });

@@ -114,97 +114,6 @@ void launch_scatter_rows(const AffinityTables& t, const int32_t* sel, int i0, in
 }
 
 // =============================================================================================
-// apply (filter.cpp:445-458):  out = V (g o (V^T z)),  V row-major (N x k).
-constexpr int AP_PIX = 1024;   // pixels per CTA in the V^T z pass
-
-int apply_blocks(long long nloc) { return cdiv(nloc, AP_PIX); }
-
-__global__ void __launch_bounds__(256)
-vtz_kernel(long long nloc, int k, const double* __restrict__ V, const uint8_t* __restrict__ z8,
-           const double* __restrict__ z64, double* __restrict__ partial) {
-    // thread v-lane layout: 256 threads = 8 pixel-lanes x 32 v-lanes; each reads V rows coalesced.
-    extern __shared__ double red[];   // 8 * kpad
-    const int vl = threadIdx.x & 31, pl = threadIdx.x >> 5;
-    const long long base = (long long)blockIdx.x * AP_PIX;
-    const int kpad = ((k + 31) / 32) * 32;
-    for (int vb = 0; vb < k; vb += 32) {
-        int v = vb + vl;
-        double acc = 0.0;
-        if (v < k) {
-            for (int q = pl; q < AP_PIX; q += 8) {
-                long long j = base + q;
-                if (j >= nloc) break;
-                double z = z8 ? (double)z8[j] : z64[j];
-                acc = fma(V[(size_t)j * k + v], z, acc);
-            }
-        }
-        red[pl * kpad + vb + vl] = acc;
-    }
-    __syncthreads();
-    for (int v = threadIdx.x; v < k; v += 256) {
-        double s = 0.0;
-        for (int q = 0; q < 8; ++q) s += red[q * kpad + v];
-        partial[(size_t)blockIdx.x * k + v] = s;
-    }
-}
-
-__global__ void vtz_final_kernel(const double* __restrict__ partial, int nblocks, int k,
-                                 double* __restrict__ tout) {
-    int v = blockIdx.x * blockDim.x + threadIdx.x;
-    if (v >= k) return;
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * k + v];
-    tout[v] = s;
-}
-
-void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, const double* z_f64,
-                double* scratch, double* t_out, cudaStream_t s) {
-    int nb = apply_blocks(nloc);
-    int kpad = ((k + 31) / 32) * 32;
-    vtz_kernel<<<nb, 256, (size_t)8 * kpad * sizeof(double), s>>>(nloc, k, V, z_u8, z_f64, scratch);
-    NLE_LAUNCH_CHECK();
-    vtz_final_kernel<<<cdiv(k, 64), 64, 0, s>>>(scratch, nb, k, t_out);
-    NLE_LAUNCH_CHECK();
-}
-
-__global__ void __launch_bounds__(256)
-recompose_kernel(long long nloc, int k, const double* __restrict__ V, const double* __restrict__ g,
-                 double* __restrict__ out64, uint8_t* __restrict__ out8) {
-    // one warp per group of pixels; lanes stride over k so V rows are read coalesced
-    extern __shared__ double gs[];
-    for (int v = threadIdx.x; v < k; v += 256) gs[v] = g[v];
-    __syncthreads();
-    const int lane = threadIdx.x & 31;
-    long long warp = ((long long)blockIdx.x * 256 + threadIdx.x) >> 5;
-    long long nwarps = ((long long)gridDim.x * 256) >> 5;
-    for (long long j = warp; j < nloc; j += nwarps) {
-        const double* vr = V + (size_t)j * k;
-        double acc = 0.0;
-        for (int v = lane; v < k; v += 32) acc = fma(vr[v], gs[v], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) {
-            if (out64) out64[j] = acc;
-            if (out8) {
-                // cv::max(.,0), cv::min(.,255), convertTo(CV_8U) = cvRound = round half to even
-                double c = fmin(fmax(acc, 0.0), 255.0);
-                out8[j] = (uint8_t)__double2int_rn(c);
-            }
-        }
-    }
-}
-
-void launch_recompose(long long nloc, int k, const double* V, const double* g, double* out_f64,
-                      uint8_t* out_u8, cudaStream_t s) {
-    if (nloc <= 0) return;
-    long long warps_needed = nloc;
-    int grid = (int)std::min<long long>((warps_needed + 7) / 8, (long long)sm_count() * 16);
-    if (grid < 1) grid = 1;
-    recompose_kernel<<<grid, 256, (size_t)(k > 0 ? k : 1) * sizeof(double), s>>>(nloc, k, V, g, out_f64, out_u8);
-    NLE_LAUNCH_CHECK();
-}
-
-// =============================================================================================
 __global__ void fill_kernel(double* p, long long n, double v) {
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i < n) p[i] = v;

@@ -66,15 +66,22 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
 void launch_scatter_rows(const AffinityTables& t, const int32_t* sel, int i0, int n, const double* src,
                          int ld, int k, double* V, cudaStream_t s);
 
-// apply:  tpart/t = V^T z ; out = V (g)   with optional clamp+round to u8.
-// z_u8 or z_f64 (exactly one non-null).  t_out: k.  scratch: nblocks*k doubles.
-int apply_blocks(long long nloc);
-void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, const double* z_f64,
-                double* scratch, double* t_out, cudaStream_t s);
-void launch_recompose(long long nloc, int k, const double* V, const double* g, double* out_f64,
-                      uint8_t* out_u8, cudaStream_t s);
+// The HBM-bound output path (apply_kernels.cu): both passes stream V (nloc x k, row-major) through shared memory with TMA
+// bulk copies; the colour conversions of NLEFilter::enhance are fused into them.
+//   launch_vtz        t = V^T z (and g = fS o t when fS != nullptr); exactly one of z_u8 / z_f64 / z_bgr non-null (z_bgr:
+//                     interleaved 8-bit BGR, z = L of its Lab conversion).  scratch: apply_blocks(nloc, k) * k doubles.
+//   launch_scale_t    g = fS o t (after the all-reduce of t in the sharded path)
+//   launch_recompose  out = V g; epilogue by the non-null output: out_f64 | out_u8 (clamp, round half to even) | out_bgr
+//                     (clamp, round, Lab2BGR with the a, b channels recomputed from bgr_in)
+bool apply_tma_supported(int k);
+int apply_blocks(long long nloc, int k);
+void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, const double* z_f64, const uint8_t* z_bgr,
+                const double* fS, double* scratch, double* t_out, double* g_out, cudaStream_t s);
+void launch_scale_t(int k, const double* t, const double* fS, double* g, cudaStream_t s);
+void launch_recompose(long long nloc, int k, const double* V, const double* g, double* out_f64, uint8_t* out_u8,
+                      uint8_t* out_bgr, const uint8_t* bgr_in, cudaStream_t s);
 
-// 8-bit BGR <-> Lab, byte-exact with cv::cvtColor on CV_8UC3 (lab.cu).  bgr: npix x 3 interleaved; L: npix; ab: npix x 2.
+// 8-bit BGR <-> Lab, byte-exact with cv::cvtColor on CV_8UC3 (apply_kernels.cu).  bgr: npix x 3 interleaved; L: npix; ab: npix x 2.
 void launch_bgr2lab(const uint8_t* bgr, long long npix, uint8_t* L, uint8_t* ab, cudaStream_t s);
 void launch_lab2bgr(const uint8_t* L, const uint8_t* ab, long long npix, uint8_t* bgr, cudaStream_t s);
 
