@@ -337,8 +337,11 @@ def _tiles(n, tile):
 
 def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx: float, hy: float,
                     n_sinkhorn_iter: int = 10, n_eigen_vectors: int = 5,
-                    tile: int = 16384, slab=None, allreduce=None, block_fn=None) -> TrainedFilter:
+                    tile: int = 16384, slab=None, allreduce=None, block_fn=None, ka_fn=None,
+                    gram_fn=None) -> TrainedFilter:
     """block_fn: affinity_block (default, NumPy) or affinity_block_c (same loop in C, threaded).
+    ka_fn / gram_fn: hooks of scripts/precision_probe.py ONLY (Ka -> perturbed Ka; X = Kab_tile * c -> X X^T evaluated in a
+    reduced-precision arithmetic); the oracle proper never passes them.
     slab=(row0,row1) restricts every pixel sum to the image rows owned by one rank and
     `allreduce(np.ndarray)` (in-place sum over ranks) completes them: the CPU model of the row-sharded
     multi-GPU path.  The returned eigvecs then cover only the slab's pixels."""
@@ -363,6 +366,8 @@ def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx:
         return blk(z, ncols, sel, rest[s:e], hx, hy)
 
     Ka = blk(z, ncols, sel, sel, hx, hy)
+    if ka_fn is not None:
+        Ka = ka_fn(Ka)
     U, lam = eigen_decomposition(Ka)                      # A.3
     r = lam.size
     inv_lam = 1.0 / lam
@@ -410,7 +415,7 @@ def train_streaming(lum: np.ndarray, n_row_samples: int, n_col_samples: int, hx:
     Gp = np.zeros((p, p))                                 # sum_j c_j^2 k_j k_j^T over rest pixels
     for s, e in _tiles(nrest, tile):
         K = kb(s, e) * c_rest[None, s:e]
-        Gp += K @ K.T
+        Gp += K @ K.T if gram_fn is None else gram_fn(K)
     allreduce(Gp)
     UL = U * inv_lam[None, :]                             # p x r : U Lam^-1
     G = UL.T @ Gp @ UL
