@@ -5,7 +5,8 @@
 // V is nloc x k doubles, row-major and dense, so any range of rows is ONE contiguous byte range: both passes stream it
 // through shared memory with the TMA engine's 1-D bulk copy (cp.async.bulk.shared::cluster.global + mbarrier
 // complete_tx; SASS UBLKCP / SYNCS.ARRIVE.TRANS64) in a ring of up to 4 stages of ~50 KB, one persistent CTA per SM.
-// No thread issues a global load for V; the 128 threads only read shared memory:
+// No thread issues a global load for V; the 256 threads only read shared memory (four independent partial sums per
+// thread: with 8 warps per SM the FP64 FMA latency of a single dependent chain was the bound, profiles/r2c):
 //   vtz_tma_kernel        t = V^T z.  Thread = (column v, row group): consecutive lanes read consecutive doubles of a row.
 //   recompose_tma_kernel  out_j = V_j . g, g = fS o t.  Thread = row, columns rotated by the lane so that the 16 lanes of
 //                         a half-warp fall into 16 different bank pairs although consecutive rows are k doubles apart.
@@ -118,7 +119,7 @@ lab2bgr_kernel(const uint8_t* __restrict__ L, const uint8_t* __restrict__ ab, lo
 
 // ---------------------------------------------------------------------------------------------
 // TMA ring: 1-D bulk copies global -> shared, completion on an mbarrier per stage.
-constexpr int AP_THREADS = 128;
+constexpr int AP_THREADS = 256;
 constexpr int AP_MAXSTAGES = 4;
 constexpr int AP_KMAX = 400;            // widest V row the shared-memory ring holds (32 rows x 400 doubles = 100 KB x 2 stages)
 
@@ -206,7 +207,7 @@ vtz_tma_kernel(long long nloc, int k, const double* __restrict__ V, const uint8_
             const long long tile = blockIdx.x + s * G;
             if (tile < geo.ntiles) issue_tile(ring + (size_t)s * geo.stage_doubles, V, tile * TR, tile_rows(tile), k, bars + s);
         }
-    // thread -> (column, row group): k <= 128: ng = 128 / k groups of k threads; k > 128: one group, NV columns per thread
+    // thread -> (column, row group): k <= 256: ng = 256 / k groups of k threads; k > 256: one group, NV columns per thread
     const int ng = (k <= AP_THREADS) ? AP_THREADS / k : 1;
     const int grp = (k <= AP_THREADS) ? tid / k : 0;
     const int v0 = (k <= AP_THREADS) ? tid - grp * k : tid;
@@ -237,7 +238,26 @@ vtz_tma_kernel(long long nloc, int k, const double* __restrict__ V, const uint8_
         mbar_wait(bars + s, parity);
         const double* tileV = ring + (size_t)s * geo.stage_doubles;
         if (active) {
-            for (int r = grp; r < nrows; r += ng) {
+            // rows grp, grp + ng, ...: four rows in flight per step (independent accumulators, fixed combination order)
+            double a1[NV], a2[NV], a3[NV];
+#pragma unroll
+            for (int i = 0; i < NV; ++i) a1[i] = a2[i] = a3[i] = 0.0;
+            int r = grp;
+            for (; r + 3 * ng < nrows; r += 4 * ng) {
+                const double z0 = zt[r], z1 = zt[r + ng], z2 = zt[r + 2 * ng], z3 = zt[r + 3 * ng];
+                const double* row = tileV + (size_t)r * k;
+#pragma unroll
+                for (int i = 0; i < NV; ++i) {
+                    const int v = v0 + i * AP_THREADS;
+                    if (NV == 1 || v < k) {
+                        acc[i] = fma(row[v], z0, acc[i]);
+                        a1[i] = fma(row[(size_t)ng * k + v], z1, a1[i]);
+                        a2[i] = fma(row[(size_t)2 * ng * k + v], z2, a2[i]);
+                        a3[i] = fma(row[(size_t)3 * ng * k + v], z3, a3[i]);
+                    }
+                }
+            }
+            for (; r < nrows; r += ng) {
                 const double z = zt[r];
                 const double* row = tileV + (size_t)r * k;
 #pragma unroll
@@ -246,6 +266,8 @@ vtz_tma_kernel(long long nloc, int k, const double* __restrict__ V, const uint8_
                     if (NV == 1 || v < k) acc[i] = fma(row[v], z, acc[i]);
                 }
             }
+#pragma unroll
+            for (int i = 0; i < NV; ++i) acc[i] += (a1[i] + a2[i]) + a3[i];
         }
         __syncthreads();                       // every thread is done with stage s (V tile and z tile)
         const long long next = tile + (long long)S * G;
@@ -307,7 +329,7 @@ recompose_tma_kernel(long long nloc, int k, const double* __restrict__ V, const 
             const long long tile = last - s * G;
             if (tile >= 0) issue_tile(ring + (size_t)s * geo.stage_doubles, V, tile * TR, tile_rows(tile), k, bars + s);
         }
-    // thread -> (row, column part): nparts = 128 / TR threads share a row and split its columns
+    // thread -> (row, column part): nparts = 256 / TR threads share a row and split its columns
     const int nparts = AP_THREADS / TR;
     const int rloc = tid % TR, prt = tid / TR;
     const int rot = (k & 1) ? 2 : 1;            // (k + rot) odd: the 16 lanes of a half-warp hit 16 different bank pairs
@@ -320,12 +342,23 @@ recompose_tma_kernel(long long nloc, int k, const double* __restrict__ V, const 
         const double* row = ring + (size_t)s * geo.stage_doubles + (size_t)rloc * k;
         double acc = 0.0;
         if (rloc < nrows) {
+            // this thread's columns: (rot * rloc + prt + m * nparts) mod k, m = 0, 1, ...; four partial sums in flight
+            double b1 = 0.0, b2 = 0.0, b3 = 0.0;
             int v = (rot * rloc + prt) % k;
-            for (int i = prt; i < k; i += nparts) {
-                acc = fma(row[v], gs[v], acc);
-                v += nparts;
-                if (v >= k) v -= k;
+            auto step = [&](int& vv) { const int cur = vv; vv += nparts; if (vv >= k) vv -= k; return cur; };
+            int i = prt;
+            for (; i + 3 * nparts < k; i += 4 * nparts) {
+                const int c0 = step(v), c1 = step(v), c2 = step(v), c3 = step(v);
+                acc = fma(row[c0], gs[c0], acc);
+                b1 = fma(row[c1], gs[c1], b1);
+                b2 = fma(row[c2], gs[c2], b2);
+                b3 = fma(row[c3], gs[c3], b3);
             }
+            for (; i < k; i += nparts) {
+                const int c0 = step(v);
+                acc = fma(row[c0], gs[c0], acc);
+            }
+            acc += (b1 + b2) + b3;
         }
         if (nparts > 1) {
             part[tid] = acc;
@@ -427,7 +460,7 @@ void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, con
     if (apply_tma_supported(k)) {
         const ApplyGeom g = apply_geometry(nloc, k);
         nb = g.grid;
-        const int nv = k <= AP_THREADS ? 1 : (k <= 2 * AP_THREADS ? 2 : 4);
+        const int nv = k <= AP_THREADS ? 1 : 2;                 // k <= AP_KMAX = 400 < 2 * AP_THREADS
         const size_t smem = vtz_smem(g, nv);
         const int zmode = z_bgr ? Z_BGR : (z_u8 ? Z_U8 : Z_F64);
         const uint8_t* z8 = z_bgr ? z_bgr : z_u8;
@@ -435,7 +468,7 @@ void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, con
             NLE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             kern<<<g.grid, AP_THREADS, smem, s>>>(nloc, k, V, z8, z_f64, zmode, g, scratch);
         };
-        if (nv == 1) go(vtz_tma_kernel<1>); else if (nv == 2) go(vtz_tma_kernel<2>); else go(vtz_tma_kernel<4>);
+        if (nv == 1) go(vtz_tma_kernel<1>); else go(vtz_tma_kernel<2>);
         NLE_LAUNCH_CHECK();
     } else {
         if (z_bgr) throw Unsupported{"fused BGR apply needs k <= " + std::to_string(AP_KMAX)};
