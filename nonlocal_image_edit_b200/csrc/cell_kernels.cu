@@ -215,7 +215,6 @@ cell_hist_kernel(AffinityTables t, const double* __restrict__ cvec, const int* _
     }
 }
 
-constexpr int GC_WARPS = 8;
 
 // One warp per task = (pair (b,b'), a-block, a'-block) x K split.  Tile: T x T with T = 8*MT grid rows.
 //   A[k][a ] = Er[row_k][a ] * Gt[|lev_k - Y[a ][b ]|]
@@ -223,16 +222,18 @@ constexpr int GC_WARPS = 8;
 // DMMA fragments (lane = 4g + tq): A elem (m = g, k = tq), B elem (k = tq, n = g), D elems (g, 2tq), (g, 2tq+1).
 // The 256-entry Gt table is replicated 16x in shared memory, interleaved so that lane L always reads bank pair
 // (L & 15): the 64-bit look-ups of a warp (two 16-lane phases) are conflict-free whatever the levels are.
-template <int MT, int NT, bool SKIP>
-__global__ void __launch_bounds__(GC_WARPS * 32, 1)
+// WARPS per CTA: 12 (three warps per sub-core) whenever the tile fits 168 registers without spilling -- up to 5 x 5
+// (ptxas: 168 registers, 0 spills); the 6 x 4 / 7 x 4 tiles of nR > 40 keep 8 warps (224 registers).
+template <int MT, int NT, bool SKIP, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
 gram_cells_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __restrict__ cell_lev,
                   const double* __restrict__ Hh, int ld, int nabA, int nabB, int ntasks, int nsplit, int accumulate,
                   double* __restrict__ part) {
     __shared__ double Gs16[256 * 16];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (int e = tid; e < 256 * 16; e += GC_WARPS * 32) Gs16[e] = t.Gt[e >> 4];
+    for (int e = tid; e < 256 * 16; e += WARPS * 32) Gs16[e] = t.Gt[e >> 4];
     __syncthreads();
-    const int task = blockIdx.x * GC_WARPS + warp;
+    const int task = blockIdx.x * WARPS + warp;
     if (task >= ntasks) return;
     const int nC = t.nC, nR = t.nR;
     constexpr int TA = 8 * MT, TB = 8 * NT;
@@ -367,7 +368,7 @@ __global__ void gram_cells_reduce_kernel(const double* __restrict__ part, int p,
 }
 
 struct CellGeom {
-    int npairs, ld, MT, NT, TA, TB, nabA, nabB, ntasks, ncta, nsplit, capc, rows_batch;
+    int npairs, ld, MT, NT, TA, TB, nabA, nabB, ntasks, warps, ncta, nsplit, capc, rows_batch;
     size_t hh_doubles, part_doubles, lev_bytes, int_count;
 };
 
@@ -386,7 +387,8 @@ CellGeom cell_geometry(const AffinityTables& t) {
     }
     g.TA = 8 * g.MT; g.TB = 8 * g.NT;
     g.ntasks = g.npairs * g.nabA * g.nabB;
-    g.ncta = cdiv(g.ntasks, GC_WARPS);
+    g.warps = tiles <= 5 ? 12 : 8;
+    g.ncta = cdiv(g.ntasks, g.warps);
     g.nsplit = std::max(1, (7 * sm_count()) / g.ncta);
     g.nsplit = std::min(g.nsplit, std::max(1, t.nrows));
     g.capc = std::min(256, (t.cols + 3) & ~3);
@@ -636,7 +638,8 @@ size_t gram_cells_scratch_doubles(const AffinityTables& t) {
 template <int MT, int NT>
 static void launch_gc(const AffinityTables& tb, const CellGeom& g, const int* koff, const uint8_t* cell_lev,
                       const double* Hh, int accumulate, double* part, cudaStream_t s) {
-    gram_cells_kernel<MT, NT, (MT != NT)><<<dim3(g.ncta, g.nsplit), GC_WARPS * 32, 0, s>>>(tb, koff, cell_lev, Hh, g.ld, g.nabA, g.nabB,
+    constexpr int WARPS = (MT <= 5 && NT <= 5 && MT == NT) ? 12 : 8;      // must match cell_geometry's g.warps
+    gram_cells_kernel<MT, NT, (MT != NT), WARPS><<<dim3(g.ncta, g.nsplit), WARPS * 32, 0, s>>>(tb, koff, cell_lev, Hh, g.ld, g.nabA, g.nabB,
                                                                                 g.ntasks, g.nsplit, accumulate, part);
     NLE_LAUNCH_CHECK();
 }

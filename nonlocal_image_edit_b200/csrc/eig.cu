@@ -46,6 +46,28 @@ __global__ void eig_symmetrize_kernel(const double* __restrict__ M, int ldm, int
     rowsum[i] = acc;
 }
 
+// As(i,j) = As(j,i) = M(i,j) for i >= j (the lower triangle defines the matrix, as Eigen's SelfAdjointEigenSolver reads it);
+// 32 x 32 tiles of the lower triangle, both writes coalesced through a shared-memory transpose.
+__global__ void __launch_bounds__(256) eig_symmetrize_tiled_kernel(const double* __restrict__ M, int ldm, int n, double* __restrict__ As) {
+    __shared__ double tile[32][33];
+    const int bi = blockIdx.x, bj = blockIdx.y;
+    if (bj > bi) return;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int q = ty; q < 32; q += 8) {
+        const int i = bi * 32 + tx, j = bj * 32 + q;
+        double v = 0.0;
+        if (i < n && j < n) v = (i >= j) ? M[i + (size_t)j * ldm] : M[j + (size_t)i * ldm];   // diagonal tiles: mirror in place
+        tile[q][tx] = v;
+        if (i < n && j < n) As[i + (size_t)j * n] = v;
+    }
+    if (bi == bj) return;
+    __syncthreads();
+    for (int q = ty; q < 32; q += 8) {
+        const int j = bj * 32 + tx, i = bi * 32 + q;      // As(j, i) = tile value of (i, j)
+        if (i < n && j < n) As[j + (size_t)i * n] = tile[tx][q];
+    }
+}
+
 __global__ void eig_sigma_kernel(const double* __restrict__ rowsum, int n, double* __restrict__ sigma) {
     __shared__ double red[256];
     double m = 0.0;
@@ -459,7 +481,7 @@ static bool sym_eig_direct(const double* M, int ldm, int n, double eps, double* 
     if ((size_t)ws.As.n < (size_t)n * n) ws.As.alloc((size_t)n * n);
     if ((size_t)ws.lam_unsorted.n < (size_t)n + 8) ws.lam_unsorted.alloc(n + 8);
     if ((size_t)ws.order.n < (size_t)n) ws.order.alloc(n);
-    eig_symmetrize_kernel<<<cdiv(n, 128), 128, 0, s>>>(M, ldm, n, ws.As.p, ws.lam_unsorted.p);
+    eig_symmetrize_tiled_kernel<<<dim3(cdiv(n, 32), cdiv(n, 32)), 256, 0, s>>>(M, ldm, n, ws.As.p);
     NLE_LAUNCH_CHECK();
     double* lam = nullptr;
     double* vec = nullptr;
