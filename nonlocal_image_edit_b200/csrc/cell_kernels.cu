@@ -414,7 +414,9 @@ CellGeom cell_geometry(const AffinityTables& t) {
 //                      DMMA with the cell's pixels (8 at a time) as the M tile, K = nC; FX is streamed once
 // Work: K_cells*p*k' + N*nC*k' multiply-adds instead of N*p*k' (extension_dmma_kernel).
 constexpr int XC_N = 56;          // eigenvector columns per block (7 DMMA n-tiles)
-constexpr int XC_CELLS = 256;     // cells per sub-tile of ext_fx_kernel (8 warps x 4 m-tiles)
+constexpr int XC_WARPS = 12;       // three warps per sub-core: the 4 x 7 tile fits 168 registers
+constexpr int XC_THREADS = XC_WARPS * 32;
+constexpr int XC_CELLS = XC_WARPS * 32;   // cells per sub-tile of ext_fx_kernel (XC_WARPS warps x 4 m-tiles)
 constexpr int XC_SUB = 4;         // sub-tiles per CTA (the Y slice and the Er rows are staged once for all of them)
 constexpr int XC_ERROWS = 64;     // image rows whose Er rows fit the staging area
 
@@ -468,8 +470,8 @@ ext_index_kernel(const uint8_t* __restrict__ lum, int nrows, int W, const int* _
     }
 }
 
-// grid (ceil(cap_cells / 256), nC, column blocks); warp = 32 cells (4 m-tiles) x 56 columns (7 n-tiles).
-__global__ void __launch_bounds__(256, 1)
+// grid (ceil(cap_cells / (XC_CELLS * XC_SUB)), nC, column blocks); warp = 32 cells (4 m-tiles) x 56 columns (7 n-tiles).
+__global__ void __launch_bounds__(XC_THREADS, 1)
 ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __restrict__ cell_lev,
               const int* __restrict__ cell_row, const double* __restrict__ Yt, int kp, double* __restrict__ FX) {
     extern __shared__ double xsm[];
@@ -485,19 +487,19 @@ ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __r
     const int K = koff[t.nrows];
     const int k0 = blockIdx.x * (XC_CELLS * XC_SUB);
     if (k0 >= K) return;
-    Gs[tid] = t.Gt[tid];
-    for (int e = tid; e < nR4 * XC_N; e += 256) {
+    if (tid < 256) Gs[tid] = t.Gt[tid];
+    for (int e = tid; e < nR4 * XC_N; e += XC_THREADS) {
         const int a = e / XC_N, m = e - a * XC_N;
         Ys[e] = a < nR ? Yt[(size_t)(a * nC + b) * kp + vb * XC_N + m] : 0.0;
     }
-    for (int a = tid; a < nR4; a += 256) ysl[a] = a < nR ? (int)t.Ysel[a * nC + b] : 0;
+    for (int a = tid; a < nR4; a += XC_THREADS) ysl[a] = a < nR ? (int)t.Ysel[a * nC + b] : 0;
     // cells are ordered by image row: the CTA's cells span rows [row_first, row_last]; their Er rows are staged in shared
     // memory when there are at most XC_ERROWS of them (ncu: 33 % of the samples sat on the Er look-up in global memory)
     const int row_first = cell_row[k0];
     const int row_last = cell_row[min(K, k0 + XC_CELLS * XC_SUB) - 1];
     const bool er_smem = row_last - row_first < XC_ERROWS;
     if (er_smem)
-        for (int e = tid; e < (row_last - row_first + 1) * nR4; e += 256) {
+        for (int e = tid; e < (row_last - row_first + 1) * nR4; e += XC_THREADS) {
             const int r = e / nR4, a = e - r * nR4;
             ErS[e] = a < nR ? t.Er[(size_t)(t.row0 + row_first + r) * nR + a] : 0.0;
         }
@@ -726,7 +728,7 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
                                                                              cell_pstart, cell_pcount, sorted);
         NLE_LAUNCH_CHECK();
         const int cap_cells = g.capc * tb.nrows;
-        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), 256, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX);
+        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), XC_THREADS, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX);
         NLE_LAUNCH_CHECK();
         ext_pix_kernel<<<sm_count() * 8, 256, 0, s>>>(tb, koff, cell_row, cell_pstart, cell_pcount, sorted, cb, FX, g.kp, g.nvb, k, Vb);
         NLE_LAUNCH_CHECK();
