@@ -387,7 +387,7 @@ CellGeom cell_geometry(const AffinityTables& t) {
     }
     g.TA = 8 * g.MT; g.TB = 8 * g.NT;
     g.ntasks = g.npairs * g.nabA * g.nabB;
-    g.warps = tiles <= 5 ? 12 : 8;
+    g.warps = 12;
     g.ncta = cdiv(g.ntasks, g.warps);
     g.nsplit = std::max(1, (7 * sm_count()) / g.ncta);
     g.nsplit = std::min(g.nsplit, std::max(1, t.nrows));
@@ -640,7 +640,7 @@ size_t gram_cells_scratch_doubles(const AffinityTables& t) {
 template <int MT, int NT>
 static void launch_gc(const AffinityTables& tb, const CellGeom& g, const int* koff, const uint8_t* cell_lev,
                       const double* Hh, int accumulate, double* part, cudaStream_t s) {
-    constexpr int WARPS = (MT <= 5 && NT <= 5 && MT == NT) ? 12 : 8;      // must match cell_geometry's g.warps
+    constexpr int WARPS = 12;      // must match cell_geometry's g.warps
     gram_cells_kernel<MT, NT, (MT != NT), WARPS><<<dim3(g.ncta, g.nsplit), WARPS * 32, 0, s>>>(tb, koff, cell_lev, Hh, g.ld, g.nabA, g.nabB,
                                                                                 g.ntasks, g.nsplit, accumulate, part);
     NLE_LAUNCH_CHECK();
