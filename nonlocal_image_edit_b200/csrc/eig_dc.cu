@@ -331,6 +331,8 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
     double* w = Wb;
     double* cn = Vb;           // updated next column -> next reflector (first reflector is built here, then becomes v)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    // (Which CTA owns which column does not matter for speed: striding the logical CTA index over the clusters / GPCs changed
+    // nothing, profiles/r2k_trd_experiments.md.)
     const int G = gridDim.x, b = blockIdx.x;
     const int q_last = (n - 1 - b) / G;          // b < G <= n
     const int c_last = b + G * q_last;           // the largest column this CTA owns
@@ -1385,28 +1387,48 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const void* kfn = kprof ? (const void*)tridiag_cluster_kernel<true> : (const void*)tridiag_cluster_kernel<false>;
         // the grid depends on how many clusters fit, which depends on the shared memory, which depends on the grid:
-        // start from one CTA per SM and shrink until the launch configuration is consistent
-        int G = (std::min(sm_count(), n) / S) * S;
-        for (int it = 0; it < 4 && G >= S; ++it) {
-            const int qmax = cdiv(n, G);
-            const size_t smem = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
-            if (smem > (size_t)max_smem) break;
+        // start from one CTA per SM and shrink until the launch configuration is consistent.  The occupancy query is a
+        // slow host call (the GPU idles meanwhile): its answer is cached per (device, n).
+        struct Cfg { int dev, n, G; size_t smem; };
+        static thread_local Cfg cache[8] = {};
+        static thread_local int cache_next = 0;
+        int G = 0;
+        size_t smem = 0;
+        for (const Cfg& c : cache)
+            if (c.G > 0 && c.dev == dev && c.n == n) { G = c.G; smem = c.smem; }
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[2];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        at[1].id = cudaLaunchAttributeCooperative;     // only for its co-residency guarantee
+        at[1].val.cooperative = 1;
+        cfg.blockDim = dim3(kTrdThreads);
+        cfg.stream = s;
+        cfg.attrs = at;
+        if (G == 0) {
+            int Gt = (std::min(sm_count(), n) / S) * S;
+            for (int it = 0; it < 4 && Gt >= S; ++it) {
+                const int qmax = cdiv(n, Gt);
+                const size_t sm = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
+                if (sm > (size_t)max_smem) break;
+                NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                cfg.gridDim = dim3(Gt);
+                cfg.dynamicSmemBytes = sm;
+                cfg.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &cfg) != cudaSuccess) { cudaGetLastError(); break; }
+                if (ncl * S < Gt) { Gt = ncl * S; continue; }      // fewer clusters fit: retry with the smaller grid
+                G = Gt;
+                smem = sm;
+                cache[cache_next] = Cfg{dev, n, G, smem};
+                cache_next = (cache_next + 1) % 8;
+                break;
+            }
+        }
+        while (G >= S) {
             NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cudaLaunchConfig_t cfg = {};
             cfg.gridDim = dim3(G);
-            cfg.blockDim = dim3(kTrdThreads);
             cfg.dynamicSmemBytes = smem;
-            cfg.stream = s;
-            cudaLaunchAttribute at[2];
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = S; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            at[1].id = cudaLaunchAttributeCooperative;     // only for its co-residency guarantee
-            at[1].val.cooperative = 1;
-            cfg.attrs = at;
-            cfg.numAttrs = 1;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, kfn, &cfg) != cudaSuccess) { cudaGetLastError(); break; }
-            if (ncl * S < G) { G = ncl * S; continue; }      // fewer clusters fit: retry with the smaller grid
             cfg.numAttrs = 2;
             const size_t cells = 4 * (size_t)n + 8;          // + 8 cells = 16 profile counters
             if (ws.trdll.n < cells) ws.trdll.alloc(cells);
