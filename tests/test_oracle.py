@@ -191,3 +191,17 @@ def test_oracle_reproduces_readme_golden(name):
     d = np.abs(out.astype(int) - gold.astype(int))
     assert d.max() <= 2, d.max()
     assert (d <= 1).mean() >= 0.999
+
+
+def test_sq_spread_separates_well_and_ill_conditioned_inputs():
+    """The evidence behind test_gpu_parity.py::sq_close (profiles/sq_conditioning.md): at a well-conditioned corner of the hx / hy
+    sweep the reference algebra pins every Sq_i far below north_star's 1e-5 under other LAPACK eigensolvers, the factor-form order
+    and eps-sized perturbations of Ka; at hx = 5000, hy = 100 (Ka of rank 32 of 99) the same variants move the smallest
+    eigenvalues by more than 1e-5, while the rank cuts stay put."""
+    from nle_testlib import oracle_sq_spread
+    L = synth_lum(72, 88, seed=21)
+    S, spread = oracle_sq_spread(L, (9, 11, 100.0, 30.0, 6, 12), draws=3)
+    assert spread is not None and spread.max() < 1e-9
+    S, spread = oracle_sq_spread(L, (9, 11, 5000.0, 100.0, 6, 12), draws=3)
+    assert spread is not None and S.size == 12
+    assert spread[:8].max() < 1e-5 < spread[-1] < 1e-2
