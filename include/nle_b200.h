@@ -52,6 +52,9 @@ typedef struct {
     int eig_sweeps[3];   /* Jacobi sweeps used by the three eigensolves (0 = direct solver) */
     int eig_fallbacks;   /* eigensolves of this training call that fell back from the direct solver to block
                             Jacobi (also reported on stderr when it happens); 0 in normal operation */
+    int topk_products;   /* block products A*X spent by the top-k solver on eig(Q) (filter.cpp:311-316); 0 = the block of Q
+                            was too small for it and the full solver ran; < 0 = it gave up after that many and the full
+                            solver ran */
 } nle_b200_info;
 
 /* Small all-reduce (sum) used by row-sharded training/apply.  `dev_buf` is a DEVICE pointer to
@@ -95,6 +98,14 @@ int nle_b200_compute_kernel(const double* channel, int rows, int cols, int nRowS
  * U: n x n (all eigenvectors, first r are the reference's result), D: n. */
 int nle_b200_eigen_decomposition(const double* M, int n, double eps, double* U, double* D,
                                  int* r_out);
+/* topkEigenDecomposition, filter.cpp:169-200 (the reference's USE_SPECTRA build; its only caller passes Q, :311).
+ * nev = min(nLargest, n-1) (:172) eigenpairs of largest magnitude in descending algebraic order; *r_out = length of the
+ * prefix with D >= eps (:189-198).  U: n x nev, D: nev.  assume_psd != 0 promises a positive semi-definite M (true for Q)
+ * and selects the Chebyshev-filtered block iteration that the training path uses for eig(Q) when n is large against nev;
+ * otherwise, or when that solver gives up, the full eigensolver runs and the nev pairs are selected from it.
+ * *products_out (optional): block products used by the fast solver (0: not used, < 0: gave up after that many). */
+int nle_b200_topk_eigen_decomposition(const double* M, int n, int nLargest, double eps, int assume_psd,
+                                      double* U, double* D, int* r_out, int* products_out);
 /* nystromApproximation, filter.cpp:257-280.  eigvals: p, phi: (p+nrest) x p (first r columns
  * valid), *r_out = rank kept. */
 int nle_b200_nystrom_approximation(const double* Ka, int p, const double* Kab, int nrest,

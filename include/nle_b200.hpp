@@ -10,6 +10,7 @@
 // over the same C calls.  Header-only; link with libnle_b200.so.  There is no CPU fallback: without a CUDA device
 // every call throws.
 #pragma once
+#include <algorithm>
 #include <cstdint>
 #include <functional>
 #include <memory>
@@ -66,6 +67,22 @@ inline std::pair<Mat, Vec> eigenDecomposition(const Mat& M, DType eps = EPS) {
     Vec D(n);
     int r = 0;
     ok(nle_b200_eigen_decomposition(M.a.data(), n, eps, U.a.data(), D.data(), &r));
+    U.a.resize((size_t)n * r);
+    U.cols = r;
+    D.resize(r);
+    return {std::move(U), std::move(D)};
+}
+
+// nle::topkEigenDecomposition (filter.cpp:169-200, USE_SPECTRA build): the min(nLargest, n-1) eigenpairs of largest magnitude,
+// descending, cut at the first eigenvalue below eps.  assume_psd (true for the reference's only caller, Q at :311) selects the
+// block solver of the training path; the result is the same either way.
+inline std::pair<Mat, Vec> topkEigenDecomposition(const Mat& M, int nLargest, DType eps = EPS, bool assume_psd = false) {
+    const int n = M.rows;
+    const int nev = std::max(1, std::min(nLargest, n - 1));
+    Mat U(n, nev);
+    Vec D(nev);
+    int r = 0;
+    ok(nle_b200_topk_eigen_decomposition(M.a.data(), n, nLargest, eps, assume_psd ? 1 : 0, U.a.data(), D.data(), &r, nullptr));
     U.a.resize((size_t)n * r);
     U.cols = r;
     D.resize(r);

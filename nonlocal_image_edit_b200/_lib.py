@@ -16,7 +16,7 @@ class Info(C.Structure):
     _fields_ = [("rows", C.c_int), ("cols", C.c_int), ("row0", C.c_int), ("row1", C.c_int),
                 ("p", C.c_int), ("r", C.c_int), ("r2", C.c_int), ("k", C.c_int),
                 ("n_row_samples_eff", C.c_int), ("n_col_samples_eff", C.c_int),
-                ("eig_sweeps", C.c_int * 3), ("eig_fallbacks", C.c_int)]
+                ("eig_sweeps", C.c_int * 3), ("eig_fallbacks", C.c_int), ("topk_products", C.c_int)]
 
 
 # every symbol include/nle_b200.h declares: name -> (restype, argtypes)
@@ -33,6 +33,7 @@ SYMBOLS = {
     "nle_b200_sample_indices": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _P, _P]),
     "nle_b200_compute_kernel": (C.c_int, [_P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double, _P, _P, _P]),
     "nle_b200_eigen_decomposition": (C.c_int, [_P, C.c_int, C.c_double, _P, _P, _I]),
+    "nle_b200_topk_eigen_decomposition": (C.c_int, [_P, C.c_int, C.c_int, C.c_double, C.c_int, _P, _P, _I, _I]),
     "nle_b200_nystrom_approximation": (C.c_int, [_P, C.c_int, _P, C.c_int, _P, _P, _I]),
     "nle_b200_sinkhorn": (C.c_int, [_P, C.c_int, C.c_int, _P, C.c_int, _P, _P]),
     "nle_b200_orthogonalize": (C.c_int, [_P, C.c_int, _P, C.c_int, C.c_int, C.c_double, _P, _P, _I]),

@@ -124,6 +124,7 @@ struct nle_b200_filter {
     DevBuf<double> Ka, lam, rvec_head, c, Wa, Q, la, Gram;
     double times_ms[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     int eig_fallbacks = 0;
+    int topk_products = 0;
     nle_b200_allreduce_fn allreduce = nullptr;
     void* user = nullptr;
     cudaStream_t stream = nullptr;
@@ -442,7 +443,18 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     scale_rows_cols(r2, r2, Mq.p, r2, irl.p, irl.p, Mq.p, r2, s);
     add_diag(Mq.p, r2, la.p, s);
     tr("small: invroot, Q");
-    f->eig_sweeps[2] = sym_eig(Mq.p, r2, r2, kEps, /*psd_hint=*/false, Zq.p, Sq.p, d_cnt.p, ws, s, /*vec_limit=*/nEig);
+    // Only the nEig largest eigenpairs are used (:313-316).  M = L+ + (positive semi-definite) >= 1e-10 I, so for a block
+    // that is large against nEig the Chebyshev-filtered block iteration (eig_topk.cu) replaces the full solve; it gives up
+    // rather than return anything doubtful, and the full solver then runs as before.
+    bool topk_done = false;
+    static const bool topk_off = [] { const char* e = getenv("NLE_B200_TOPK"); return e && std::string(e) == "off"; }();   // cross-check only
+    if (!topk_off && sym_eig_topk_supported(r2, nEig)) {
+        symmetrize_lower(Mq.p, r2, r2, T2.p, s);                                      // the lower triangle defines M, as in sym_eig
+        topk_done = sym_eig_topk(T2.p, r2, nEig, kEps, Zq.p, Sq.p, d_cnt.p, ws, s, &f->topk_products);
+        if (!topk_done) f->topk_products = -f->topk_products;                        // < 0: tried and fell back
+    }
+    if (!topk_done)
+        f->eig_sweeps[2] = sym_eig(Mq.p, r2, r2, kEps, /*psd_hint=*/false, Zq.p, Sq.p, d_cnt.p, ws, s, /*vec_limit=*/nEig);
     const int nq = read_int(d_cnt.p, s);
     tr("small: eig Q");
     TmpBuf<double> Q;
@@ -642,6 +654,54 @@ int nle_b200_eigen_decomposition(const double* M, int n, double eps, double* U, 
         if (n < 0) throw InvalidArg{"n must be >= 0"};
         int r = (n == 0) ? 0 : eig_host(M, n, eps, false, U, D);
         if (r_out) *r_out = r;
+    });
+}
+
+int nle_b200_topk_eigen_decomposition(const double* M, int n, int nLargest, double eps, int assume_psd, double* U, double* D,
+                                      int* r_out, int* products_out) {
+    return guarded([&] {
+        require_device();
+        if (n < 2) throw InvalidArg{"topkEigenDecomposition needs n >= 2 (nLargest = min(nLargest, n - 1) must be positive)"};
+        if (nLargest < 1) throw InvalidArg{"nLargest must be >= 1"};
+        const int nev = std::min(nLargest, n - 1);                                    // filter.cpp:172
+        cudaStream_t s = nullptr;
+        thread_arena().reset();
+        DevBuf<double> dM((size_t)n * n), dA((size_t)n * n), dU((size_t)n * n), dD(n);
+        DevBuf<int> dr(1);
+        dM.upload(M, (size_t)n * n, s);
+        EigWorkspace ws;
+        int products = 0, r = -1;
+        if (assume_psd && sym_eig_topk_supported(n, nev)) {
+            symmetrize_lower(dM.p, n, n, dA.p, s);
+            if (sym_eig_topk(dA.p, n, nev, eps, dU.p, dD.p, dr.p, ws, s, &products)) r = read_int(dr.p, s);
+            else products = -products;
+        }
+        if (r >= 0) {
+            dU.download(U, (size_t)n * nev, s);
+            dD.download(D, nev, s);
+            NLE_CUDA(cudaStreamSynchronize(s));
+        } else {
+            // full solve, then Spectra's selection rule: the nev eigenvalues of LARGEST MAGNITUDE, reported in descending
+            // algebraic order (SymEigsSolver<LARGEST_MAGN>, results sorted LARGEST_ALGE), cut at the first one below eps (:189-198)
+            std::vector<double> hU((size_t)n * n), hD(n);
+            sym_eig(dM.p, n, n, -1e300, false, dU.p, dD.p, dr.p, ws, s);
+            dU.download(hU.data(), (size_t)n * n, s);
+            dD.download(hD.data(), n, s);
+            NLE_CUDA(cudaStreamSynchronize(s));
+            std::vector<int> idx(n);
+            for (int i = 0; i < n; ++i) idx[i] = i;
+            std::stable_sort(idx.begin(), idx.end(), [&](int a, int b) { return std::fabs(hD[a]) > std::fabs(hD[b]); });
+            idx.resize(nev);
+            std::sort(idx.begin(), idx.end());                                        // hD is descending: index order = algebraic order
+            r = 0;
+            for (int j = 0; j < nev; ++j) {
+                D[j] = hD[idx[j]];
+                std::copy(hU.begin() + (size_t)idx[j] * n, hU.begin() + (size_t)(idx[j] + 1) * n, U + (size_t)j * n);
+            }
+            while (r < nev && D[r] >= eps) ++r;
+        }
+        if (r_out) *r_out = r;
+        if (products_out) *products_out = products;
     });
 }
 
@@ -921,6 +981,7 @@ int nle_b200_filter_info(const nle_b200_filter* f, nle_b200_info* info) {
         info->n_row_samples_eff = f->nR; info->n_col_samples_eff = f->nC;
         for (int i = 0; i < 3; ++i) info->eig_sweeps[i] = f->eig_sweeps[i];
         info->eig_fallbacks = f->eig_fallbacks;
+        info->topk_products = f->topk_products;
     });
 }
 

@@ -130,6 +130,13 @@ int sm_count();
 // C(m x n) = alpha * op(A) * op(B) + beta * C
 void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const double* A, int lda,
            const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t s);
+// Split-K form for skinny outputs (few 64 x 64 tiles, long k): partial products per k slice, then
+// C = alpha * sum_z part_z + beta * P + gamma * Z  (slices summed in index order).  part: slices * m * n doubles.
+int dgemm_splitk_slices(int m, int n, int k);
+void dgemm_splitk(bool transA, int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* part,
+                  cudaStream_t s);
+void dgemm_combine(int m, int n, int k, const double* part, double alpha, double beta, const double* P, int ldp, double gamma,
+                   const double* Z, int ldz, double* C, int ldc, cudaStream_t s);
 // y(m) = A(m x n) x        /  y(n) = A(m x n)^T x
 void dgemv_n(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s);
 void dgemv_t(int m, int n, const double* A, int lda, const double* x, double* y, cudaStream_t s);
@@ -186,5 +193,18 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
 // remaining columns of U are unspecified); < 0: all n columns are valid.
 int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
             int* d_r, EigWorkspace& ws, cudaStream_t s, int vec_limit = -1);
+
+// As(i,j) = As(j,i) = M(i,j), i >= j: full storage of the symmetric matrix the LOWER triangle of M defines (eig.cu).
+void symmetrize_lower(const double* M, int ldm, int n, double* As, cudaStream_t s);
+
+// ---- eig_topk.cu : top-k eigenpairs of a symmetric POSITIVE SEMI-DEFINITE matrix (third eigensolve, filter.cpp:311-316) ----
+// Chebyshev-filtered block subspace iteration, Cholesky-QR, Rayleigh-Ritz; all products on the FP64 tensor pipe.
+int topk_block_width(int k);                 // k + guard columns, multiple of 8
+bool sym_eig_topk_supported(int n, int k);   // block fits one CTA's shared memory and n is large enough for the method to pay
+// A: n x n, FULL storage (ld n).  Z: n x k (ld n) eigenvectors of the k largest eigenvalues, descending; S: k eigenvalues;
+// d_count: length of the prefix with S >= eps.  false = gave up (Cholesky breakdown, no convergence, k-th eigenvalue < eps):
+// the caller runs sym_eig instead.  gemms (host, optional): number of A * X block products used.
+bool sym_eig_topk(const double* A, int n, int k, double eps, double* Z, double* S, int* d_count, EigWorkspace& ws,
+                  cudaStream_t s, int* gemms);
 
 }  // namespace nle

@@ -4,6 +4,8 @@
 // thousand) and FP64; B200 has no FP64 tcgen05 path, and the N-scaled work lives elsewhere.
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace nle {
 
 thread_local long long g_launches = 0;
@@ -97,8 +99,12 @@ constexpr int GBM = 64, GBN = 64, GBK = 16, GLDS = 64 + 8;
 
 template <bool TA, bool TB>
 __global__ void __launch_bounds__(128)
-dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, int lda,
-             const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc) {
+dgemm_kernel(int M, int N, int Kfull, double alpha, const double* __restrict__ A, int lda,
+             const double* __restrict__ B, int ldb, double beta, double* __restrict__ C, int ldc, int kchunk, size_t cz) {
+    // split-K (dgemm_splitk): grid.z slices of kchunk; slice z writes its partial product to C + z * cz
+    const int kbeg = blockIdx.z * kchunk;
+    const int K = min(Kfull, kbeg + kchunk);
+    C += (size_t)blockIdx.z * cz;
     __shared__ double As[GBK][GLDS];     // As[k][i] = op(A)[i0+i][k0+k]
     __shared__ double Bs[GBK][GLDS];     // Bs[k][j] = op(B)[k0+k][j0+j]
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -137,8 +143,8 @@ dgemm_kernel(int M, int N, int K, double alpha, const double* __restrict__ A, in
             Bs[kb][j] = pb[l];
         }
     };
-    fetch(0);
-    for (int k0 = 0; k0 < K; k0 += GBK) {
+    fetch(kbeg);
+    for (int k0 = kbeg; k0 < K; k0 += GBK) {
         __syncthreads();                   // previous chunk consumed
         commit();
         __syncthreads();
@@ -178,10 +184,56 @@ void dgemm(bool transA, bool transB, int m, int n, int k, double alpha, const do
            const double* B, int ldb, double beta, double* C, int ldc, cudaStream_t s) {
     if (m <= 0 || n <= 0) return;
     dim3 grid(cdiv(m, GBM), cdiv(n, GBN));
-    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
-    else dgemm_kernel<true, true><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc);
+    if (!transA && !transB) dgemm_kernel<false, false><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, k, 0);
+    else if (transA && !transB) dgemm_kernel<true, false><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, k, 0);
+    else if (!transA && transB) dgemm_kernel<false, true><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, k, 0);
+    else dgemm_kernel<true, true><<<grid, 128, 0, s>>>(m, n, k, alpha, A, lda, B, ldb, beta, C, ldc, k, 0);
+    NLE_LAUNCH_CHECK();
+}
+
+// Split-K product for skinny outputs (the block eigensolver of eig_topk.cu: m x n is n x 64 or 64 x 64 with k in the
+// thousands, i.e. a handful of 64 x 64 tiles that would otherwise run on a handful of SMs): slice z of the k range writes
+// its partial product (m x n, ld m) to part + z*m*n; dgemm_combine sums the slices in index order (deterministic) and
+// applies the epilogue  C = alpha * sum_z part_z + beta * P + gamma * Z.
+int dgemm_splitk_slices(int m, int n, int k) {
+    const int tiles = cdiv(m, GBM) * cdiv(n, GBN);
+    int want = std::max(1, (2 * sm_count()) / tiles);            // ~two CTAs per SM
+    int kchunk = std::max(GBK * 2, cdiv(cdiv(k, want), GBK) * GBK);
+    return cdiv(k, kchunk);
+}
+
+void dgemm_splitk(bool transA, int m, int n, int k, const double* A, int lda, const double* B, int ldb, double* part,
+                  cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    const int nz = dgemm_splitk_slices(m, n, k);
+    const int kchunk = cdiv(cdiv(k, nz), GBK) * GBK;
+    dim3 grid(cdiv(m, GBM), cdiv(n, GBN), cdiv(k, kchunk));
+    if (!transA) dgemm_kernel<false, false><<<grid, 128, 0, s>>>(m, n, k, 1.0, A, lda, B, ldb, 0.0, part, m, kchunk, (size_t)m * n);
+    else dgemm_kernel<true, false><<<grid, 128, 0, s>>>(m, n, k, 1.0, A, lda, B, ldb, 0.0, part, m, kchunk, (size_t)m * n);
+    NLE_LAUNCH_CHECK();
+}
+
+__global__ void __launch_bounds__(256)
+dgemm_combine_kernel(int m, int n, const double* __restrict__ part, int nz, double alpha, double beta,
+                     const double* __restrict__ P, int ldp, double gamma, const double* __restrict__ Z, int ldz,
+                     double* __restrict__ C, int ldc) {
+    const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (long long)m * n) return;
+    const int i = (int)(e % m), j = (int)(e / m);
+    double acc = 0.0;
+    for (int z = 0; z < nz; ++z) acc += part[(size_t)z * m * n + e];
+    double r = alpha * acc;
+    if (beta != 0.0) r = fma(beta, P[i + (size_t)j * ldp], r);
+    if (gamma != 0.0) r = fma(gamma, Z[i + (size_t)j * ldz], r);
+    C[i + (size_t)j * ldc] = r;
+}
+
+void dgemm_combine(int m, int n, int k, const double* part, double alpha, double beta, const double* P, int ldp, double gamma,
+                   const double* Z, int ldz, double* C, int ldc, cudaStream_t s) {
+    if (m <= 0 || n <= 0) return;
+    const int nz = dgemm_splitk_slices(m, n, k);
+    const int kchunk = cdiv(cdiv(k, nz), GBK) * GBK;
+    dgemm_combine_kernel<<<cdiv((long long)m * n, 256), 256, 0, s>>>(m, n, part, cdiv(k, kchunk), alpha, beta, P, ldp, gamma, Z, ldz, C, ldc);
     NLE_LAUNCH_CHECK();
 }
 

@@ -493,6 +493,11 @@ static bool sym_eig_direct(const double* M, int ldm, int n, double eps, double* 
     return true;
 }
 
+void symmetrize_lower(const double* M, int ldm, int n, double* As, cudaStream_t s) {
+    eig_symmetrize_tiled_kernel<<<dim3(cdiv(n, 32), cdiv(n, 32)), 256, 0, s>>>(M, ldm, n, As);
+    NLE_LAUNCH_CHECK();
+}
+
 int sym_eig(const double* M, int ldm, int n, double eps, bool psd_hint, double* U, double* D,
             int* d_r, EigWorkspace& ws, cudaStream_t s, int vec_limit) {
     (void)psd_hint;

@@ -596,28 +596,47 @@ dc_leaf_kernel(const double* __restrict__ d_in, const double* __restrict__ e_in,
             g = ds[mm] - ds[l] + es[l] / (g + copysign(r, g));
             double s = 1.0, c = 1.0, p = 0.0;
             bool broke = false;
+            // The scalar recurrence is one dependent chain per rotation; what is not on it is kept off it: d[i], e[i] are
+            // fetched one rotation ahead (nothing in the loop writes them before they are read), d[i+1] and the eigenvector
+            // entry Z[lane][i+1] are carried in registers, and r = sqrt(f^2 + g^2) with its reciprocal comes from one rsqrt
+            // instead of hypot + two divisions (library hypot only outside the range where f^2 + g^2 is safely normal).
+            double e_nx = es[mm - 1], d_nx = ds[mm - 1], d_ip1 = ds[mm];
+            double zc = Zs[lane][mm];
             for (int i = mm - 1; i >= l; --i) {
-                double f = s * es[i];
-                const double bb = c * es[i];
-                r = hypot(f, g);
+                const double ei = e_nx, di = d_nx;
+                if (i > l) { e_nx = es[i - 1]; d_nx = ds[i - 1]; }
+                const double z0 = Zs[lane][i];
+                const double f = s * ei;
+                const double bb = c * ei;
+                const double h2 = fma(f, f, g * g);
+                double r, rinv;
+                if (h2 > 1e-280 && h2 < 1e280) {
+                    rinv = rsqrt(h2);
+                    r = h2 * rinv;
+                } else {
+                    r = hypot(f, g);
+                    rinv = (r == 0.0) ? 0.0 : 1.0 / r;
+                }
                 es[i + 1] = r;
                 if (r == 0.0) {
-                    ds[i + 1] -= p;
+                    ds[i + 1] = d_ip1 - p;
                     es[mm] = 0.0;
+                    Zs[lane][i + 1] = zc;
                     broke = true;
                     break;
                 }
-                s = f / r;
-                c = g / r;
-                g = ds[i + 1] - p;
-                r = (ds[i] - g) * s + 2.0 * c * bb;
+                s = f * rinv;
+                c = g * rinv;
+                g = d_ip1 - p;
+                r = (di - g) * s + 2.0 * c * bb;
                 p = s * r;
                 ds[i + 1] = g + p;
                 g = c * r - bb;
-                const double z1 = Zs[lane][i + 1], z0 = Zs[lane][i];
-                Zs[lane][i + 1] = s * z0 + c * z1;
-                Zs[lane][i] = c * z0 - s * z1;
+                Zs[lane][i + 1] = s * z0 + c * zc;
+                zc = c * z0 - s * zc;
+                d_ip1 = di;
             }
+            if (!broke) Zs[lane][l] = zc;
             if (broke) continue;
             ds[l] -= p;
             es[l] = g;

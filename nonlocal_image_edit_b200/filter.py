@@ -80,6 +80,25 @@ def eigenDecomposition(M, eps=EPS):
     return np.asfortranarray(U[:, :r.value]), D[:r.value].copy()
 
 
+def topkEigenDecomposition(M, nLargest, eps=EPS, assume_psd=False, return_products=False):
+    """nle::topkEigenDecomposition (filter.cpp:169-200, USE_SPECTRA build) -> (U n x r, D r): the min(nLargest, n-1) eigenpairs
+    of largest magnitude in descending order, cut at the first eigenvalue below eps.  assume_psd=True (the reference's only
+    caller passes Q, positive semi-definite) selects the block solver the training path uses for eig(Q)."""
+    lib = _lib.load()
+    M, pM = _colmajor(M)
+    n = M.shape[0]
+    if M.shape != (n, n):
+        raise ValueError("M must be square")
+    nev = max(1, min(int(nLargest), n - 1))
+    U = np.empty((n, nev), dtype=np.float64, order="F")
+    D = np.empty(nev, dtype=np.float64)
+    r, prod = C.c_int(0), C.c_int(0)
+    check(lib.nle_b200_topk_eigen_decomposition(pM, n, int(nLargest), float(eps), int(bool(assume_psd)), _ptr(U), _ptr(D),
+                                                C.byref(r), C.byref(prod)))
+    out = (np.asfortranarray(U[:, :r.value]), D[:r.value].copy())
+    return out + (prod.value,) if return_products else out
+
+
 def nystromApproximation(Ka, Kab):
     """nle::nystromApproximation (filter.cpp:257-280) -> (eigvals r, phi N x r)."""
     lib = _lib.load()

@@ -8,13 +8,16 @@ L channel as PNG.  tests/test_gpu_oracle_big.py compares the CUDA path with thes
 
   c3      BASELINE configs[2] (the benchmarked one): bench.workload_images(1024, 1024) luminance, 40x40 samples,
           hx=500 hy=30, T=20, k=50, weights 2 3 4 1
+  c3x2    the image bench.py trains at --gpus 2 (weak scaling: bench.workload_images(2048, 1024), same grid and widths as c3).
+          Its block of Q is 855 x 855, above the size from which the training path solves eig(Q) with the top-k block
+          solver (csrc/eig_topk.cu): the fixture that pins THAT path to the oracle
   c4      BASELINE configs[3]: full-resolution data/rock2.jpg (tests/golden/rock2_input.png), 50x50 samples,
           hx=500 hy=10, T=50, k=100, weights 4 3 4 1
   c5crop  BASELINE configs[4] on its top-left 1024x1024 crop: bench.synth_luminance(4096, 4096)[:1024, :1024],
           50x50 samples, hx=500 hy=30, T=20, k=100, weights 2 3 4 1
 
 Run in the build container (8 host threads):  python tests/golden/make_oracle_big.py c3 c4 c5crop
-(c3 ~ 15 min, c4 ~ 25 min, c5crop ~ 25 min).
+(c3 ~ 15 min, c3x2 ~ 35 min, c4 ~ 25 min, c5crop ~ 25 min).
 """
 import hashlib
 import json
@@ -35,6 +38,9 @@ import bench  # noqa: E402
 def config(name):
     if name == "c3":
         _, lum = bench.workload_images(1024, 1024)
+        return lum, (40, 40, 500.0, 30.0, 20, 50), [2.0, 3.0, 4.0, 1.0]
+    if name == "c3x2":
+        _, lum = bench.workload_images(2048, 1024)
         return lum, (40, 40, 500.0, 30.0, 20, 50), [2.0, 3.0, 4.0, 1.0]
     if name == "c4":
         img = cv2.imread(os.path.join(HERE, "rock2_input.png"))

@@ -7,6 +7,8 @@
   forces the latter, so each side runs in its own process.
 * Eigensolver family: the direct solver (tridiagonalisation + divide & conquer) against the block-Jacobi fallback
   (NLE_B200_EIG=jacobi) to rounding.
+* Third eigensolve: when the block of Q is at least 10 x the block width, eig(Q) runs the top-k block solver
+  (csrc/eig_topk.cu) instead of the full solver (NLE_B200_TOPK=off): eigenvalues to 1e-12, identical output image.
 * Sinkhorn pixel pass: sample grids wider than 64 columns take the per-row staged kernel (sk_pix_kernel) instead of the
   cell kernel; both against the oracle."""
 import os
@@ -108,3 +110,35 @@ def test_wide_sample_grid_takes_the_row_kernel_and_matches_the_oracle(nb):
     out = f.enhanceLuminance(L, [2.0, 3.0, 4.0, 1.0])
     d = np.abs(out.astype(int) - O.enhance_luminance(ref, L, [2.0, 3.0, 4.0, 1.0]).astype(int))
     assert d.max() <= 1 and (d <= 1).mean() >= 0.999
+
+
+TOPK_CHILD = r"""
+import sys, numpy as np
+sys.path.insert(0, sys.argv[2])
+import nonlocal_image_edit_b200 as nb
+import bench
+_, lum = bench.workload_images(2048, 1024)
+f = nb.NLEFilter().trainFilter(lum, 40, 40, bench.HX, bench.HY, bench.T_SINK, bench.K_EIG)
+inf = f.info()
+np.savez(sys.argv[1], S=f.eigvals, out=f.enhanceLuminance(lum, [2.0, 3.0, 4.0, 1.0]),
+         info=np.array([inf.p, inf.r, inf.r2, inf.k, inf.topk_products, inf.eig_fallbacks]))
+"""
+
+
+def test_topk_solver_for_eig_q_matches_the_full_solver(tmp_path):
+    """The 2048 x 1024 image of the 2-GPU weak-scaling run: r2 = 855, above 640 = 10 x the block width for k = 50."""
+    outs = []
+    for tag, extra in (("topk", {}), ("full", {"NLE_B200_TOPK": "off"})):
+        env = {k: v for k, v in os.environ.items() if not k.startswith("NLE_B200_")}
+        env.update(extra)
+        env["NLE_B200_EIG_STRICT"] = "1"
+        out = str(tmp_path / f"{tag}.npz")
+        subprocess.run([sys.executable, "-c", TOPK_CHILD, out, ROOT], env=env, check=True, timeout=600)
+        outs.append(np.load(out))
+    a, b = outs
+    assert a["info"][2] >= 640, a["info"]
+    assert a["info"][4] > 0 and b["info"][4] == 0, (a["info"], b["info"])       # block solver ran and converged / was off
+    assert np.array_equal(a["info"][:4], b["info"][:4]) and a["info"][5] == 0 and b["info"][5] == 0
+    assert np.abs(a["S"] - b["S"]).max() <= 1e-12 * b["S"][0]
+    d = np.abs(a["out"].astype(int) - b["out"].astype(int))
+    assert d.max() <= 1 and (d == 0).mean() >= 0.9999, (int(d.max()), float((d == 0).mean()))

@@ -6,6 +6,8 @@ pinned to the dense restatement on small inputs and to the README goldens) and a
 tests/golden/oracle_big.json + <name>_oracle_L.png:
 
   c3      configs[2], the bench workload: 1024x1024, 40x40 samples, hx=500 hy=30, T=20, k=50
+  c3x2    the image of the 2-GPU weak-scaling run (2048x1024, same grid and widths): its block of Q (855 x 855) is solved
+          by the top-k block solver (csrc/eig_topk.cu), which c3 / c4 / c5crop are too small to reach
   c4      configs[3]: full-resolution rock2 (584x876), 50x50 samples, hx=500 hy=10, T=50, k=100
   c5crop  configs[4] on its top-left 1024x1024 crop, 50x50 samples, hx=500 hy=30, T=20, k=100
 
@@ -35,7 +37,7 @@ def _fixtures():
 FIX = _fixtures()
 
 
-@pytest.mark.parametrize("name", ["c3", "c4", "c5crop"])
+@pytest.mark.parametrize("name", ["c3", "c3x2", "c4", "c5crop"])
 def test_cuda_path_matches_streaming_oracle(nb, name):
     if name not in FIX:
         pytest.fail(f"fixture {name} missing from tests/golden/oracle_big.json (run tests/golden/make_oracle_big.py)")
@@ -50,6 +52,7 @@ def test_cuda_path_matches_streaming_oracle(nb, name):
     inf = f.info()
     assert (inf.p, inf.r, inf.r2, inf.k) == (fx["p"], fx["r"], fx["r2"], fx["k"]), (inf.p, inf.r, inf.r2, inf.k)
     assert inf.eig_fallbacks == 0
+    assert (inf.topk_products > 0) == (name == "c3x2"), inf.topk_products     # which solver took eig(Q)
     S, So = f.eigvals, np.array(fx["Sq"])
     rel = np.abs(S - So) / So
     assert rel.max() <= 1e-5, (rel.max(), int(rel.argmax()), So[int(rel.argmax())])       # north_star: 1e-5 relative
