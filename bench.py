@@ -534,8 +534,12 @@ def run_b200(args, rank, world, local_rank):
     pp, nR, nC, kk = inf.p, inf.n_row_samples_eff, inf.n_col_samples_eff, inf.k
     slab = lum[row0:row1]
     k_cells = int(sum(np.unique(r).size for r in slab))
-    dfma_peak = lib.nle_b200_fp64_fma_peak_tflops()
-    dmma_peak = lib.nle_b200_fp64_dmma_peak_tflops()
+    pk = (C.c_double * 8)()
+    _lib.check(lib.nle_b200_measured_peaks(pk, 8))            # csrc/peaks.cu, outside every timed region
+    dfma_peak, dmma_peak = float(pk[0]), float(pk[1])
+    measured_peaks = {"fp64_fma_tflops": pk[0], "fp64_dmma_tflops": pk[1], "fp32_fma_tflops": pk[2], "mufu_ex2_gops": pk[3],
+                      "shared_load_gbs": pk[4], "shared_load_bytes_per_sm_clk": pk[7], "l2_read_gbs_32mb": pk[5], "hbm_copy_gbs": pk[6],
+                      "source": "microbenchmarks of csrc/peaks.cu run on this GPU in this process (best of 5 launches each)"}
     nominal = 148 * 64 * 2 * 1.965e9 * 1e-12
     peak_src = ("measured in this run: register-resident DFMA microbenchmark (nle_b200_fp64_fma_peak_tflops) and back-to-back "
                 "mma.sync.m8n8k4.f64 microbenchmark (nle_b200_fp64_dmma_peak_tflops); nominal 148 SM x 64 FP64 lanes x 2 x "
@@ -604,6 +608,7 @@ def run_b200(args, rank, world, local_rank):
         "clocks": clocks,
         "roofline": roofline,
         "roofline_all": roofline_all,
+        "measured_peaks": measured_peaks,
         "cpu_baseline": cpu,
         "stage_ms": {"setup_tables_Ka": float(st[0]), "eig_Ka": float(st[1]), "sinkhorn_passes": float(st[2]),
                      "gram": float(st[3]), "small_algebra_2eigs": float(st[4]), "extension": float(st[5]),
@@ -611,7 +616,7 @@ def run_b200(args, rank, world, local_rank):
                      "divide_conquer_3_solves": float(st[9]), "back_transform_3_solves": float(st[10])},
         "step_ms": step_ms,
         "filter": {"p": inf.p, "r": inf.r, "r2": inf.r2, "k": inf.k, "eig_sweeps": list(inf.eig_sweeps),
-                   "eig_fallbacks": inf.eig_fallbacks},
+                   "eig_fallbacks": inf.eig_fallbacks, "topk_products": inf.topk_products},
         "multi_gpu_parity": parity,
         "enhance_only": enhance_only,
         "c5_strong": c5,

@@ -217,6 +217,10 @@ long long nle_b200_launch_count(int reset);
 double nle_b200_fp64_fma_peak_tflops(void);
 /* Same for the FP64 tensor pipe: back-to-back mma.sync.m8n8k4.f64 (SASS DMMA) with register operands (TFLOP/s). */
 double nle_b200_fp64_dmma_peak_tflops(void);
+/* All measured ceilings bench.py quotes (csrc/peaks.cu), out[0..min(n,8)): FP64 FMA TFLOP/s, FP64 tensor pipe TFLOP/s,
+ * FP32 FMA TFLOP/s, MUFU ex2 Gop/s, shared-memory load GB/s, L2 read GB/s (32 MB working set), HBM copy GB/s
+ * (read + write bytes), shared-memory load bytes per SM clock.  Allocates 2 GiB of device memory for the duration of the call. */
+int nle_b200_measured_peaks(double* out, int n);
 
 void nle_b200_free(nle_b200_filter* f);
 /* Releases what the calling thread keeps between calls (the parked eigenvector buffer of the last freed filter and the

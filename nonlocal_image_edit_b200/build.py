@@ -5,7 +5,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-SOURCES = ["api.cu", "dense.cu", "eig.cu", "eig_dc.cu", "eig_topk.cu", "filter_kernels.cu", "cell_kernels.cu", "sinkhorn_cells.cu", "apply_kernels.cu", "nccl_comm.cu"]
+SOURCES = ["api.cu", "dense.cu", "eig.cu", "eig_dc.cu", "eig_topk.cu", "filter_kernels.cu", "cell_kernels.cu", "sinkhorn_cells.cu", "apply_kernels.cu", "nccl_comm.cu", "peaks.cu"]
 LIB = os.path.join(HERE, "libnle_b200.so")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "-shared"]

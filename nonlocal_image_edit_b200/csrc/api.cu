@@ -234,6 +234,8 @@ double measure_dmma_peak_tflops() {
     return best;
 }
 
+void measure_peaks(double* out, int n);   // peaks.cu
+
 // small vector helpers used by the Sinkhorn loop
 __global__ void vec_axpy_kernel(double* y, const double* x, const double* scale, int n) {
     int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1205,6 +1207,14 @@ void nle_b200_release_cache(void) {
     g_v_cache.release();
     g_v_cache_dev = -1;
     thread_arena().release_all();
+}
+
+int nle_b200_measured_peaks(double* out, int n) {
+    return guarded([&] {
+        require_device();
+        if (!out || n < 1) throw InvalidArg{"out must hold at least one double"};
+        nle::measure_peaks(out, n);
+    });
 }
 
 double nle_b200_fp64_fma_peak_tflops(void) {
