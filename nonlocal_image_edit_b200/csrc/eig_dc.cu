@@ -286,6 +286,15 @@ __device__ __forceinline__ uint4 ll_load(const uint4* cell) {
     r.x = (unsigned)a; r.y = (unsigned)(a >> 32); r.z = (unsigned)b; r.w = (unsigned)(b >> 32);
     return r;
 }
+// Two adjacent cells (one 32-byte sector) with one request: the exchange is bound by the NUMBER of L2 requests (every CTA
+// reads every cell of the step), not by their bytes.  Each 8-byte half still carries its own tag, so nothing beyond 8-byte
+// atomicity is assumed.  SASS: LDG.E.ENL2.256.STRONG.GPU.
+__device__ __forceinline__ void ll_load2(const uint4* cell_pair /* 32-byte aligned */, uint4& c0, uint4& c1) {
+    unsigned long long a, b, c, d;
+    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(cell_pair) : "memory");
+    c0.x = (unsigned)a; c0.y = (unsigned)(a >> 32); c0.z = (unsigned)b; c0.w = (unsigned)(b >> 32);
+    c1.x = (unsigned)c; c1.y = (unsigned)(c >> 32); c1.z = (unsigned)d; c1.w = (unsigned)(d >> 32);
+}
 __device__ __forceinline__ double ll_value(const uint4& c) {
     return __longlong_as_double((long long)(((unsigned long long)c.z << 32) | (unsigned long long)c.x));
 }
@@ -347,8 +356,9 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
     long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = 0, rounds = 0;
     // cells of tag t: p at ll + (t&1)*2n, next column at ll + (t&1)*2n + n
-    auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n; };
-    auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * n + n; };
+    const int ne = (n + 1) & ~1;                 // even stride: every vector of cells starts on a 32-byte sector
+    auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * ne; };
+    auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * ne + ne; };
 
     auto make_reflector = [&](int j0, double& tau_out) -> double {     // identical to tridiag_kernel's
         const double alpha = cn[j0 + 1];
@@ -416,37 +426,48 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
         // (1) this CTA polls the cells of rows j+1+rank, j+1+rank+S, ... only (1/S of the readers per cell) and
         //     writes what it received into the w / cn vectors of every CTA of the cluster (distributed shared memory)
         {
+            // sector s holds the cells of rows 2s and 2s+1; this CTA polls the sectors s0 + rank, s0 + rank + S, ...
             const uint4* pc = pcell(T);
             const uint4* cc = ccell(T);
-            uint4 P[kResPer], C[kResPer];
-            unsigned pend = 0, spins = 0;
+            constexpr int SP = kResPer / 2;                 // sectors per thread and vector
+            uint4 P[SP][2], C[SP][2];
+            unsigned pend = 0, valid = 0, spins = 0;
+            const int s0 = (j + 1) >> 1;
 #pragma unroll
-            for (int u = 0; u < kResPer; ++u)
-                if (j + 1 + rank + S * (tid + u * kTrdThreads) < n) pend |= (1u | (1u << kResPer)) << u;
-            const unsigned mine = pend;
+            for (int u = 0; u < SP; ++u) {
+                const int r0 = 2 * (s0 + rank + S * (tid + u * kTrdThreads));
+                const unsigned v0 = (r0 >= j + 1 && r0 < n), v1 = (r0 + 1 < n);      // r0 + 1 >= j + 1 always
+                valid |= (v0 | (v1 << 1)) << (2 * u);
+                if (v0 | v1) pend |= (1u | (1u << SP)) << u;
+            }
             while (pend) {
 #pragma unroll
-                for (int u = 0; u < kResPer; ++u) {
-                    const int i = j + 1 + rank + S * (tid + u * kTrdThreads);
-                    if (pend & (1u << u)) P[u] = ll_load(pc + i);
-                    if (pend & (1u << (kResPer + u))) C[u] = ll_load(cc + i);
+                for (int u = 0; u < SP; ++u) {
+                    const int r0 = 2 * (s0 + rank + S * (tid + u * kTrdThreads));
+                    if (pend & (1u << u)) ll_load2(pc + r0, P[u][0], P[u][1]);
+                    if (pend & (1u << (SP + u))) ll_load2(cc + r0, C[u][0], C[u][1]);
                 }
 #pragma unroll
-                for (int u = 0; u < kResPer; ++u) {
-                    if ((pend & (1u << u)) && P[u].y == T && P[u].w == T) pend &= ~(1u << u);
-                    if ((pend & (1u << (kResPer + u))) && C[u].y == T && C[u].w == T) pend &= ~(1u << (kResPer + u));
+                for (int u = 0; u < SP; ++u) {
+                    const bool v0 = (valid >> (2 * u)) & 1u, v1 = (valid >> (2 * u + 1)) & 1u;
+                    if ((pend & (1u << u)) && (!v0 || (P[u][0].y == T && P[u][0].w == T)) && (!v1 || (P[u][1].y == T && P[u][1].w == T)))
+                        pend &= ~(1u << u);
+                    if ((pend & (1u << (SP + u))) && (!v0 || (C[u][0].y == T && C[u][0].w == T)) &&
+                        (!v1 || (C[u][1].y == T && C[u][1].w == T)))
+                        pend &= ~(1u << (SP + u));
                 }
                 if (PROF) ++rounds;
                 if (++spins > kTrdSpinLimit) __trap();   // a lost peer must not hang the device: abort the launch loudly
             }
-            TRD_STAMP(0, ll_value(P[0]));
+            TRD_STAMP(0, ll_value(P[0][0]));
             for (int r = 0; r < S; ++r) {
                 double* wr = cluster.map_shared_rank(w, r);
                 double* cr = cluster.map_shared_rank(cn, r);
 #pragma unroll
-                for (int u = 0; u < kResPer; ++u) {
-                    const int i = j + 1 + rank + S * (tid + u * kTrdThreads);
-                    if (mine & (1u << u)) { wr[i] = ll_value(P[u]); cr[i] = ll_value(C[u]); }
+                for (int u = 0; u < SP; ++u) {
+                    const int r0 = 2 * (s0 + rank + S * (tid + u * kTrdThreads));
+                    if ((valid >> (2 * u)) & 1u) { wr[r0] = ll_value(P[u][0]); cr[r0] = ll_value(C[u][0]); }
+                    if ((valid >> (2 * u + 1)) & 1u) { wr[r0 + 1] = ll_value(P[u][1]); cr[r0 + 1] = ll_value(C[u][1]); }
                 }
             }
         }
@@ -1449,12 +1470,13 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
             cfg.gridDim = dim3(G);
             cfg.dynamicSmemBytes = smem;
             cfg.numAttrs = 2;
-            const size_t cells = 4 * (size_t)n + 8;          // + 8 cells = 16 profile counters
+            const size_t ne = ((size_t)n + 1) & ~(size_t)1;  // even stride per vector of cells (32-byte sector polls)
+            const size_t cells = 4 * ne + 8;                 // + 8 cells = 16 profile counters
             if (ws.trdll.n < cells) ws.trdll.alloc(cells);
             NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));   // tag 0 = never written
             int lda = n;
             uint4* ll = ws.trdll.p;
-            long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * (size_t)n);
+            long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * ne);
             void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp};
             // Without the co-residency guarantee of a cooperative launch the polling CTAs could wait for CTAs that are
             // not running: if the launch is refused, fall through to the grid.sync kernel instead of launching anyway.
