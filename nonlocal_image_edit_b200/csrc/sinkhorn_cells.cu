@@ -37,7 +37,7 @@ constexpr int DG_MT = DG_ROWS / 8;   // DMMA m-tiles per warp
 // F[row][b][l] = sum_a Er[row][a] * w_ab * Gt[|l - Y_ab|].   grid (ceil(nrows/DG_ROWS), nC), 256 threads.
 // Warp w owns levels [32w, 32w+32) (4 n-tiles) for all DG_ROWS rows.
 __global__ void __launch_bounds__(256, 2)
-sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ F, int level_major) {
+sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __restrict__ F) {
     extern __shared__ double dsm[];
     const int nR = t.nR, nC = t.nC;
     const int nRp = (nR + 3) & ~3;
@@ -87,19 +87,231 @@ sk_dot_gemm_kernel(AffinityTables t, const double* __restrict__ w, double* __res
     for (int u = 0; u < DG_MT; ++u) {
         const int r = r0 + 8 * u + g;
         if (r >= t.nrows) continue;
-        if (!level_major) {                                   // F[row][b][l]
-            double* o = F + ((size_t)r * nC + b) * NL + warp * 32 + 2 * tq;
+        double* o = F + ((size_t)r * nC + b) * NL + warp * 32 + 2 * tq;          // F[row][b][l]
 #pragma unroll
-            for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
-        } else {                                              // F[row][l][b]: a cell's nC values are contiguous
-            double* o = F + ((size_t)r * NL + warp * 32 + 2 * tq) * nC + b;
+        for (int v = 0; v < 4; ++v) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][v][0], acc[u][v][1]);
+    }
+}
+
+// ---- level-major tables for the cell pass ----------------------------------------------------------------------------
+// sk_pix_cells_kernel reads, per cell, the nC values F[row][.][l] and writes the nC bins Hx[row][.][l]: with the sample column b
+// as the fastest index (F[row][l][ldb], ldb = nC rounded up to 4) these are 10 full 32-byte sectors per cell instead of 40
+// sectors used for 8 bytes each (ncu, profiles/r2f: the pass is bound by L1 sector throughput; 40 % of its sectors were those;
+// measured: 141 -> 98 us per pass).  The two level GEMMs put the sample column on the N axis of the DMMA tile, so that the
+// accumulator layout (a lane holds two adjacent N columns, four lanes hold eight) is b-contiguous by itself: no transposition,
+// every global access a run of 64 bytes.  (Keeping the level on the N axis and only switching the layout made the dot GEMM 4x
+// slower -- scattered 8-byte stores --, transposing through shared memory 2x: 81 and 52 us against 37 and 36.)
+
+// F[row][l][b] = sum_a Er[row][a] * (w_ab * Gt[|l - Y_ab|]):  for a fixed level an (image rows x nR) * (nR x nC) product whose B
+// operand is generated in registers from the sample tables.   grid (ceil(nrows/(8 RT)), 256/(8 LW)), 256 threads: warp = LW
+// levels, all RT row tiles of the CTA (a generated B fragment -- one look-up and one multiply -- feeds RT DMMAs), LQ levels at a time.
+template <int NT, int LQ, int RT, int LW>
+__global__ void __launch_bounds__(256, 2)
+sk_dot_gemm_nb_kernel(AffinityTables t, const double* __restrict__ w, int ldb, double* __restrict__ F) {
+    extern __shared__ double dsm[];
+    const int nR = t.nR, nC = t.nC;
+    const int nRp = (nR + 3) & ~3;
+    const int lda = nRp + ((12 - (nRp & 15)) & 15);          // lda % 16 == 12: conflict-free A fragments
+    constexpr int ST = 8 * NT + 4;                           // table row stride, % 16 == 4 or 12: ditto for the B look-ups
+    double* As = dsm;                                        // 8 RT * lda
+    double* Gs16 = As + 8 * RT * lda;                        // 256 * 16: Gt replicated so that lane L reads bank pair L & 15 -- the
+                                                             // look-ups of a warp (32 different samples) are conflict-free
+    double* wS = Gs16 + NL * 16;                             // nRp * ST   w_ab, 0 outside the grid
+    int* yS = reinterpret_cast<int*>(wS + (size_t)nRp * ST); // nRp * ST   Y_ab
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int r0 = blockIdx.x * (8 * RT);
+    {
+        const double gv = t.Gt[tid];
 #pragma unroll
-            for (int v = 0; v < 4; ++v) {
-                o[(size_t)(8 * v) * nC] = acc[u][v][0];
-                o[(size_t)(8 * v + 1) * nC] = acc[u][v][1];
+        for (int k = 0; k < 16; ++k) Gs16[tid * 16 + ((k + tid) & 15)] = gv;      // rotated: the lanes of a store hit different banks
+    }
+    for (int e = tid; e < nRp * ST; e += 256) {
+        const int a = e / ST, b = e - a * ST;
+        const bool ok = a < nR && b < nC;
+        wS[e] = ok ? w[a * nC + b] : 0.0;
+        yS[e] = ok ? (int)t.Ysel[a * nC + b] : 0;
+    }
+    for (int e = tid; e < 8 * RT * nRp; e += 256) {
+        const int r = e / nRp, a = e - r * nRp;
+        As[r * lda + a] = (r0 + r < t.nrows && a < nR) ? t.Er[(size_t)(t.row0 + r0 + r) * nR + a] : 0.0;
+    }
+    __syncthreads();
+    const int lbase = 8 * LW * blockIdx.y + LW * warp;
+    const double* Gl = Gs16 + (lane & 15);
+    for (int lg = 0; lg < LW; lg += LQ) {
+        double acc[RT][LQ][NT][2];
+#pragma unroll
+        for (int u = 0; u < RT; ++u)
+#pragma unroll
+            for (int j = 0; j < LQ; ++j)
+#pragma unroll
+                for (int v = 0; v < NT; ++v) acc[u][j][v][0] = acc[u][j][v][1] = 0.0;
+        for (int kk = 0; kk < nRp; kk += 4) {
+            const int a = kk + tq;
+            double af[RT];
+#pragma unroll
+            for (int u = 0; u < RT; ++u) af[u] = As[(8 * u + g) * lda + a];
+            double wv[NT];
+            int yv[NT];
+#pragma unroll
+            for (int v = 0; v < NT; ++v) {
+                wv[v] = wS[a * ST + 8 * v + g];
+                yv[v] = yS[a * ST + 8 * v + g];
+            }
+#pragma unroll
+            for (int j = 0; j < LQ; ++j) {
+                const int l = lbase + lg + j;
+#pragma unroll
+                for (int v = 0; v < NT; ++v) {
+                    const int d = l - yv[v];
+                    const double bf = wv[v] * Gl[(d < 0 ? -d : d) << 4];
+#pragma unroll
+                    for (int u = 0; u < RT; ++u) dmma884(acc[u][j][v][0], acc[u][j][v][1], af[u], bf);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < RT; ++u) {
+            const int row = r0 + 8 * u + g;
+            if (row >= t.nrows) continue;
+#pragma unroll
+            for (int j = 0; j < LQ; ++j) {
+                double* o = F + ((size_t)row * NL + lbase + lg + j) * ldb + 2 * tq;
+#pragma unroll
+                for (int v = 0; v < NT; ++v)
+                    if (8 * v + 2 * tq < ldb) *reinterpret_cast<double2*>(o + 8 * v) = make_double2(acc[u][j][v][0], acc[u][j][v][1]);
             }
         }
     }
+}
+
+// P[ks][level group][i] = sum over the group's 8 levels of  Gt[|l - Y_i|] * sum_{row in split ks} Er[row][a] * Hx[row][l][b],
+// i = a * nC + b: for a fixed level an (nR x rows) * (rows x nC) product with both operands read as 64-byte runs; the level
+// weight is applied to the finished tile and the 8 warps (= 8 levels) of the CTA are summed in warp order through shared
+// memory.  s = sum over (ks, group) of P (sk_sum_partials_kernel).   grid (ceil(256/WARPS), nks, nab), WARPS warps, warp = level.
+constexpr int RB_ST = 6;          // ring stages per warp (4 image rows each)
+template <int MT, int NT, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+sk_reduce_gemm_nb_kernel(AffinityTables t, const double* __restrict__ Hx, int ldb, int nks, int ring_doubles, double* __restrict__ P) {
+    extern __shared__ double rsm[];          // 8 warps x ring_doubles (cp.async rings, later the weighted tiles) | Er slice
+    const int nR = t.nR, nC = t.nC;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = lane >> 2, tq = lane & 3;
+    const int l = min(WARPS * (int)blockIdx.x + warp, NL - 1), ks = blockIdx.y, a0 = blockIdx.z * (8 * MT);
+    const bool live = WARPS * (int)blockIdx.x + warp < NL;      // the last CTA of a level split that does not divide 256
+    const int rb = (int)(((long long)t.nrows * ks) / nks);
+    const int re = (int)(((long long)t.nrows * (ks + 1)) / nks);
+    double acc[MT][NT][2];
+#pragma unroll
+    for (int u = 0; u < MT; ++u)
+#pragma unroll
+        for (int v = 0; v < NT; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+    // Er rows of the CTA's split (shared by its 8 warps): rows x 8 MT values, stride % 16 == 4 or 12 (conflict-free A fragments)
+    constexpr int AS = 8 * MT + 4;
+    double* ErS = rsm + (size_t)WARPS * ring_doubles;
+    for (int e = tid; e < (re - rb) * (8 * MT); e += WARPS * 32) {
+        const int rr = e / (8 * MT), a = e - rr * (8 * MT);
+        ErS[rr * AS + a] = (a0 + a < nR) ? t.Er[(size_t)(t.row0 + rb + rr) * nR + a0 + a] : 0.0;
+    }
+    // Per-warp ring of RB_ST stages x 4 image rows of the warp's level, filled with 16-byte cp.async copies (each row of Hx[.][l][.]
+    // is one contiguous run of ldb doubles): the loads run RB_ST - 1 DMMA rounds ahead of their use without holding registers.
+    // Row stride % 16 == 4: the B fragments (4 rows x 8 columns per half warp) fall into 16 different banks.
+    const int RS = ldb + ((20 - (ldb & 15)) & 15);
+    double* ring = rsm + (size_t)warp * ring_doubles;
+    const int nvec = ldb / 2;                                   // 16-byte pieces per row; 4 * nvec <= 128 pieces per stage
+    int p_row[4], p_dst[4], p_src[4];                           // the pieces this lane copies: row in the stage, offsets (doubles)
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int e = lane + 32 * i;
+        const int rr = e / nvec, c = e - rr * nvec;
+        p_row[i] = (e < 4 * nvec) ? rr : 1 << 20;
+        p_dst[i] = rr * RS + 2 * c;
+        p_src[i] = rr * NL * ldb + 2 * c;
+    }
+    const unsigned ring_sa = (unsigned)__cvta_generic_to_shared(ring);
+    const double* hx_l = Hx + (size_t)l * ldb;
+    auto issue = [&](int r, int stage) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            if (r + p_row[i] < re)
+                asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(ring_sa + 8u * (unsigned)(stage * 4 * RS + p_dst[i])),
+                             "l"(hx_l + (size_t)r * NL * ldb + p_src[i])
+                             : "memory");
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    };
+    const int nsteps = live ? (re - rb + 3) / 4 : 0;
+#pragma unroll
+    for (int i = 0; i < RB_ST - 1; ++i) issue(rb + 4 * i, i);      // empty groups past the end keep the group count uniform
+    __syncthreads();                                               // ErS complete
+    int stage = 0;
+    for (int it = 0; it < nsteps; ++it) {
+        const int r = rb + 4 * it;
+        issue(r + 4 * (RB_ST - 1), stage == 0 ? RB_ST - 1 : stage - 1);
+        asm volatile("cp.async.wait_group %0;" ::"n"(RB_ST - 1) : "memory");
+        __syncwarp();
+        const double* cur = ring + (size_t)stage * 4 * RS;
+        const bool ok = r + tq < re;
+        double af[MT], bf[NT];
+        const double* er = ErS + (size_t)(r - rb + tq) * AS + g;
+#pragma unroll
+        for (int u = 0; u < MT; ++u) af[u] = ok ? er[8 * u] : 0.0;
+#pragma unroll
+        for (int v = 0; v < NT; ++v) bf[v] = (ok && 8 * v + g < ldb) ? cur[tq * RS + 8 * v + g] : 0.0;
+#pragma unroll
+        for (int u = 0; u < MT; ++u)
+#pragma unroll
+            for (int v = 0; v < NT; ++v) dmma884(acc[u][v][0], acc[u][v][1], af[u], bf[v]);
+        __syncwarp();                                              // the stage is refilled RB_ST - 1 rounds later
+        stage = (stage + 1 == RB_ST) ? 0 : stage + 1;
+    }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
+    __syncthreads();                                               // the rings are reused for the weighted tiles below
+    const int tile = 8 * MT * nC;             // <= ring_doubles
+    double* mine = rsm + (size_t)warp * tile;
+#pragma unroll
+    for (int u = 0; u < MT; ++u) {
+        const int a = a0 + 8 * u + g;
+#pragma unroll
+        for (int v = 0; v < NT; ++v)
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                const int b = 8 * v + 2 * tq + e;
+                if (a < nR && b < nC) {
+                    const int d = l - (int)t.Ysel[a * nC + b];
+                    mine[(8 * u + g) * nC + b] = live ? t.Gt[d < 0 ? -d : d] * acc[u][v][e] : 0.0;
+                }
+            }
+    }
+    __syncthreads();
+    const int na = min(8 * MT, nR - a0);
+    double* out = P + ((size_t)ks * gridDim.x + blockIdx.x) * t.p + (size_t)a0 * nC;
+    for (int e = tid; e < na * nC; e += WARPS * 32) {
+        double sum = 0.0;
+#pragma unroll
+        for (int wv = 0; wv < WARPS; ++wv) sum += rsm[(size_t)wv * tile + e];
+        out[e] = sum;
+    }
+}
+
+// s[i] = sum_q P[q][i], q = 0 .. nq-1 in ascending order (four interleaved partial sums per sample, combined in a fixed order)
+__global__ void __launch_bounds__(256)
+sk_sum_partials_kernel(const double* __restrict__ P, int nq, int p, double* __restrict__ s_out) {
+    __shared__ double part[4][64];
+    const int i = blockIdx.x * 64 + (threadIdx.x & 63), c = threadIdx.x >> 6;
+    double acc = 0.0;
+    if (i < p) {
+        int q = c;
+        for (; q + 12 < nq; q += 16) {
+            const double x0 = P[(size_t)q * p + i], x1 = P[(size_t)(q + 4) * p + i];
+            const double x2 = P[(size_t)(q + 8) * p + i], x3 = P[(size_t)(q + 12) * p + i];
+            acc += x0; acc += x1; acc += x2; acc += x3;
+        }
+        for (; q < nq; q += 4) acc += P[(size_t)q * p + i];
+    }
+    part[c][threadIdx.x & 63] = acc;
+    __syncthreads();
+    if (threadIdx.x < 64 && i < p) s_out[i] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
 }
 
 // One CTA per image row.  FH row block: [nC][256] in global memory; on entry F (ignored when w_given == 0:
@@ -176,12 +388,11 @@ sk_pix_kernel(AffinityTables t, int w_given, double* __restrict__ x, double* __r
 // share the level, so its F row (nC values) lives in registers and its
 // histogram bins are register accumulators that are stored once.  Lanes = 4 pixel slots x 8 b-lanes (b = sub + 8i):
 // every Ec row is loaded once and serves both the dot (xor-shuffle tree inside the 8-lane group) and the histogram.
-//   F: [row][b][l] (read; gathered, one 32-byte sector per b: the level-major layout that would make a cell's F row
-//   contiguous costs the dot GEMM 4x in scattered 8-byte stores, measured 151 vs 37 us), H: [row][b][l] (written for the non-empty cells only; the rest was zeroed once per training
-//   call and is never touched), x: slab vector.
+//   F: [row][l][ldb] level-major (read: the nC values of a cell are contiguous), H: same layout (written for the non-empty
+//   cells only; the rest was zeroed once per training call and is never touched), x: slab vector.
 template <int NB>
 __global__ void __launch_bounds__(256)
-sk_pix_cells_kernel(AffinityTables t, CellIndex ci, int w_given, const double* __restrict__ F, double* __restrict__ x,
+sk_pix_cells_kernel(AffinityTables t, CellIndex ci, int w_given, const double* __restrict__ F, int ldb, double* __restrict__ x,
                     double* __restrict__ H) {
     const int nC = t.nC, W = t.cols;
     const int lane = threadIdx.x & 31, q = lane >> 3, sub = lane & 7;
@@ -205,7 +416,7 @@ sk_pix_cells_kernel(AffinityTables t, CellIndex ci, int w_given, const double* _
 #pragma unroll
         for (int i = 0; i < NB; ++i) {
             const int b = sub + 8 * i;
-            f[i] = (w_given && b < nC) ? F[((size_t)rl * nC + b) * NL + lev] : 0.0;      // F[row][b][l]: one sector per b
+            f[i] = (w_given && b < nC) ? F[((size_t)rl * NL + lev) * ldb + b] : 0.0;      // F[row][l][b]: the cell's row is contiguous
             acc[i] = 0.0;
         }
         for (int p0 = 0; p0 < np; p0 += 4) {
@@ -242,7 +453,7 @@ sk_pix_cells_kernel(AffinityTables t, CellIndex ci, int w_given, const double* _
 #pragma unroll
             for (int i = 0; i < NB; ++i) {
                 const int b = sub + 8 * i;
-                if (b < nC) H[((size_t)rl * nC + b) * NL + lev] = acc[i];
+                if (b < nC) H[((size_t)rl * NL + lev) * ldb + b] = acc[i];
             }
         }
     }
@@ -333,8 +544,9 @@ sk_reduce_final_kernel(AffinityTables t, const double* __restrict__ Mpart, int n
 }
 
 struct SkGeom {
-    int nRp, MT, nab, nks;
-    size_t fh_doubles, mpart_doubles, pix_smem, dot_smem;
+    int nRp, MT, nab, nks, ldb;
+    int NTb, MTb, nabb, nksb, ringb, wrb, lgb;   // level-major GEMMs (wrb warps = levels per CTA of the reduce GEMM, lgb level groups) of the cell path: n-tiles of sample columns, m-tiles of grid rows per CTA
+    size_t fh_doubles, mpart_doubles, pix_smem, dot_smem, dot_nb_smem, red_nb_smem;
 };
 
 SkGeom sk_geometry(const AffinityTables& t) {
@@ -345,13 +557,30 @@ SkGeom sk_geometry(const AffinityTables& t) {
     g.MT = cdiv(tiles, g.nab);
     g.nRp = g.nab * g.MT * 8;
     g.nks = std::max(1, std::min(std::max(1, t.nrows / 32), (2 * sm_count()) / std::max(1, t.nC * g.nab)));
-    g.fh_doubles = (size_t)t.nrows * t.nC * NL;
+    g.ldb = (t.nC + 3) & ~3;                                  // level-major tables of the cell path: F[row][l][ldb]
+    g.fh_doubles = (size_t)t.nrows * g.ldb * NL;
     g.mpart_doubles = (size_t)g.nks * t.nC * g.nRp * NL;
     const int nCp = t.nC | 1;
     g.pix_smem = ((size_t)NL * nCp + 32 * (size_t)t.nC + t.cols) * sizeof(double) + ((t.cols + 15) / 16) * 16 + 64;
     const int nR4 = (t.nR + 3) & ~3;
     const int lda = nR4 + ((12 - (nR4 & 15)) & 15);
     g.dot_smem = ((size_t)DG_ROWS * lda + NL + nR4) * sizeof(double) + (size_t)nR4 * sizeof(int) + 64;
+    g.NTb = std::max(1, std::min(8, cdiv(t.nC, 8)));
+    static const int mt_for_nt[9] = {0, 7, 7, 7, 7, 5, 4, 4, 3};        // MTb * NTb * 2 <= 56 accumulators per lane
+    g.MTb = mt_for_nt[g.NTb];
+    g.nabb = cdiv(cdiv(t.nR, 8), g.MTb);
+    g.wrb = (g.MTb * g.NTb <= 25) ? 12 : 8;                   // three warps per sub-core where the tile leaves the registers for it
+    g.lgb = cdiv(NL, g.wrb);
+    const int st = 8 * g.NTb + 4;
+    g.dot_nb_smem = ((size_t)32 * lda + 16 * NL + (size_t)nR4 * st) * sizeof(double) + (size_t)nR4 * st * sizeof(int) + 64;
+    g.ringb = (int)std::max((size_t)(8 * g.MTb) * t.nC, (size_t)RB_ST * 4 * (g.ldb + 16));
+    g.ringb = (g.ringb + 1) & ~1;
+    // row splits: one wave of one CTA per SM; the Er slice of a split sits in shared memory next to the rings
+    const long long room = 227 * 1024 - 64 - (long long)g.wrb * g.ringb * 8;
+    const int cap_rows = (int)std::max<long long>(8, room / ((8 * g.MTb + 4) * 8) - 1);
+    g.nksb = std::max({1, std::min(std::max(1, t.nrows / 32), sm_count() / (g.lgb * g.nabb)), cdiv(t.nrows, cap_rows)});
+    const int rows_split = cdiv(t.nrows, g.nksb) + 1;
+    g.red_nb_smem = ((size_t)g.wrb * g.ringb + (size_t)rows_split * (8 * g.MTb + 4)) * sizeof(double) + 64;
     return g;
 }
 
@@ -359,12 +588,12 @@ SkGeom sk_geometry(const AffinityTables& t) {
 
 bool sinkhorn_cells_supported(const AffinityTables& t) {
     const SkGeom g = sk_geometry(t);
-    return (t.nC <= 64 || g.pix_smem <= 227 * 1024) && g.dot_smem <= 227 * 1024;
+    return t.nC <= 64 ? (g.dot_nb_smem <= 227 * 1024 && g.red_nb_smem <= 227 * 1024) : (g.pix_smem <= 227 * 1024 && g.dot_smem <= 227 * 1024);
 }
 
 size_t sinkhorn_cells_scratch_doubles(const AffinityTables& t) {
     const SkGeom g = sk_geometry(t);
-    return 2 * g.fh_doubles + g.mpart_doubles + 8;
+    return 2 * g.fh_doubles + std::max(g.mpart_doubles, (size_t)g.nksb * g.lgb * t.p) + 8;
 }
 
 // Zeroes the histogram table once per training call (the cell pass only ever writes the non-empty cells).
@@ -374,15 +603,30 @@ void sinkhorn_cells_prepare(const AffinityTables& t, double* scratch, cudaStream
 }
 
 template <int NB>
-static void launch_pc(const AffinityTables& t, const CellIndex& ci, int w_given, const double* F, double* x, double* H,
+static void launch_pc(const AffinityTables& t, const CellIndex& ci, int w_given, const double* F, int ldb, double* x, double* H,
                       cudaStream_t s) {
-    sk_pix_cells_kernel<NB><<<sm_count() * 8, 256, 0, s>>>(t, ci, w_given, F, x, H);
+    sk_pix_cells_kernel<NB><<<sm_count() * 8, 256, 0, s>>>(t, ci, w_given, F, ldb, x, H);
     NLE_LAUNCH_CHECK();
 }
 
 template <int MT>
 static void launch_rg(const AffinityTables& t, const SkGeom& g, const double* FH, double* Mpart, cudaStream_t s) {
     sk_reduce_gemm_kernel<MT><<<dim3(t.nC, g.nks, g.nab), 256, 0, s>>>(t, FH, g.nks, g.nRp, Mpart);
+    NLE_LAUNCH_CHECK();
+}
+
+template <int NT, int LQ, int RT>
+static void launch_dot_nb(const AffinityTables& t, const SkGeom& g, const double* w, double* F, cudaStream_t s) {
+    constexpr int LW = (RT == 4) ? 4 : 8;       // 8 RT rows x 8 LW levels per CTA: 32 x 32 or 16 x 64 -> the same number of CTAs
+    NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_nb_kernel<NT, LQ, RT, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_nb_smem));
+    sk_dot_gemm_nb_kernel<NT, LQ, RT, LW><<<dim3(cdiv(t.nrows, 8 * RT), NL / (8 * LW)), 256, g.dot_nb_smem, s>>>(t, w, g.ldb, F);
+    NLE_LAUNCH_CHECK();
+}
+
+template <int MT, int NT, int WARPS>
+static void launch_red_nb(const AffinityTables& t, const SkGeom& g, const double* Hx, double* P, cudaStream_t s) {
+    NLE_CUDA(cudaFuncSetAttribute(sk_reduce_gemm_nb_kernel<MT, NT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.red_nb_smem));
+    sk_reduce_gemm_nb_kernel<MT, NT, WARPS><<<dim3(g.lgb, g.nksb, g.nabb), WARPS * 32, g.red_nb_smem, s>>>(t, Hx, g.ldb, g.nksb, g.ringb, P);
     NLE_LAUNCH_CHECK();
 }
 
@@ -397,28 +641,56 @@ void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const d
     double* Hc = scratch + g.fh_doubles;               // cell path: separate histogram table
     double* Mpart = scratch + 2 * g.fh_doubles;
     if (!cells) NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
-    NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_smem));
     if (w) {
-        sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH, 0);
-        NLE_LAUNCH_CHECK();
+        if (cells) {
+            switch (g.NTb) {
+                case 1: launch_dot_nb<1, 1, 4>(t, g, w, FH, s); break;
+                case 2: launch_dot_nb<2, 1, 4>(t, g, w, FH, s); break;
+                case 3: launch_dot_nb<3, 1, 4>(t, g, w, FH, s); break;
+                case 4: launch_dot_nb<4, 1, 4>(t, g, w, FH, s); break;
+                case 5: launch_dot_nb<5, 1, 4>(t, g, w, FH, s); break;
+                case 6: launch_dot_nb<6, 1, 2>(t, g, w, FH, s); break;
+                case 7: launch_dot_nb<7, 1, 2>(t, g, w, FH, s); break;
+                default: launch_dot_nb<8, 1, 2>(t, g, w, FH, s); break;
+            }
+        } else {
+            NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_smem));
+            sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH);
+            NLE_LAUNCH_CHECK();
+        }
     }
     const double* Hx = FH;
     if (cells) {
         const int nb = cdiv(t.nC, 8);
         switch (nb) {
-            case 1: launch_pc<1>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            case 2: launch_pc<2>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            case 3: launch_pc<3>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            case 4: launch_pc<4>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            case 5: launch_pc<5>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            case 6: launch_pc<6>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            case 7: launch_pc<7>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
-            default: launch_pc<8>(t, *ci, w ? 1 : 0, FH, x, Hc, s); break;
+            case 1: launch_pc<1>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            case 2: launch_pc<2>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            case 3: launch_pc<3>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            case 4: launch_pc<4>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            case 5: launch_pc<5>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            case 6: launch_pc<6>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            case 7: launch_pc<7>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
+            default: launch_pc<8>(t, *ci, w ? 1 : 0, FH, g.ldb, x, Hc, s); break;
         }
         Hx = Hc;
     } else {
         sk_pix_kernel<<<t.nrows, 256, g.pix_smem, s>>>(t, w ? 1 : 0, x, FH);
         NLE_LAUNCH_CHECK();
+    }
+    if (cells) {
+        switch (g.NTb) {
+            case 1: launch_red_nb<7, 1, 12>(t, g, Hx, Mpart, s); break;
+            case 2: launch_red_nb<7, 2, 12>(t, g, Hx, Mpart, s); break;
+            case 3: launch_red_nb<7, 3, 12>(t, g, Hx, Mpart, s); break;
+            case 4: launch_red_nb<7, 4, 8>(t, g, Hx, Mpart, s); break;
+            case 5: launch_red_nb<5, 5, 12>(t, g, Hx, Mpart, s); break;
+            case 6: launch_red_nb<4, 6, 12>(t, g, Hx, Mpart, s); break;
+            case 7: launch_red_nb<4, 7, 8>(t, g, Hx, Mpart, s); break;
+            default: launch_red_nb<3, 8, 12>(t, g, Hx, Mpart, s); break;
+        }
+        sk_sum_partials_kernel<<<cdiv(t.p, 64), 256, 0, s>>>(Mpart, g.nksb * g.lgb, t.p, s_out);
+        NLE_LAUNCH_CHECK();
+        return;
     }
     switch (g.MT) {
         case 1: launch_rg<1>(t, g, Hx, Mpart, s); break;

@@ -432,3 +432,26 @@ def test_two_slab_sharding_equals_single(nb):
     for j in range(Vf.shape[1]):
         s = np.sign(np.dot(V[:, j], Vf[:, j]))
         assert np.allclose(s * V[:, j], Vf[:, j], atol=1e-8)
+
+
+# every width class of the level-major Sinkhorn GEMMs (sk_dot_gemm_nb_kernel / sk_reduce_gemm_nb_kernel are instantiated per
+# number of 8-column tiles of the sample grid, 1 .. 8) and the m-tile blocking of the grid rows (7, 5, 4, 3 tiles per CTA)
+@pytest.mark.parametrize("grid", [(6, 7), (5, 12), (9, 20), (60, 28), (4, 36), (7, 44), (34, 52), (3, 60), (58, 64)])
+def test_sinkhorn_gemm_width_classes_match_oracle(nb, grid):
+    nR, nC = grid
+    L = synth_lum(max(64, nR + 3), max(96, nC + 5), seed=nR * 100 + nC)
+    a = (nR, nC, 35.0, 28.0, 5, 8)
+    f = nb.NLEFilter().trainFilter(L, *a)
+    fo = O.train_dense(L.astype(np.float64), *a)
+    st, inf = fo.stages, f.info()
+    assert (inf.p, inf.r, inf.r2, inf.k) == (st["p"], st["r"], st["r2"], fo.eigvals.size)
+    cg = f.stage(3)
+    co = np.empty_like(cg)
+    co[st["perm"]] = st["c"]
+    mask = np.ones(cg.size, bool)
+    mask[st["perm"][:inf.p]] = False
+    assert np.abs(cg[mask] - co[mask]).max() <= 1e-9 * np.abs(co).max()           # Sinkhorn scaling vector c on the rest pixels
+    assert sq_close(f.eigvals, fo.eigvals)
+    w = [2.0, 3.0, 4.0, 1.0]
+    d = np.abs(f.enhanceLuminance(L, w).astype(int) - O.enhance_luminance(fo, L, w).astype(int))
+    assert d.max() <= 1 and (d <= 1).mean() >= PIX_FRAC
