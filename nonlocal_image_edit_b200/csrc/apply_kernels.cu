@@ -465,7 +465,7 @@ void launch_vtz(long long nloc, int k, const double* V, const uint8_t* z_u8, con
         const int zmode = z_bgr ? Z_BGR : (z_u8 ? Z_U8 : Z_F64);
         const uint8_t* z8 = z_bgr ? z_bgr : z_u8;
         auto go = [&](auto kern) {
-            NLE_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            allow_max_dynamic_smem((const void*)kern);
             kern<<<g.grid, AP_THREADS, smem, s>>>(nloc, k, V, z8, z_f64, zmode, g, scratch);
         };
         if (nv == 1) go(vtz_tma_kernel<1>); else go(vtz_tma_kernel<2>);
@@ -496,7 +496,7 @@ void launch_recompose(long long nloc, int k, const double* V, const double* g, d
         const ApplyGeom geo = apply_geometry(nloc, k);
         const size_t smem = recompose_smem(geo, k);
         const int omode = out_bgr ? OUT_BGR : (out_u8 ? OUT_U8 : OUT_F64);
-        NLE_CUDA(cudaFuncSetAttribute(recompose_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allow_max_dynamic_smem((const void*)recompose_tma_kernel);
         recompose_tma_kernel<<<geo.grid, AP_THREADS, smem, s>>>(nloc, k, V, g, omode, out_f64, out_bgr ? out_bgr : out_u8, bgr_in, geo);
         NLE_LAUNCH_CHECK();
     } else {

@@ -656,7 +656,7 @@ void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch
     const size_t hsm = (size_t)2 * HS * t.nC * sizeof(double) + (size_t)(256 * 3 + 260 + 8 + t.cols) * sizeof(int) +
                        2 * (size_t)((t.cols + 15) / 16) * 16 + 64;
     if (hsm > 227 * 1024) throw Unsupported{"gram: image too wide for the per-row cell sort (cols=" + std::to_string(t.cols) + ")"};
-    NLE_CUDA(cudaFuncSetAttribute(cell_hist_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)hsm));
+    allow_max_dynamic_smem((const void*)cell_hist_kernel);
     for (int r0 = 0, batch = 0; r0 < t.nrows; r0 += g.rows_batch, ++batch) {
         AffinityTables tb = t;
         tb.row0 = t.row0 + r0;
@@ -711,8 +711,8 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
     const int nR4 = (t.nR + 3) & ~3;
     const size_t fsm = ((size_t)nR4 * XC_N + 256 + (size_t)XC_ERROWS * nR4) * sizeof(double) + (size_t)(nR4 + 2) * sizeof(int) + 16;
     if (ism > 227 * 1024 || fsm > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
-    NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
-    NLE_CUDA(cudaFuncSetAttribute(ext_fx_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fsm));
+    allow_max_dynamic_smem((const void*)ext_index_kernel);
+    allow_max_dynamic_smem((const void*)ext_fx_kernel);
     for (int r0 = 0; r0 < t.nrows; r0 += g.rows_batch) {
         AffinityTables tb = t;
         tb.row0 = t.row0 + r0;
@@ -761,7 +761,7 @@ CellIndex build_cell_index(const AffinityTables& t, double* scratch, cudaStream_
     int* sorted = cell_pcount + cells;
     const size_t ism = (size_t)(256 * 3 + 260 + 8) * sizeof(int) + ((t.cols + 15) / 16) * 16 + 16;
     if (ism > 227 * 1024) throw Unsupported{"cell index: image too wide (cols=" + std::to_string(t.cols) + ")"};
-    NLE_CUDA(cudaFuncSetAttribute(ext_index_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ism));
+    allow_max_dynamic_smem((const void*)ext_index_kernel);
     cell_count_kernel<<<std::min(t.nrows, sm_count() * 8), 256, 0, s>>>(t.lum, t.nrows, t.cols, cnt);
     NLE_LAUNCH_CHECK();
     cell_scan_kernel<<<1, 1024, 0, s>>>(cnt, t.nrows, koff);

@@ -125,6 +125,12 @@ __device__ __forceinline__ void dmma884(double& d0, double& d1, double a, double
 #endif
 
 int sm_count();
+// Largest shared memory a CTA may opt into on the current device.
+int smem_optin_max();
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) with the largest value the kernel can take (opt-in maximum minus its static
+// shared memory), done once per (kernel, device).  Never the size of the launch at hand: the attribute is per function and
+// device, and host threads that train different slabs on one device would otherwise lower it under each other's launches.
+void allow_max_dynamic_smem(const void* kernel);
 
 // ---- dense.cu : column-major FP64 building blocks ------------------------------------------
 // C(m x n) = alpha * op(A) * op(B) + beta * C

@@ -5,6 +5,9 @@
 #include "common.cuh"
 
 #include <algorithm>
+#include <mutex>
+#include <set>
+#include <utility>
 
 namespace nle {
 
@@ -88,6 +91,33 @@ int sm_count() {
         cached[dev] = n;
     }
     return n;
+}
+
+int smem_optin_max() {
+    static int cached[64] = {0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) dev = 0;
+    int v = cached[dev];
+    if (!v) {
+        cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+        if (v <= 0) v = 227 * 1024;
+        cached[dev] = v;
+    }
+    return v;
+}
+
+void allow_max_dynamic_smem(const void* kernel) {
+    static std::mutex mu;
+    static std::set<std::pair<const void*, int>> done;
+    int dev = 0;
+    NLE_CUDA(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(mu);
+    if (done.count({kernel, dev})) return;
+    cudaFuncAttributes fa;
+    NLE_CUDA(cudaFuncGetAttributes(&fa, kernel));
+    NLE_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_optin_max() - (int)fa.sharedSizeBytes));
+    done.insert({kernel, dev});
 }
 
 // ------------------------------------------------------------------------------------------

@@ -420,7 +420,7 @@ static int sym_eig_once(const double* M, int ldm, int n, double eps, bool psd_hi
     double tol = (double)(npad < 16 ? 16 : npad) * 1.1102230246251565e-16;
     int max_sweeps = 60, max_inner = ws.max_inner;
     void* kfn = (B2 == 16) ? (void*)jacobi_kernel<16> : (void*)jacobi_kernel<8>;
-    NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    allow_max_dynamic_smem((const void*)kfn);
     int per_sm = 0;
     NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, 256, smem));
     if (per_sm < 1) throw Unsupported{"eigensolver: Jacobi kernel does not fit on an SM"};

@@ -1451,7 +1451,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
                 const int qmax = cdiv(n, Gt);
                 const size_t sm = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
                 if (sm > (size_t)max_smem) break;
-                NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
+                allow_max_dynamic_smem((const void*)kfn);
                 cfg.gridDim = dim3(Gt);
                 cfg.dynamicSmemBytes = sm;
                 cfg.numAttrs = 1;
@@ -1466,7 +1466,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
             }
         }
         while (G >= S) {
-            NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            allow_max_dynamic_smem((const void*)kfn);
             cfg.gridDim = dim3(G);
             cfg.dynamicSmemBytes = smem;
             cfg.numAttrs = 2;
@@ -1501,7 +1501,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     if (!trd_done) {
         size_t smem = (3 * (size_t)n + 2 * kTrdWarps) * sizeof(double);
         const void* kfn = (const void*)tridiag_kernel;
-        NLE_CUDA(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allow_max_dynamic_smem((const void*)kfn);
         int per_sm = 0;
         NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
         if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(n) + ")"};
@@ -1529,7 +1529,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         const int nmerge = 1 << t;
         const int nm_max = (n + nmerge - 1) / nmerge;
         const size_t smem = (size_t)nm_max * (3 * sizeof(double) + 2 * sizeof(int));
-        NLE_CUDA(cudaFuncSetAttribute(dc_setup_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allow_max_dynamic_smem((const void*)dc_setup_kernel);
         const int threads = nm_max >= 1024 ? 1024 : (nm_max >= 256 ? 256 : 64);
         dc_setup_kernel<<<nmerge, threads, smem, s>>>(n, t, e0, dc, Qc, n, dn, a);
         NLE_LAUNCH_CHECK();
@@ -1570,7 +1570,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         int wpb = std::max(2, cdiv(std::max(m, 1), sm_count()));
         wpb = std::min(wpb, std::min(max_wpb, 16));
         const size_t smem = (size_t)(wpb + 6) * n * sizeof(double);
-        NLE_CUDA(cudaFuncSetAttribute(backtransform_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        allow_max_dynamic_smem((const void*)backtransform_kernel);
         int* collist = a.colmap;  // the D&C column map is free again
         dc_collist_kernel<<<cdiv(n, 128), 128, 0, s>>>(order, n, collist);
         NLE_LAUNCH_CHECK();
@@ -1587,7 +1587,7 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
             if (ws.wyT.n < (size_t)nblocks * kWyB * kWyB) ws.wyT.alloc((size_t)nblocks * kWyB * kWyB);
             bt_tfactor_kernel<<<nblocks, 256, 0, s>>>(As, n, n, tau, nrefl, ws.wyT.p);
             NLE_LAUNCH_CHECK();
-            NLE_CUDA(cudaFuncSetAttribute(bt_wy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wy_smem));
+            allow_max_dynamic_smem((const void*)bt_wy_kernel);
             bt_wy_kernel<<<cdiv(m, 8), 256, wy_smem, s>>>(As, n, n, ws.wyT.p, nblocks, nrefl, Qc, n, collist, count, vec_limit);
             NLE_LAUNCH_CHECK();
         } else if (m > 0) {

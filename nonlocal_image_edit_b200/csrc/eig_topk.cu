@@ -232,7 +232,7 @@ bool sym_eig_topk(const double* A, int n, int k, double eps, double* Z, double* 
     b.fail = d_fail.p;
     NLE_CUDA(cudaMemsetAsync(b.fail, 0, 4 * sizeof(int), s));
     const size_t csm = (size_t)m * (m + 1) * sizeof(double);      // two packed triangles
-    NLE_CUDA(cudaFuncSetAttribute(topk_chol_inv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)csm));
+    allow_max_dynamic_smem((const void*)topk_chol_inv_kernel);
     int ngemm = 0;
 
     auto ax = [&](const double* Xin, double* out, double alpha, double beta, const double* P, double gamma, const double* Zt) {

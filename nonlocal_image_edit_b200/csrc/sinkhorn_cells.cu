@@ -618,14 +618,15 @@ static void launch_rg(const AffinityTables& t, const SkGeom& g, const double* FH
 template <int NT, int LQ, int RT>
 static void launch_dot_nb(const AffinityTables& t, const SkGeom& g, const double* w, double* F, cudaStream_t s) {
     constexpr int LW = (RT == 4) ? 4 : 8;       // 8 RT rows x 8 LW levels per CTA: 32 x 32 or 16 x 64 -> the same number of CTAs
-    NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_nb_kernel<NT, LQ, RT, LW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_nb_smem));
+    // the device maximum, not this call's size: host threads that train different slabs on one device share the attribute
+    allow_max_dynamic_smem((const void*)sk_dot_gemm_nb_kernel<NT, LQ, RT, LW>);
     sk_dot_gemm_nb_kernel<NT, LQ, RT, LW><<<dim3(cdiv(t.nrows, 8 * RT), NL / (8 * LW)), 256, g.dot_nb_smem, s>>>(t, w, g.ldb, F);
     NLE_LAUNCH_CHECK();
 }
 
 template <int MT, int NT, int WARPS>
 static void launch_red_nb(const AffinityTables& t, const SkGeom& g, const double* Hx, double* P, cudaStream_t s) {
-    NLE_CUDA(cudaFuncSetAttribute(sk_reduce_gemm_nb_kernel<MT, NT, WARPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.red_nb_smem));
+    allow_max_dynamic_smem((const void*)sk_reduce_gemm_nb_kernel<MT, NT, WARPS>);
     sk_reduce_gemm_nb_kernel<MT, NT, WARPS><<<dim3(g.lgb, g.nksb, g.nabb), WARPS * 32, g.red_nb_smem, s>>>(t, Hx, g.ldb, g.nksb, g.ringb, P);
     NLE_LAUNCH_CHECK();
 }
@@ -640,7 +641,7 @@ void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const d
     double* FH = scratch;                              // staged path: F, overwritten in place by the histogram
     double* Hc = scratch + g.fh_doubles;               // cell path: separate histogram table
     double* Mpart = scratch + 2 * g.fh_doubles;
-    if (!cells) NLE_CUDA(cudaFuncSetAttribute(sk_pix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.pix_smem));
+    if (!cells) allow_max_dynamic_smem((const void*)sk_pix_kernel);
     if (w) {
         if (cells) {
             switch (g.NTb) {
@@ -654,7 +655,7 @@ void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const d
                 default: launch_dot_nb<8, 1, 2>(t, g, w, FH, s); break;
             }
         } else {
-            NLE_CUDA(cudaFuncSetAttribute(sk_dot_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)g.dot_smem));
+            allow_max_dynamic_smem((const void*)sk_dot_gemm_kernel);
             sk_dot_gemm_kernel<<<dim3(cdiv(t.nrows, DG_ROWS), t.nC), 256, g.dot_smem, s>>>(t, w, FH);
             NLE_LAUNCH_CHECK();
         }
