@@ -395,7 +395,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     TmpBuf<double> Gp((size_t)p * p);
     {
         TmpBuf<double> gscratch(gram_cells_scratch_doubles(tb));
-        launch_gram_cells(tb, cfull.p, gscratch.p, Gp.p, s);
+        launch_gram_cells(tb, cfull.p, gscratch.p, Gp.p, s, &cidx);
         clk.mark(4);                                        // cell sort + histograms + gram_cells_kernel + reduce
         do_allreduce(f.get(), Gp.p, (size_t)p * p);
     }

@@ -216,6 +216,63 @@ cell_hist_kernel(AffinityTables t, const double* __restrict__ cvec, const int* _
 }
 
 
+// Hh[cell][q(b, b')] = sum_{col in cell} (c_j^2 Ec[col][b]) * Ec[col][b'],  b <= b', on the FP64 tensor pipe: one warp per cell of
+// an existing cell index (the one the Sinkhorn passes use), the cell's pixels four at a time as the K dimension, the sample
+// column on both the M and the N axis -- the same Ec values serve as A (scaled by c_j^2) and as B fragment, loaded once as
+// 64-byte runs; only the tiles on and above the diagonal are issued.  (cell_hist_kernel above does the same sums with two
+// shared-memory look-ups per multiply-add and is bound by shared-memory bandwidth: 0.75 ms per 1024 x 1024 image against 0.86 G
+// multiply-adds; it remains for slabs whose Hh table has to be built in batches of rows.)  Pixels are taken in ascending
+// column order, as there.
+template <int NB>
+__global__ void __launch_bounds__(256)
+cell_hist_dmma_kernel(AffinityTables t, CellIndex ci, const double* __restrict__ cvec, int ld, double* __restrict__ Hh) {
+    const int nC = t.nC, W = t.cols;
+    const int lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
+    const int K = ci.koff[t.nrows];
+    const int nwarps = gridDim.x * (blockDim.x >> 5);
+    for (int cell = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); cell < K; cell += nwarps) {
+        const int np = ci.pcount[cell], rl = ci.row[cell];
+        const int* pix = ci.sorted + ci.pstart[cell];
+        const double* cg = cvec + (size_t)rl * W;
+        double acc[NB][NB][2];
+#pragma unroll
+        for (int u = 0; u < NB; ++u)
+#pragma unroll
+            for (int v = u; v < NB; ++v) acc[u][v][0] = acc[u][v][1] = 0.0;
+        for (int p0 = 0; p0 < np; p0 += 4) {
+            const bool ok = p0 + tq < np;
+            const int col = ok ? pix[p0 + tq] : 0;
+            const double cj = ok ? cg[col] : 0.0;
+            const double c2 = cj * cj;
+            const double* ecr = t.Ec + (size_t)col * nC + g;
+            double ev[NB], av[NB];
+#pragma unroll
+            for (int u = 0; u < NB; ++u) {
+                ev[u] = (ok && 8 * u + g < nC) ? ecr[8 * u] : 0.0;
+                av[u] = c2 * ev[u];
+            }
+#pragma unroll
+            for (int u = 0; u < NB; ++u)
+#pragma unroll
+                for (int v = u; v < NB; ++v) dmma884(acc[u][v][0], acc[u][v][1], av[u], ev[v]);
+        }
+        double* h = Hh + (size_t)cell * ld;
+#pragma unroll
+        for (int u = 0; u < NB; ++u) {
+            const int b = 8 * u + g;
+            if (b >= nC) continue;
+            double* hb = h + pair_start(b, nC) - b;
+#pragma unroll
+            for (int v = u; v < NB; ++v)
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    const int bp = 8 * v + 2 * tq + e;
+                    if (bp >= b && bp < nC) hb[bp] = acc[u][v][e];
+                }
+        }
+    }
+}
+
 // One warp per task = (pair (b,b'), a-block, a'-block) x K split.  Tile: T x T with T = 8*MT grid rows.
 //   A[k][a ] = Er[row_k][a ] * Gt[|lev_k - Y[a ][b ]|]
 //   B[k][a'] = Er[row_k][a'] * Gt[|lev_k - Y[a'][b']|] * Hh[k][pair]
@@ -646,10 +703,43 @@ static void launch_gc(const AffinityTables& tb, const CellGeom& g, const int* ko
     NLE_LAUNCH_CHECK();
 }
 
-void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s) {
+template <int NB>
+static void launch_hist_dmma(const AffinityTables& t, const CellIndex& ci, const double* c, int ld, double* Hh, cudaStream_t s) {
+    cell_hist_dmma_kernel<NB><<<sm_count() * 8, 256, 0, s>>>(t, ci, c, ld, Hh);
+    NLE_LAUNCH_CHECK();
+}
+
+void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s, const CellIndex* ci) {
     const CellGeom g = cell_geometry(t);
     double* Hh = scratch;
     double* part = Hh + g.hh_doubles;
+    if (ci != nullptr && g.rows_batch >= t.nrows && t.nC <= 64) {
+        // the slab's cell index exists already and Hh fits in one batch: histograms on the tensor pipe, no second sort
+        switch (cdiv(t.nC, 8)) {
+            case 1: launch_hist_dmma<1>(t, *ci, c, g.ld, Hh, s); break;
+            case 2: launch_hist_dmma<2>(t, *ci, c, g.ld, Hh, s); break;
+            case 3: launch_hist_dmma<3>(t, *ci, c, g.ld, Hh, s); break;
+            case 4: launch_hist_dmma<4>(t, *ci, c, g.ld, Hh, s); break;
+            case 5: launch_hist_dmma<5>(t, *ci, c, g.ld, Hh, s); break;
+            case 6: launch_hist_dmma<6>(t, *ci, c, g.ld, Hh, s); break;
+            case 7: launch_hist_dmma<7>(t, *ci, c, g.ld, Hh, s); break;
+            default: launch_hist_dmma<8>(t, *ci, c, g.ld, Hh, s); break;
+        }
+        switch (g.MT * 10 + g.NT) {
+            case 11: launch_gc<1, 1>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            case 22: launch_gc<2, 2>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            case 33: launch_gc<3, 3>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            case 44: launch_gc<4, 4>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            case 55: launch_gc<5, 5>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            case 64: launch_gc<6, 4>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            case 74: launch_gc<7, 4>(t, g, ci->koff, ci->lev, Hh, 0, part, s); break;
+            default: throw Unsupported{"gram: no kernel instance for the warp tile " + std::to_string(g.MT) + " x " + std::to_string(g.NT)};
+        }
+        gram_cells_reduce_kernel<<<dim3(cdiv(t.p, 128), t.p), 128, 0, s>>>(part, t.p, t.nR, t.nC, g.TA, g.TB, g.nabA, g.nabB,
+                                                                           g.ntasks, g.nsplit, G);
+        NLE_LAUNCH_CHECK();
+        return;
+    }
     uint8_t* cell_lev = reinterpret_cast<uint8_t*>(part + g.part_doubles);
     int* cnt = reinterpret_cast<int*>(cell_lev + ((g.lev_bytes + 7) / 8) * 8);
     int* koff = cnt + g.rows_batch + 4;

@@ -55,7 +55,10 @@ void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const d
 // Weighted Gram  G = sum_j c_j^2 k_j k_j^T  (p x p, column-major, both triangles) over the slab, contracted over the
 // (image row, luminance level) cells (cell_kernels.cu): K_cells*p*(p+1) flop instead of N*p*(p+1).
 size_t gram_cells_scratch_doubles(const AffinityTables& t);
-void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s);
+// ci (optional): the slab's cell index (build_cell_index); with it the per-cell histograms Hh are built on the tensor pipe from
+// that index instead of sorting every image row again.
+void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch, double* G, cudaStream_t s,
+                       const CellIndex* ci = nullptr);
 
 // Extension  V_j = c_j * k_j^T Y  for the non-sample slab pixels.  Y: p x k (column-major), V: (nrows*cols) x k ROW-major
 // (k fastest).  Through the (image row, luminance level) cells (cell_kernels.cu): K_cells*p*k + N*nC*k multiply-adds.
