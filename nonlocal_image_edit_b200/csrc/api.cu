@@ -501,7 +501,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     dgemm(false, false, p, k, r, 1.0, U.p, p, Y1.p, r, 0.0, Y.p, p, s);
     {
         TmpBuf<double> xscratch(extension_cells_scratch_doubles(tb, k));
-        launch_extension_cells(tb, cfull.p, Y.p, k, xscratch.p, f->V.p, s);
+        launch_extension_cells(tb, cfull.p, Y.p, k, xscratch.p, f->V.p, s, &cidx);
     }
     clk.mark(7);
     NLE_CUDA(cudaStreamSynchronize(s));

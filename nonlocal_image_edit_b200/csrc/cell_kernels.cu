@@ -782,7 +782,7 @@ size_t extension_cells_scratch_doubles(const AffinityTables& t, int k) {
 
 // V_j = c_j k_j^T Y for the non-sample slab pixels (contract in kernels.cuh).
 void launch_extension_cells(const AffinityTables& t, const double* c, const double* Y, int k, double* scratch, double* V,
-                            cudaStream_t s) {
+                            cudaStream_t s, const CellIndex* ci) {
     if (k <= 0 || t.nrows <= 0) return;
     const ExtGeom g = ext_geometry(t, k);
     double* FX = scratch;
@@ -803,6 +803,15 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
     if (ism > 227 * 1024 || fsm > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
     allow_max_dynamic_smem((const void*)ext_index_kernel);
     allow_max_dynamic_smem((const void*)ext_fx_kernel);
+    if (ci != nullptr && g.rows_batch >= t.nrows) {
+        // one batch and the slab's cell index exists already: no second per-row sort
+        const int cap_cells = g.capc * t.nrows;
+        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), XC_THREADS, fsm, s>>>(t, ci->koff, ci->lev, ci->row, Yt, g.kp, FX);
+        NLE_LAUNCH_CHECK();
+        ext_pix_kernel<<<sm_count() * 8, 256, 0, s>>>(t, ci->koff, ci->row, ci->pstart, ci->pcount, ci->sorted, c, FX, g.kp, g.nvb, k, V);
+        NLE_LAUNCH_CHECK();
+        return;
+    }
     for (int r0 = 0; r0 < t.nrows; r0 += g.rows_batch) {
         AffinityTables tb = t;
         tb.row0 = t.row0 + r0;

@@ -63,8 +63,9 @@ void launch_gram_cells(const AffinityTables& t, const double* c, double* scratch
 // Extension  V_j = c_j * k_j^T Y  for the non-sample slab pixels.  Y: p x k (column-major), V: (nrows*cols) x k ROW-major
 // (k fastest).  Through the (image row, luminance level) cells (cell_kernels.cu): K_cells*p*k + N*nC*k multiply-adds.
 size_t extension_cells_scratch_doubles(const AffinityTables& t, int k);
+// ci (optional): the slab's cell index; used instead of a second per-row sort when FX fits in one batch of rows.
 void launch_extension_cells(const AffinityTables& t, const double* c, const double* Y, int k, double* scratch, double* V,
-                            cudaStream_t s);
+                            cudaStream_t s, const CellIndex* ci = nullptr);
 // V[pixel(sel[i0+i]) - slab offset][:] = src(i, :)  for samples that fall in the slab.  src: n x k col-major (ld).
 void launch_scatter_rows(const AffinityTables& t, const int32_t* sel, int i0, int n, const double* src,
                          int ld, int k, double* V, cudaStream_t s);
