@@ -10,8 +10,8 @@ Metric (BASELINE.json): enhance MP/s (p=1600, k=50).  A "step" = train + enhance
 N=1 workload = BASELINE.json configs[2]: synthetic 1024x1024 gray image, 40x40=1600 samples,
 hx=500 hy=30, 20 Sinkhorn iterations, k=50, weights 2 3 4 1 (SURVEY.md 8d "S-gray-1024").
 N>1 = weak scaling: the image grows to (1024*N) x 1024 and is sharded by image rows, one slab per
-rank; NCCL (the library's own communicator, csrc/nccl_comm.cu) carries the p-vector Sinkhorn sums, one p x p Gram and
-the k-vector V^T z.  At N>1 the line also carries "multi_gpu_parity": every rank's enhanced slab against the SAME image
+rank; the library's own communicator (csrc/nccl_comm.cu) carries the p-vector Sinkhorn sums and the k-vector V^T z
+(peer_allreduce_kernel over NVLink peer memory) and one p x p Gram (ncclAllReduce).  At N>1 the line also carries "multi_gpu_parity": every rank's enhanced slab against the SAME image
 trained unsharded on rank 0 (outside the timed region; the run fails if they differ by more than 1 LSB).
 Extra keys measured after the main timed region: "enhance_only" (train once, 50 enhance calls: the HBM-bound apply
 pass), "c5_strong" (BASELINE configs[4]: 4096x4096 BGR, p=2500, k=100, strong-scaled over the N ranks, BGR in/out) and
@@ -275,7 +275,7 @@ def run_b200(args, rank, world, local_rank):
     comm = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-        comm = LibraryComm(dev)          # ncclAllReduce enqueued by the library itself (csrc/nccl_comm.cu)
+        comm = LibraryComm(dev)          # all-reduces enqueued by the library itself (csrc/nccl_comm.cu)
     cb = comm.callback if comm else C.cast(None, _lib.ALLREDUCE_FN)
     user = comm.user if comm else None
 
@@ -523,6 +523,7 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
+    comm_info = comm.info() if comm else None
     total_mp = rows * COLS / 1e6
     ms_step = ms_dev / args.steps
     value = total_mp / (ms_step * 1e-3)
@@ -621,7 +622,11 @@ def run_b200(args, rank, world, local_rank):
         "enhance_only": enhance_only,
         "c5_strong": c5,
         "c4_strong": c4,
-        "collectives": "library-owned NCCL communicator (ncclAllReduce from csrc/nccl_comm.cu)" if world > 1 else None,
+        "collectives": ({"owner": "library-owned communicator (csrc/nccl_comm.cu)",
+                         "small_messages": ("peer_allreduce_kernel: flagged cells stored into every rank's inbox over NVLink peer memory "
+                                            "(CUDA IPC), summed in rank order, one launch per reduction") if comm_info["peer_path"]
+                         else "ncclAllReduce (peer-memory path unavailable: %s)" % comm_info["why"],
+                         "gram": "ncclAllReduce (p x p doubles)", **comm_info} if world > 1 else None),
     }
     print(json.dumps(line), flush=True)
     if comm:

@@ -67,11 +67,17 @@ typedef int (*nle_b200_allreduce_fn)(void* dev_buf, size_t count, void* cuda_str
  * library itself links no NCCL).  Rank 0 calls nle_b200_comm_unique_id and the host ferries the 128 bytes to the other
  * ranks (any transport); then EVERY rank calls nle_b200_comm_create on its own device (collective).  Pass
  * nle_b200_comm_allreduce as `allreduce` and the communicator as `user` to the sharded training entry points: the
- * p-vector / Gram / k-vector sums are then ncclAllReduce calls enqueued by the library on its own stream. */
+ * sums are then enqueued by the library on its own stream.  The p x p Gram is an ncclAllReduce; the latency-sized
+ * messages (p-vectors, k-vectors: up to 8192 doubles) are ONE launch of the library's own peer_allreduce_kernel, which
+ * stores flagged cells straight into every rank's inbox over NVLink peer memory (CUDA IPC, set up in
+ * nle_b200_comm_create) and sums them in rank order -- bit-identical on every rank; where peers cannot map each other's
+ * memory they fall back to ncclAllReduce.  nle_b200_comm_info reports which path is in use (*peer_path = 1: peer
+ * memory), the reductions issued so far on the peer / NCCL path, and returns "ok" or the reason. */
 typedef struct nle_b200_comm nle_b200_comm;
 int nle_b200_comm_unique_id(unsigned char id[128]);
 int nle_b200_comm_create(const unsigned char id[128], int rank, int nranks, nle_b200_comm** out);
 int nle_b200_comm_allreduce(void* dev_buf, size_t count, void* cuda_stream, void* user /* nle_b200_comm* */);
+const char* nle_b200_comm_info(nle_b200_comm* comm, int* peer_path, unsigned long long calls[2]);
 void nle_b200_comm_destroy(nle_b200_comm* comm);
 
 const char* nle_b200_last_error(void);

@@ -61,6 +61,7 @@ SYMBOLS = {
     "nle_b200_comm_unique_id": (C.c_int, [_P]),
     "nle_b200_comm_create": (C.c_int, [_P, C.c_int, C.c_int, C.POINTER(_P)]),
     "nle_b200_comm_allreduce": (C.c_int, [_P, C.c_size_t, _P, _P]),
+    "nle_b200_comm_info": (C.c_char_p, [_P, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)]),
     "nle_b200_comm_destroy": (None, [_P]),
     "nle_b200_measured_peaks": (C.c_int, [_P, C.c_int]),
     "nle_b200_fp64_fma_peak_tflops": (C.c_double, []),

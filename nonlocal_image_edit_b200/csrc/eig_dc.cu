@@ -11,12 +11,13 @@
 //                         grid.sync per Householder step: the rank-2 update of step j is fused with
 //                         the symmetric matrix-vector product of step j+1 (the next reflector is
 //                         derived redundantly by every CTA from the updated column j+1).
-//   tridiag_cluster_kernel   the default for 64 <= n <= 2048: same arithmetic in the same order (bit-identical d, e,
+//   tridiag_cluster_kernel   the default for n >= 64: same arithmetic in the same order (bit-identical d, e,
 //                         tau, reflectors), trailing matrix resident in shared memory, flagged-cell exchange instead
 //                         of grid.sync, thread-block clusters of 2 CTAs share the polling through distributed shared
 //                         memory (profiles/r2a_trd_sweep.md: 14-19 % faster than tridiag_kernel at n = 612...1600).
-//                         tridiag_kernel remains the general path (n > 2048: the matrix no longer fits in the
-//                         shared memory of 148 SMs) and the cross-check of tests/test_gpu_eig_variants.py.
+//                         A matrix whose columns do not fit in the shared memory of 148 SMs (n > ~1700) is reduced by
+//                         tridiag_kernel (partial mode) until the trailing block fits and then handed over; alone,
+//                         tridiag_kernel is the fallback and the cross-check of tests/test_gpu_eig_variants.py.
 //   dc_leaf_kernel        implicit-shift QL on leaves of <= 32 rows, one warp per leaf.
 //   dc_setup_kernel       per merge: z vector, rank sort, LAPACK dlaed2-style deflation.
 //   dc_rotate_kernel      applies the deflation Givens rotations to the eigenvector columns.
@@ -85,9 +86,15 @@ __device__ __forceinline__ double block_sum(double v, double* red /*>= 2*kTrdWar
 // triangles, column-major).  On exit: d (n), e (n-1), tau (n-1); reflector j (H_j = I - tau_j v v^T,
 // v[j+1] = 1) is stored in A(j+1:n, j) including the explicit 1.
 //
+// nstop < n - 2: PARTIAL reduction.  Only the reflectors 0 .. nstop-1 are produced (d, e, tau [0, nstop) written) and the
+// kernel leaves the trailing block A(nstop:n, nstop:n) fully updated in global memory, both triangles.  Householder
+// tridiagonalisation of the rest is then an independent problem on that block: a second launch (of this kernel or of
+// tridiag_cluster_kernel) on (A + nstop*lda + nstop, lda, n - nstop, d + nstop, e + nstop, tau + nstop) performs exactly the
+// operations the uninterrupted kernel would have performed, in the same order -- the result is bit-identical.  This is how
+// matrices too large for the shared memory of the SMs (n > ~1700) get the resident kernel for their last ~1700 columns.
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
-               double* __restrict__ tau, double* __restrict__ pbuf) {
+               double* __restrict__ tau, double* __restrict__ pbuf, int nstop) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];
     double* v = sm;            // current reflector, global row indexing
@@ -157,6 +164,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
     for (int j = 0; j <= n - 3; ++j) {
         const double* p = pbuf + (size_t)(j & 1) * n;
         double* pn = pbuf + (size_t)((j + 1) & 1) * n;
+        const bool last_partial = (j == nstop - 1);     // partial reduction: reflector j is the last one of this launch
         // (0) publish reflector j (column j of A is no longer read by anybody in this kernel)
         if (b == 0) {
             double* col = A + (size_t)j * lda;
@@ -188,13 +196,21 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
         }
         const double diag_next = cn[j + 1];
         double tau_next = 0.0, beta_next;
-        if (j + 1 <= n - 3) {
+        if (last_partial) {
+            // hand-over: the updated column j+1 goes back to A unscaled (the next launch builds reflector j+1 from it);
+            // its mirror image, row j+1 of the columns c >= j+2, is written by the owners of those columns below
+            beta_next = 0.0;
+            if (b == 0) {
+                double* col = A + (size_t)(j + 1) * lda;
+                for (int i = j + 1 + tid; i < n; i += kTrdThreads) col[i] = cn[i];
+            }
+        } else if (j + 1 <= n - 3) {
             beta_next = make_reflector(j + 1, tau_next);
         } else {
             beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
         }
         // (3) rank-2 update of the owned columns c >= j+2 fused with the next symv
-        const bool has_next = (j + 1 <= n - 3);
+        const bool has_next = (j + 1 <= n - 3) && !last_partial;
         for (int q = warp; ; q += kTrdWarps) {
             const int c = b + G * q;
             if (c >= n) break;
@@ -238,7 +254,9 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
                 acc = warp_sum(acc);
                 if (lane == 0) pn[c] = acc;
             }
+            if (last_partial && lane == 0) col[j + 1] = cn[c];
         }
+        if (last_partial) return;      // d, e, tau [0, nstop) and the trailing block are complete
         // rotate state
         diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
         { double* t = v; v = cn; cn = t; }
@@ -1439,29 +1457,48 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     NLE_CUDA(cudaMemsetAsync(fail, 0, sizeof(int), s));
 
     // ---- 1. tridiagonalisation
-    // Default for 64 <= n <= 2048: tridiag_cluster_kernel, clusters of 2 CTAs (falls through to tridiag_kernel when the
-    // resident columns do not fit in shared memory or the cluster launch is refused).  NLE_B200_TRD=gridsync forces
-    // tridiag_kernel (the bit-equality cross-check of tests/test_gpu_eig_variants.py); NLE_B200_TRD_PROF=1 prints the
-    // per-phase cycle counts of a step on stderr.
-    bool trd_done = false;
+    // Default for n >= 64: tridiag_cluster_kernel, clusters of 2 CTAs, on the largest trailing block whose columns fit in
+    // shared memory (the whole matrix up to n ~ 1700; before that, tridiag_kernel in partial mode); falls through to
+    // tridiag_kernel when the cluster launch is refused.  NLE_B200_TRD=gridsync forces tridiag_kernel alone (the
+    // bit-equality cross-check of tests/test_gpu_eig_variants.py), NLE_B200_TRD=nohybrid the round-2 rule (no hand-over:
+    // tridiag_kernel for every matrix that does not fit; timing comparisons); NLE_B200_TRD_PROF=1 prints the per-phase
+    // cycle counts of a step on stderr.
     static const bool force_gridsync = [] { const char* e = getenv("NLE_B200_TRD"); return e && std::string(e) == "gridsync"; }();
-    if (!force_gridsync && n >= 64 && n <= kResPer * kTrdThreads) {
+    int dev = 0, max_smem_trd = 0;
+    NLE_CUDA(cudaGetDevice(&dev));
+    NLE_CUDA(cudaDeviceGetAttribute(&max_smem_trd, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
+    constexpr int S = 2;
+    // shared memory of tridiag_cluster_kernel for an m x m problem on a grid of Gt CTAs
+    auto cluster_smem = [&](int m, int Gt) { return ((5 + (size_t)cdiv(m, Gt)) * m + 2 * kTrdWarps) * sizeof(double); };
+    // grid.sync kernel on the block (Ab, lda = n, m): reflectors [0, nstop) only when nstop < m - 2
+    auto launch_gridsync = [&](double* Ab, int m, double* db, double* eb, double* taub, int nstop) {
+        size_t smem = (3 * (size_t)m + 2 * kTrdWarps) * sizeof(double);
+        const void* kfn = (const void*)tridiag_kernel;
+        allow_max_dynamic_smem((const void*)kfn);
+        int per_sm = 0;
+        NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
+        if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(m) + ")"};
+        int grid = std::min(sm_count(), m);
+        int lda = n;
+        void* args[] = {&Ab, &lda, &m, &db, &eb, &taub, &pbuf, &nstop};
+        NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
+        ++g_launches;
+    };
+    // resident kernel on the block (Ab, lda = n, m); false if it does not fit or the cluster launch is refused
+    auto launch_cluster = [&](double* Ab, int m, double* db, double* eb, double* taub) -> bool {
+        if (m < 64 || m > kResPer * kTrdThreads) return false;
         const bool kprof = getenv("NLE_B200_TRD_PROF") != nullptr;
-        constexpr int S = 2;
-        int dev = 0, max_smem = 0;
-        NLE_CUDA(cudaGetDevice(&dev));
-        NLE_CUDA(cudaDeviceGetAttribute(&max_smem, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
         const void* kfn = kprof ? (const void*)tridiag_cluster_kernel<true> : (const void*)tridiag_cluster_kernel<false>;
         // the grid depends on how many clusters fit, which depends on the shared memory, which depends on the grid:
         // start from one CTA per SM and shrink until the launch configuration is consistent.  The occupancy query is a
-        // slow host call (the GPU idles meanwhile): its answer is cached per (device, n).
+        // slow host call (the GPU idles meanwhile): its answer is cached per (device, m).
         struct Cfg { int dev, n, G; size_t smem; };
         static thread_local Cfg cache[8] = {};
         static thread_local int cache_next = 0;
         int G = 0;
         size_t smem = 0;
         for (const Cfg& c : cache)
-            if (c.G > 0 && c.dev == dev && c.n == n) { G = c.G; smem = c.smem; }
+            if (c.G > 0 && c.dev == dev && c.n == m) { G = c.G; smem = c.smem; }
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
@@ -1472,11 +1509,10 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         cfg.stream = s;
         cfg.attrs = at;
         if (G == 0) {
-            int Gt = (std::min(sm_count(), n) / S) * S;
+            int Gt = (std::min(sm_count(), m) / S) * S;
             for (int it = 0; it < 4 && Gt >= S; ++it) {
-                const int qmax = cdiv(n, Gt);
-                const size_t sm = ((5 + (size_t)qmax) * n + 2 * kTrdWarps) * sizeof(double);
-                if (sm > (size_t)max_smem) break;
+                const size_t sm = cluster_smem(m, Gt);
+                if (sm > (size_t)max_smem_trd) break;
                 allow_max_dynamic_smem((const void*)kfn);
                 cfg.gridDim = dim3(Gt);
                 cfg.dynamicSmemBytes = sm;
@@ -1486,56 +1522,61 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
                 if (ncl * S < Gt) { Gt = ncl * S; continue; }      // fewer clusters fit: retry with the smaller grid
                 G = Gt;
                 smem = sm;
-                cache[cache_next] = Cfg{dev, n, G, smem};
+                cache[cache_next] = Cfg{dev, m, G, smem};
                 cache_next = (cache_next + 1) % 8;
                 break;
             }
         }
-        while (G >= S) {
-            allow_max_dynamic_smem((const void*)kfn);
-            cfg.gridDim = dim3(G);
-            cfg.dynamicSmemBytes = smem;
-            cfg.numAttrs = 2;
-            const size_t ne = ((size_t)n + 1) & ~(size_t)1;  // even stride per vector of cells (32-byte sector polls)
-            const size_t cells = 4 * ne + 8;                 // + 8 cells = 16 profile counters
-            if (ws.trdll.n < cells) ws.trdll.alloc(cells);
-            NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));   // tag 0 = never written
-            int lda = n;
-            uint4* ll = ws.trdll.p;
-            long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * ne);
-            void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &ll, &kp};
-            // Without the co-residency guarantee of a cooperative launch the polling CTAs could wait for CTAs that are
-            // not running: if the launch is refused, fall through to the grid.sync kernel instead of launching anyway.
-            if (cudaLaunchKernelExC(&cfg, kfn, args) != cudaSuccess) { cudaGetLastError(); break; }
-            ++g_launches;
-            trd_done = true;
-            if (kprof) {
-                long long h[16];
-                NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
-                NLE_CUDA(cudaStreamSynchronize(s));
-                const double st = (double)std::max(1LL, h[11]);
-                double tot = 0;
-                for (int k = 0; k < 10; ++k) tot += (double)h[k];
-                fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: poll %.0f | forward+cluster.sync %.0f | dot-reduce %.0f | w %.0f | "
-                        "col %.0f | norm-reduce %.0f | sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; "
-                        "poll rounds/step %.2f\n", S, G, n, h[0] / st, h[9] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st,
-                        h[5] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
-            }
-            break;
-        }
-    }
-    if (!trd_done) {
-        size_t smem = (3 * (size_t)n + 2 * kTrdWarps) * sizeof(double);
-        const void* kfn = (const void*)tridiag_kernel;
+        if (G < S) return false;
         allow_max_dynamic_smem((const void*)kfn);
-        int per_sm = 0;
-        NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
-        if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(n) + ")"};
-        int grid = std::min(sm_count(), n);
+        cfg.gridDim = dim3(G);
+        cfg.dynamicSmemBytes = smem;
+        cfg.numAttrs = 2;
+        const size_t ne = ((size_t)m + 1) & ~(size_t)1;  // even stride per vector of cells (32-byte sector polls)
+        const size_t cells = 4 * ne + 8;                 // + 8 cells = 16 profile counters
+        if (ws.trdll.n < cells) ws.trdll.alloc(cells);
+        NLE_CUDA(cudaMemsetAsync(ws.trdll.p, 0, cells * sizeof(uint4), s));   // tag 0 = never written
         int lda = n;
-        void* args[] = {&As, &lda, &n, &d0, &e0, &tau, &pbuf};
-        NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
+        uint4* ll = ws.trdll.p;
+        long long* kp = reinterpret_cast<long long*>(ws.trdll.p + 4 * ne);
+        void* args[] = {&Ab, &lda, &m, &db, &eb, &taub, &ll, &kp};
+        // Without the co-residency guarantee of a cooperative launch the polling CTAs could wait for CTAs that are
+        // not running: if the launch is refused, the caller falls through to the grid.sync kernel instead of launching anyway.
+        if (cudaLaunchKernelExC(&cfg, kfn, args) != cudaSuccess) { cudaGetLastError(); return false; }
         ++g_launches;
+        if (kprof) {
+            long long h[16];
+            NLE_CUDA(cudaMemcpyAsync(h, kp, sizeof(h), cudaMemcpyDeviceToHost, s));
+            NLE_CUDA(cudaStreamSynchronize(s));
+            const double st = (double)std::max(1LL, h[11]);
+            double tot = 0;
+            for (int k = 0; k < 10; ++k) tot += (double)h[k];
+            fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: poll %.0f | forward+cluster.sync %.0f | dot-reduce %.0f | w %.0f | "
+                    "col %.0f | norm-reduce %.0f | sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; "
+                    "poll rounds/step %.2f\n", S, G, m, h[0] / st, h[9] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st,
+                    h[5] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
+        }
+        return true;
+    };
+    if (force_gridsync || n < 64) {
+        launch_gridsync(As, n, d0, e0, tau, n);
+    } else {
+        // the largest trailing block whose columns fit in the shared memory of one CTA per SM
+        const int Gfull = (sm_count() / S) * S;
+        int m = std::min(n, kResPer * kTrdThreads);
+        while (m >= 64 && cluster_smem(m, std::min(Gfull, (m / S) * S)) > (size_t)max_smem_trd) --m;
+        static const bool no_hybrid = [] { const char* e = getenv("NLE_B200_TRD"); return e && std::string(e) == "nohybrid"; }();
+        if (m == n) {
+            if (!launch_cluster(As, n, d0, e0, tau)) launch_gridsync(As, n, d0, e0, tau, n);
+        } else if (m < 64 || n - m > n - 3 || no_hybrid) {
+            launch_gridsync(As, n, d0, e0, tau, n);
+        } else {
+            // n too large: the first n - m reflectors on the L2-resident matrix, the last m columns in shared memory
+            const int s0 = n - m;
+            launch_gridsync(As, n, d0, e0, tau, s0);
+            double* Ab = As + (size_t)s0 * n + s0;
+            if (!launch_cluster(Ab, m, d0 + s0, e0 + s0, tau + s0)) launch_gridsync(Ab, m, d0 + s0, e0 + s0, tau + s0, m);
+        }
     }
     auto t_trd = tnow();
     ws.phase_mark(s);

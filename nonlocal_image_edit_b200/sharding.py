@@ -48,8 +48,10 @@ def torch_allreduce(device=None, group=None):
 
 
 class LibraryComm:
-    """The library's own NCCL communicator (csrc/nccl_comm.cu): the all-reduces of a sharded training call become
-    ncclAllReduce calls enqueued by libnle_b200.so itself -- no Python between a kernel and its collective.
+    """The library's own communicator (csrc/nccl_comm.cu): the all-reduces of a sharded training call are enqueued by
+    libnle_b200.so itself -- no Python between a kernel and its collective.  The p x p Gram is an ncclAllReduce; the
+    latency-sized p- and k-vectors are single launches of the library's peer_allreduce_kernel over NVLink peer memory
+    (CUDA IPC inboxes), with ncclAllReduce as the fallback where peers cannot map each other's memory (`info()`).
 
     torch.distributed is only the bootstrap: rank 0 draws the 128-byte NCCL unique id and it is broadcast once over the
     already initialised process group.  `callback` / `user` are what the sharded entry points of the C ABI take
@@ -72,6 +74,14 @@ class LibraryComm:
         self.handle = h
         self.callback = C.cast(self._lib.nle_b200_comm_allreduce, _lib.ALLREDUCE_FN)
         self.user = h
+
+    def info(self):
+        """Which path the latency-sized all-reduces take: {'peer_path': bool, 'why': str, 'peer_calls': n, 'nccl_calls': n}."""
+        peer = C.c_int(0)
+        calls = (C.c_ulonglong * 2)()
+        why = self._lib.nle_b200_comm_info(self.handle, C.byref(peer), calls)
+        return {"peer_path": bool(peer.value), "why": why.decode() if why else "", "peer_calls": int(calls[0]),
+                "nccl_calls": int(calls[1])}
 
     def close(self):
         if self.handle:

@@ -1,10 +1,11 @@
 """GPU: the kernel choices that are made automatically must not change results.
 
-* Tridiagonalisation: tridiag_cluster_kernel (default for 64 <= n <= 2048: trailing matrix resident in shared memory,
+* Tridiagonalisation: tridiag_cluster_kernel (default for n >= 64: trailing matrix resident in shared memory,
   flagged-cell exchange, clusters of 2 CTAs) performs the same FP64 operations in the same order as tridiag_kernel
-  (one grid.sync per Householder step; the path for n > 2048): d, e, tau and the reflectors -- hence the whole
-  eigen-decomposition and the enhanced image -- must be BIT-identical.  NLE_B200_TRD=gridsync (read once per process)
-  forces the latter, so each side runs in its own process.
+  (one grid.sync per Householder step): d, e, tau and the reflectors -- hence the whole eigen-decomposition and the
+  enhanced image -- must be BIT-identical.  Matrices whose columns do not fit in shared memory (n > ~1700) are reduced
+  by tridiag_kernel until the trailing block fits and handed over to the resident kernel (sizes 1709 ... 2300 below).
+  NLE_B200_TRD=gridsync (read once per process) forces tridiag_kernel alone, so each side runs in its own process.
 * Eigensolver family: the direct solver (tridiagonalisation + divide & conquer) against the block-Jacobi fallback
   (NLE_B200_EIG=jacobi) to rounding.
 * Third eigensolve: when the block of Q is at least 10 x the block width, eig(Q) runs the top-k block solver
@@ -23,7 +24,7 @@ from oracle import nle_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-SIZES = [3, 5, 63, 64, 65, 149, 300, 612, 1041, 1600, 2048, 2049]
+SIZES = [3, 5, 63, 64, 65, 149, 300, 612, 1041, 1600, 1709, 1800, 2048, 2049, 2300]
 
 CHILD = r"""
 import sys, numpy as np
