@@ -81,6 +81,63 @@ __device__ __forceinline__ double block_sum(double v, double* red /*>= 2*kTrdWar
     return s;
 }
 
+constexpr int kTrdRed = 2 * kTrdWarps + 4;     // block_sum slots + 4 scalars handed from their owner thread to the CTA
+
+// w_i = tau p_i - kappa v_i and the updated entry of column j+1, in ONE fixed form (explicit roundings) so that both
+// tridiagonalisation kernels -- and the shortcut w_{j+1} = tau p_{j+1} - kappa every thread computes for itself -- agree
+// bit for bit.
+__device__ __forceinline__ double trd_w(double tau, double p, double kappa, double v) { return fma(tau, p, -__dmul_rn(kappa, v)); }
+__device__ __forceinline__ double trd_cn(double c, double v, double wj1, double w) { return __dsub_rn(fma(-v, wj1, c), w); }
+
+// Steps (1b)-(2) of Householder step j, shared by tridiag_kernel and tridiag_cluster_kernel.
+// On entry thread tid has written w[i] = p_i and cn[i] = A(i, j+1) for its rows i = j+1+tid, j+1+tid+kTrdThreads, ...,
+// `part` = its share of p.v over the same rows, and the owner of row j+1 has stored p_{j+1} in sc[2]; NO barrier yet.
+// Every loop below runs over the thread's own rows again, so the only barriers are the two inside the block sums and the
+// final one: w = tau p - kappa v, cn = updated column j+1, its diagonal and sub-diagonal entries travel through sc[0..1];
+// if `make`, cn(j+3:) is scaled into reflector j+1 (cn[j+2] = 1).  All threads return the same scalars.
+__device__ __forceinline__ void trd_step_vectors(int j, int n, double tau_j, double part, double* __restrict__ w,
+                                                 const double* __restrict__ v, double* __restrict__ cn, double* red, int& phase,
+                                                 bool make, double& diag_next, double& beta_next, double& tau_next) {
+    const int tid = threadIdx.x;
+    double* sc = red + 2 * kTrdWarps;
+    const double dot = block_sum(part, red, phase);
+    const double kappa = 0.5 * tau_j * tau_j * dot;
+    const double wj1 = trd_w(tau_j, sc[2], kappa, 1.0);      // = w[j+1]  (v[j+1] == 1)
+    double part2 = 0.0;
+    for (int i = j + 1 + tid; i < n; i += kTrdThreads) {
+        const double vi = v[i];
+        const double wi = trd_w(tau_j, w[i], kappa, vi);
+        const double ci = trd_cn(cn[i], vi, wj1, wi);
+        w[i] = wi;
+        cn[i] = ci;
+        if (i >= j + 3) part2 = fma(ci, ci, part2);
+        else sc[i - (j + 1)] = ci;                           // rows j+1 (next diagonal) and j+2 (alpha)
+    }
+    tau_next = 0.0;
+    if (!make) {
+        __syncthreads();
+        diag_next = sc[0];
+        beta_next = (j + 2 < n) ? sc[1] : 0.0;               // j+1 == n-2: the last off-diagonal
+        return;
+    }
+    const double xn2 = block_sum(part2, red, phase);         // its barrier also publishes w, cn and sc
+    diag_next = sc[0];
+    const double alpha = sc[1];
+    if (xn2 == 0.0) {
+        beta_next = alpha;
+        if (tid == 1) cn[j + 2] = 1.0;                       // thread 1 owns row j+2
+    } else {
+        beta_next = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
+        tau_next = (beta_next - alpha) / beta_next;
+        const double scal = 1.0 / (alpha - beta_next);
+        for (int i = j + 1 + tid; i < n; i += kTrdThreads) {
+            if (i >= j + 3) cn[i] *= scal;
+            else if (i == j + 2) cn[i] = 1.0;
+        }
+    }
+    __syncthreads();
+}
+
 // ---------------------------------------------------------------------------------------------
 // Householder tridiagonalisation A = Q T Q^T of a symmetric matrix held in FULL storage (both
 // triangles, column-major).  On exit: d (n), e (n-1), tau (n-1); reflector j (H_j = I - tau_j v v^T,
@@ -100,7 +157,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
     double* v = sm;            // current reflector, global row indexing
     double* w = sm + n;
     double* cn = sm + 2 * (size_t)n;   // updated next column -> next reflector
-    double* red = sm + 3 * (size_t)n;  // 2*kTrdWarps
+    double* red = sm + 3 * (size_t)n;  // kTrdRed
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, b = blockIdx.x;
     int phase = 0;
@@ -118,7 +175,10 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
     auto make_reflector = [&](int j0, double& tau_out) -> double {
         const double alpha = cn[j0 + 1];
         double part = 0.0;
-        for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
+        // thread tid sums the rows j0 + tid, j0 + tid + kTrdThreads, ... (from j0 + 2 on): the row-to-thread map of
+        // trd_step_vectors, so that a reduction that starts on a trailing block reproduces the uninterrupted one bit for bit
+        for (int i = j0 + tid; i < n; i += kTrdThreads)
+            if (i >= j0 + 2) part = fma(cn[i], cn[i], part);
         const double xn2 = block_sum(part, red, phase);
         double beta;
         if (xn2 == 0.0) {
@@ -182,35 +242,22 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
                 w[i] = pi;
                 cn[i] = ci;
                 part = fma(pi, v[i], part);
+                if (i == j + 1) red[2 * kTrdWarps + 2] = pi;
             }
         }
-        const double dot = block_sum(part, red, phase);
-        const double kappa = 0.5 * tau_j * tau_j * dot;
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
-        __syncthreads();
-        // (2) updated column j+1 (rows j+1..n-1) -> next diagonal and next reflector
-        {
-            const double wj1 = w[j + 1];   // v[j+1] == 1
-            for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
-            __syncthreads();
-        }
-        const double diag_next = cn[j + 1];
-        double tau_next = 0.0, beta_next;
+        // (1b)-(2) w, the updated column j+1 (rows j+1..n-1), the next diagonal and the next reflector
+        const bool has_next = (j + 1 <= n - 3) && !last_partial;
+        double diag_next, tau_next, beta_next;
+        trd_step_vectors(j, n, tau_j, part, w, v, cn, red, phase, has_next, diag_next, beta_next, tau_next);
         if (last_partial) {
             // hand-over: the updated column j+1 goes back to A unscaled (the next launch builds reflector j+1 from it);
             // its mirror image, row j+1 of the columns c >= j+2, is written by the owners of those columns below
-            beta_next = 0.0;
             if (b == 0) {
                 double* col = A + (size_t)(j + 1) * lda;
                 for (int i = j + 1 + tid; i < n; i += kTrdThreads) col[i] = cn[i];
             }
-        } else if (j + 1 <= n - 3) {
-            beta_next = make_reflector(j + 1, tau_next);
-        } else {
-            beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
         }
         // (3) rank-2 update of the owned columns c >= j+2 fused with the next symv
-        const bool has_next = (j + 1 <= n - 3) && !last_partial;
         for (int q = warp; ; q += kTrdWarps) {
             const int c = b + G * q;
             if (c >= n) break;
@@ -334,11 +381,48 @@ __device__ __forceinline__ long long clock_after(double dep) {
         }                                                              \
     } while (0)
 
-// The step is bound by every CTA reading every cell (profiles/r1l_trd_phases.md), so the CTAs of a thread-block cluster
-// share the polling: CTA `rank` polls every S-th cell and forwards what it receives to its peers through distributed
-// shared memory, one cluster barrier per step makes the vectors complete everywhere.  Readers per cell: G/S.  Measured
-// (profiles/r2a_trd_sweep.md): S = 2 is the optimum (n = 1600: 8.7 ms against 10.2 ms for tridiag_kernel, 10.1 ms for
-// S = 4, where the forwarding and the cluster barrier cost more than the polling saves).
+// ---- TMA multicast landing of the exchange cells (MC = true) ----------------------------------------------------
+// One elected thread of cluster rank 0 issues, per Householder step, two 1-D bulk copies (the p cells and the next-column
+// cells of the rows still alive) with .multicast::cluster: the TMA engine reads the cells from L2 ONCE per cluster and
+// writes them into the landing buffers of every CTA of the cluster, completing a transaction count on each CTA's own
+// mbarrier -- no thread issues a load for the bulk of the exchange and nothing is forwarded through distributed shared
+// memory by threads.  What lands is validated cell by cell (tags); a cell that was not yet written when the copy passed
+// is re-polled by its thread with the strong 16-byte load, so the copy never has to be repeated as a whole.
+__device__ __forceinline__ uint32_t trd_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void trd_mbar_init(uint64_t* bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(trd_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void trd_mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(trd_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void trd_mbar_wait(uint64_t* bar, unsigned parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(trd_smem_u32(bar)), "r"(parity)
+        : "memory");
+}
+__device__ __forceinline__ void trd_tma_multicast(void* dst_smem, const void* src_gmem, unsigned bytes, uint64_t* bar, unsigned short mask) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;" ::"r"(
+                     trd_smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(trd_smem_u32(bar)), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void trd_cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+__device__ __forceinline__ void trd_cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
+
+// Clusters: the CTAs of a thread-block cluster receive the cells of a step with ONE L2 read (TMA multicast).  Round 2
+// history (profiles/r2a_trd_sweep.md, r2zb_trd_multicast.md): per-thread polling of all cells by every CTA (n = 1600:
+// 9.5 ms); clusters of 2 whose CTAs poll every second cell with strong 256-bit loads and forward them through distributed
+// shared memory, one cluster.sync per step (8.7 - 9.0 ms); the multicast landing below (7.9 ms): the poll + forward phase
+// of 6.6k cycles per step became 3.7k (copy in flight) + 1.5k (validation); the copy is issued column first because the p
+// cells are the last thing a producer writes.  Unicast copies per CTA measure the same as the multicast (the L2 merges the
+// concurrent reads of a cluster), larger clusters gain < 2 % at n <= 1041 and do not fit at n = 1600.
 template <bool PROF>
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
@@ -346,14 +430,17 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
                         long long* __restrict__ prof /* 16 counters when PROF */) {
     cg::cluster_group cluster = cg::this_cluster();
     const int S = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
-    extern __shared__ double sm[];
-    // Peers write p and the next column straight into this CTA's vectors, possibly one step ahead of it: w has two
-    // buffers (step parity) and the reflector / next-column vectors rotate through three, so a buffer is written
-    // again only behind the cluster barrier of the step after its last reader.
-    double* Wb = sm;                       // 2 n
-    double* Vb = sm + 2 * (size_t)n;       // 3 n
-    double* red = sm + 5 * (size_t)n;      // 2*kTrdWarps
-    double* cols = red + 2 * kTrdWarps;    // owned columns, slot q holds column b + G*q (all n rows)
+    extern __shared__ __align__(16) double sm[];
+    // Nobody but the TMA engine writes into this CTA's shared memory: the cells land in LP / LC (16 bytes per row and
+    // vector), w is one vector, v / cn ping-pong between two.
+    const int ne = (n + 1) & ~1;                 // even stride: every vector of cells starts on a 32-byte sector
+    uint4* LP = reinterpret_cast<uint4*>(sm);                    // ne cells (p)
+    uint4* LC = LP + ne;                                         // ne cells (next column)
+    double* Wb = sm + 4 * (size_t)ne;                            // n
+    double* Vb = Wb + (size_t)n;                                 // 2 n
+    double* red = Vb + 2 * (size_t)n;                            // kTrdRed
+    uint64_t* mbar = reinterpret_cast<uint64_t*>(red + kTrdRed); // one mbarrier (+ 8 bytes of padding)
+    double* cols = red + kTrdRed + 2;                            // owned columns, slot q holds column b + G*q (all n rows)
     double* v = Vb;            // current reflector, global row indexing
     double* w = Wb;
     double* cn = Vb;           // updated next column -> next reflector (first reflector is built here, then becomes v)
@@ -369,21 +456,27 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
         const int br = b - rank + r;
         cl_last = max(cl_last, br + G * ((n - 1 - br) / G));
     }
-    cluster.sync();            // no CTA touches a peer's shared memory before that peer is running
+    if (tid == 0) {
+        trd_mbar_init(mbar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    cluster.sync();            // no multicast reaches a CTA before its mbarrier exists
+    trd_cluster_arrive();      // matches the wait in front of the first multicast
     int phase = 0;
     long long pacc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tprev = 0, rounds = 0;
     // cells of tag t: p at ll + (t&1)*2n, next column at ll + (t&1)*2n + n
-    const int ne = (n + 1) & ~1;                 // even stride: every vector of cells starts on a 32-byte sector
     auto pcell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * ne; };
     auto ccell = [&](unsigned t) { return ll + (size_t)(t & 1u) * 2 * ne + ne; };
 
     auto make_reflector = [&](int j0, double& tau_out) -> double {     // identical to tridiag_kernel's
         const double alpha = cn[j0 + 1];
         double part = 0.0;
-        for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) part = fma(cn[i], cn[i], part);
+        // thread tid sums the rows j0 + tid, j0 + tid + kTrdThreads, ... (from j0 + 2 on): the row-to-thread map of
+        // trd_step_vectors, so that a reduction that starts on a trailing block reproduces the uninterrupted one bit for bit
+        for (int i = j0 + tid; i < n; i += kTrdThreads)
+            if (i >= j0 + 2) part = fma(cn[i], cn[i], part);
         const double xn2 = block_sum(part, red, phase);
-        TRD_STAMP(4, xn2);
         double beta;
         if (xn2 == 0.0) {
             tau_out = 0.0;
@@ -394,7 +487,6 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
             beta = -copysign(sqrt(fma(alpha, alpha, xn2)), alpha);
             tau_out = (beta - alpha) / beta;
             const double scal = 1.0 / (alpha - beta);
-            TRD_STAMP(5, scal + tau_out);
             __syncthreads();
             for (int i = j0 + 2 + tid; i < n; i += kTrdThreads) cn[i] *= scal;
             if (tid == 0) cn[j0 + 1] = 1.0;
@@ -414,7 +506,7 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
     double tau_j, beta_j, diag_j;
     diag_j = cn[0];
     beta_j = make_reflector(0, tau_j);
-    v = Vb;                    // step j: v = Vb[j % 3], cn = Vb[(j + 1) % 3], w = Wb[j & 1]
+    v = Vb;                    // step j: v = Vb[j & 1], cn = Vb[(j + 1) & 1]
     // p = A v over the owned columns c >= 1 (tag 1); the owner of column 1 also publishes that column
     for (int q = warp; q <= q_last; q += kTrdWarps) {
         const int c = b + G * q;
@@ -434,83 +526,61 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
     }
 
     for (int j = 0; j <= n - 3; ++j) {
-        if (cl_last < j + 2) return;      // cluster-uniform: the whole cluster leaves together, after its last barrier
-        v = Vb + (size_t)(j % 3) * n;
-        cn = Vb + (size_t)((j + 1) % 3) * n;
-        w = Wb + (size_t)(j & 1) * n;
+        if (cl_last < j + 2) {            // cluster-uniform: the whole cluster leaves together, after its last barrier
+            trd_cluster_wait();
+            return;
+        }
+        v = Vb + (size_t)(j & 1) * n;
+        cn = Vb + (size_t)((j + 1) & 1) * n;
         const unsigned T = (unsigned)(j + 1);
         const bool has_next = (j + 1 <= n - 3);
-        double diag_next, tau_next = 0.0, beta_next;
-        // (1) this CTA polls the cells of rows j+1+rank, j+1+rank+S, ... only (1/S of the readers per cell) and
-        //     writes what it received into the w / cn vectors of every CTA of the cluster (distributed shared memory)
-        {
-            // sector s holds the cells of rows 2s and 2s+1; this CTA polls the sectors s0 + rank, s0 + rank + S, ...
-            const uint4* pc = pcell(T);
-            const uint4* cc = ccell(T);
-            constexpr int SP = kResPer / 2;                 // sectors per thread and vector
-            uint4 P[SP][2], C[SP][2];
-            unsigned pend = 0, valid = 0, spins = 0;
-            const int s0 = (j + 1) >> 1;
-#pragma unroll
-            for (int u = 0; u < SP; ++u) {
-                const int r0 = 2 * (s0 + rank + S * (tid + u * kTrdThreads));
-                const unsigned v0 = (r0 >= j + 1 && r0 < n), v1 = (r0 + 1 < n);      // r0 + 1 >= j + 1 always
-                valid |= (v0 | (v1 << 1)) << (2 * u);
-                if (v0 | v1) pend |= (1u | (1u << SP)) << u;
-            }
-            while (pend) {
-#pragma unroll
-                for (int u = 0; u < SP; ++u) {
-                    const int r0 = 2 * (s0 + rank + S * (tid + u * kTrdThreads));
-                    if (pend & (1u << u)) ll_load2(pc + r0, P[u][0], P[u][1]);
-                    if (pend & (1u << (SP + u))) ll_load2(cc + r0, C[u][0], C[u][1]);
-                }
-#pragma unroll
-                for (int u = 0; u < SP; ++u) {
-                    const bool v0 = (valid >> (2 * u)) & 1u, v1 = (valid >> (2 * u + 1)) & 1u;
-                    if ((pend & (1u << u)) && (!v0 || (P[u][0].y == T && P[u][0].w == T)) && (!v1 || (P[u][1].y == T && P[u][1].w == T)))
-                        pend &= ~(1u << u);
-                    if ((pend & (1u << (SP + u))) && (!v0 || (C[u][0].y == T && C[u][0].w == T)) &&
-                        (!v1 || (C[u][1].y == T && C[u][1].w == T)))
-                        pend &= ~(1u << (SP + u));
-                }
-                if (PROF) ++rounds;
-                if (++spins > kTrdSpinLimit) __trap();   // a lost peer must not hang the device: abort the launch loudly
-            }
-            TRD_STAMP(0, ll_value(P[0][0]));
-            for (int r = 0; r < S; ++r) {
-                double* wr = cluster.map_shared_rank(w, r);
-                double* cr = cluster.map_shared_rank(cn, r);
-#pragma unroll
-                for (int u = 0; u < SP; ++u) {
-                    const int r0 = 2 * (s0 + rank + S * (tid + u * kTrdThreads));
-                    if ((valid >> (2 * u)) & 1u) { wr[r0] = ll_value(P[u][0]); cr[r0] = ll_value(C[u][0]); }
-                    if ((valid >> (2 * u + 1)) & 1u) { wr[r0 + 1] = ll_value(P[u][1]); cr[r0 + 1] = ll_value(C[u][1]); }
-                }
+        double diag_next, tau_next, beta_next;
+        // (1) the cells of rows j+1 .. n-1 land in every CTA of the cluster with one L2 read per cluster
+        trd_cluster_wait();            // every CTA of the cluster has finished reading the landing buffers of step j-1
+        if (tid == 0) {
+            const unsigned bytes = (unsigned)(n - (j + 1)) * (unsigned)sizeof(uint4);
+            trd_mbar_expect_tx(mbar, 2 * bytes);
+            if (rank == 0) {
+                const unsigned short mask = (unsigned short)((1u << S) - 1u);
+                // column first: its cells were published while the producers were still updating; the p cells are the last
+                // thing a producer writes in a step, so they are read last
+                trd_tma_multicast(LC + (j + 1), ccell(T) + (j + 1), bytes, mbar, mask);
+                trd_tma_multicast(LP + (j + 1), pcell(T) + (j + 1), bytes, mbar, mask);
             }
         }
-        cluster.sync();       // every CTA of the cluster now holds all of p (in w) and of column j+1 (in cn)
-        TRD_STAMP(9, w[j + 1]);
+        trd_mbar_wait(mbar, (unsigned)(j & 1));
+        TRD_STAMP(0, __longlong_as_double((long long)LP[j + 1].x));      // slot 0 = barrier + copy in flight
         double part = 0.0;
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) part = fma(w[i], v[i], part);
-        // w = tau*p - (tau^2/2)(p.v) v
-        const double dot = block_sum(part, red, phase);
-        TRD_STAMP(1, dot);
-        const double kappa = 0.5 * tau_j * tau_j * dot;
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) w[i] = tau_j * w[i] - kappa * v[i];
-        __syncthreads();
-        // (2) updated column j+1 -> next diagonal and next reflector
-        const double wj1 = w[j + 1];   // v[j+1] == 1
-        TRD_STAMP(2, wj1);
-        for (int i = j + 1 + tid; i < n; i += kTrdThreads) cn[i] = cn[i] - v[i] * wj1 - w[i];
-        __syncthreads();
-        diag_next = cn[j + 1];
-        TRD_STAMP(3, diag_next);
-        if (has_next) {
-            beta_next = make_reflector(j + 1, tau_next);     // stamps 4, 5
-        } else {
-            beta_next = cn[j + 2];     // j+1 == n-2: last off-diagonal, no reflector
+        {
+            unsigned spins = 0;
+#pragma unroll
+            for (int u = 0; u < kResPer; ++u) {
+                const int i = j + 1 + tid + u * kTrdThreads;
+                if (i < n) {
+                    uint4 P = LP[i], C = LC[i];
+                    while (P.y != T || P.w != T) {                 // not yet written when the copy passed: poll the cell itself
+                        P = ll_load(pcell(T) + i);
+                        if (PROF) ++rounds;
+                        if (++spins > kTrdSpinLimit) __trap();     // a lost peer must not hang the device: abort the launch loudly
+                    }
+                    while (C.y != T || C.w != T) {
+                        C = ll_load(ccell(T) + i);
+                        if (PROF) ++rounds;
+                        if (++spins > kTrdSpinLimit) __trap();
+                    }
+                    const double pi = ll_value(P);
+                    w[i] = pi;
+                    cn[i] = ll_value(C);
+                    part = fma(pi, v[i], part);
+                    if (i == j + 1) red[2 * kTrdWarps + 2] = pi;
+                }
+            }
         }
+        __syncwarp();
+        trd_cluster_arrive();          // this thread is done with the landing buffers
+        TRD_STAMP(9, part);            // slot 9 = validation + re-polls
+        // (1b)-(2) w = tau*p - (tau^2/2)(p.v) v, updated column j+1 -> next diagonal and next reflector
+        trd_step_vectors(j, n, tau_j, part, w, v, cn, red, phase, has_next, diag_next, beta_next, tau_next);
         TRD_STAMP(6, beta_next);
         // (3) rank-2 update of the owned columns c >= j+2 (in shared memory) fused with the next symv;
         //     the owner of column j+2 publishes the updated column as it goes
@@ -579,9 +649,10 @@ tridiag_cluster_kernel(double* __restrict__ A, int lda, int n, double* __restric
             if (tid == 0) { d[j] = diag_j; e[j] = beta_j; tau[j] = tau_j; }
         }
         diag_j = diag_next; beta_j = beta_next; tau_j = tau_next;
-        __syncthreads();   // keeps the warps of a CTA together so that the poll starts once per CTA, not once per warp
+        __syncthreads();   // the vectors of this step are dead: the next landing may overwrite w / cn's partner
         TRD_STAMP(8, cn[j + 2]);
     }
+    trd_cluster_wait();
     if (writer && tid == 0) {
         d[n - 2] = diag_j;
         e[n - 2] = beta_j;
@@ -1468,11 +1539,14 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     NLE_CUDA(cudaGetDevice(&dev));
     NLE_CUDA(cudaDeviceGetAttribute(&max_smem_trd, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
     constexpr int S = 2;
-    // shared memory of tridiag_cluster_kernel for an m x m problem on a grid of Gt CTAs
-    auto cluster_smem = [&](int m, int Gt) { return ((5 + (size_t)cdiv(m, Gt)) * m + 2 * kTrdWarps) * sizeof(double); };
+    // shared memory of tridiag_cluster_kernel for an m x m problem on a grid of Gt CTAs: landing cells (4 m), w, v, cn,
+    // reduction slots + mbarrier, the resident columns
+    auto cluster_smem = [&](int m, int Gt) {
+        return (7 * (size_t)m + 8 + kTrdRed + 2 + (size_t)cdiv(m, Gt) * m) * sizeof(double);
+    };
     // grid.sync kernel on the block (Ab, lda = n, m): reflectors [0, nstop) only when nstop < m - 2
     auto launch_gridsync = [&](double* Ab, int m, double* db, double* eb, double* taub, int nstop) {
-        size_t smem = (3 * (size_t)m + 2 * kTrdWarps) * sizeof(double);
+        size_t smem = (3 * (size_t)m + kTrdRed) * sizeof(double);
         const void* kfn = (const void*)tridiag_kernel;
         allow_max_dynamic_smem((const void*)kfn);
         int per_sm = 0;
@@ -1551,10 +1625,9 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
             const double st = (double)std::max(1LL, h[11]);
             double tot = 0;
             for (int k = 0; k < 10; ++k) tot += (double)h[k];
-            fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: poll %.0f | forward+cluster.sync %.0f | dot-reduce %.0f | w %.0f | "
-                    "col %.0f | norm-reduce %.0f | sqrt,div %.0f | scale %.0f | update+symv %.0f | tail %.0f | total %.0f ; "
-                    "poll rounds/step %.2f\n", S, G, m, h[0] / st, h[9] / st, h[1] / st, h[2] / st, h[3] / st, h[4] / st,
-                    h[5] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
+            fprintf(stderr, "[trd cluster S=%d G=%d n=%d] cycles/step: barrier + multicast in flight %.0f | validation + re-polls %.0f | "
+                    "w, column, two reductions, reflector %.0f | update+symv %.0f | tail %.0f | total %.0f ; re-polls of thread 0 per step %.2f\n",
+                    S, G, m, h[0] / st, h[9] / st, h[6] / st, h[7] / st, h[8] / st, tot / st, h[10] / st);
         }
         return true;
     };
