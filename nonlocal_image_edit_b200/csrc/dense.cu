@@ -325,29 +325,31 @@ __global__ void dgemv_t_kernel(int m, int n, const double* __restrict__ A, int l
 // Sinkhorn half-step, sample side, one pass over U instead of two dgemv_n + two vector kernels:
 //   w[i]  = sum_j U[i,j] t[j]                               (rest pixels use k_j^T w)
 //   xs[i] = recip( sum_j U[i,j] (lam[j] t[j]) )             (samples: U[s,:] Lam t, inplaceReciprocal filter.cpp:42-54)
-// Same column phases and summation order as dgemv_n_kernel.
-__global__ void __launch_bounds__(GV_WARPS * 32)
+// U (13 MB at the bench config) does not survive in L2 between two half-iterations (each streams > 150 MB of level tables), so
+// both kernels below are bound by the latency of a few dependent batches of loads, not by bandwidth: they are shaped for many
+// CTAs and many loads in flight.  CTA = 8 rows x 16 warps; a quarter-warp covers the 8 rows (64-byte row segments), the 64 column
+// phases (16 warps x 4 quarters) stride over the columns, partial sums are combined in shared memory in a fixed order.
+constexpr int SS_ROWS = 8, SS_WARPS = 16, SS_PH = SS_WARPS * (32 / SS_ROWS);
+__global__ void __launch_bounds__(SS_WARPS * 32)
 sk_sample_step_kernel(int m, int n, const double* __restrict__ A, int lda, const double* __restrict__ t,
                       const double* __restrict__ lam, double eps, double* __restrict__ w, double* __restrict__ xs) {
-    __shared__ double part[2][GV_WARPS * 2][GV_ROWS + 1];
+    __shared__ double part[2][SS_PH][SS_ROWS + 1];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int r = lane & 15, half = lane >> 4;
-    const int i = blockIdx.x * GV_ROWS + r;
-    const int slot = warp * 2 + half;
+    const int r = lane & (SS_ROWS - 1), sub = lane / SS_ROWS;
+    const int i = blockIdx.x * SS_ROWS + r;
+    const int slot = warp * (32 / SS_ROWS) + sub;
     double acc0 = 0.0, acc1 = 0.0;
     if (i < m) {
         const double* a = A + i;
         int j = slot;
-        // 8 column phases in flight per thread (the matrix is L2 resident: the pass is latency bound); summation order
-        // is the plain ascending one
-        for (; j + 7 * 32 < n; j += 8 * 32) {
+        for (; j + 7 * SS_PH < n; j += 8 * SS_PH) {          // 8 column phases in flight per thread, ascending summation order
             double av[8], tv[8], lv[8];
 #pragma unroll
-            for (int u = 0; u < 8; ++u) { av[u] = a[(size_t)(j + 32 * u) * lda]; tv[u] = t[j + 32 * u]; lv[u] = lam[j + 32 * u]; }
+            for (int u = 0; u < 8; ++u) { av[u] = a[(size_t)(j + SS_PH * u) * lda]; tv[u] = t[j + SS_PH * u]; lv[u] = lam[j + SS_PH * u]; }
 #pragma unroll
             for (int u = 0; u < 8; ++u) { acc0 = fma(av[u], tv[u], acc0); acc1 = fma(av[u], lv[u] * tv[u], acc1); }
         }
-        for (; j < n; j += 32) {
+        for (; j < n; j += SS_PH) {
             const double a0 = a[(size_t)j * lda], t0 = t[j];
             acc0 = fma(a0, t0, acc0);
             acc1 = fma(a0, lam[j] * t0, acc1);
@@ -356,13 +358,17 @@ sk_sample_step_kernel(int m, int n, const double* __restrict__ A, int lda, const
     part[0][slot][r] = acc0;
     part[1][slot][r] = acc1;
     __syncthreads();
-    if (threadIdx.x < 2 * GV_ROWS) {
-        const int which = threadIdx.x / GV_ROWS, rr = threadIdx.x % GV_ROWS;
-        const int ii = blockIdx.x * GV_ROWS + rr;
+    if (threadIdx.x < 2 * SS_ROWS) {
+        const int which = threadIdx.x / SS_ROWS, rr = threadIdx.x % SS_ROWS;
+        const int ii = blockIdx.x * SS_ROWS + rr;
         if (ii < m) {
-            double sum = 0.0;
+            double s4[4] = {0.0, 0.0, 0.0, 0.0};                 // four interleaved chains, combined in a fixed order
 #pragma unroll
-            for (int q = 0; q < GV_WARPS * 2; ++q) sum += part[which][q][rr];
+            for (int q = 0; q < SS_PH; q += 4) {
+                s4[0] += part[which][q][rr]; s4[1] += part[which][q + 1][rr];
+                s4[2] += part[which][q + 2][rr]; s4[3] += part[which][q + 3][rr];
+            }
+            const double sum = (s4[0] + s4[1]) + (s4[2] + s4[3]);
             if (which == 0) w[ii] = sum;
             else xs[ii] = (fabs(sum) >= eps) ? 1.0 / sum : 0.0;
         }
@@ -370,46 +376,69 @@ sk_sample_step_kernel(int m, int n, const double* __restrict__ A, int lda, const
 }
 
 // t[j] = sum_i U[i,j] x[i] + inv_lam[j] * sum_i U[i,j] s[i]     (phi^T x in factor form): one pass over U instead of
-// two dgemv_t + an axpy; same summation order as dgemv_t_kernel.
-__global__ void sk_phiT_kernel(int m, int n, const double* __restrict__ A, int lda, const double* __restrict__ x,
-                               const double* __restrict__ sv, const double* __restrict__ inv_lam, double* __restrict__ t) {
-    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (warp >= n) return;
-    const double* col = A + (size_t)warp * lda;
+// two dgemv_t + an axpy.  CTA = 8 warps = 2 columns x 4 row quarters (one warp per column left 8 warps per SM with seven
+// dependent batches of loads each); the quarters are combined in a fixed order.
+__global__ void __launch_bounds__(256)
+sk_phiT_kernel(int m, int n, const double* __restrict__ A, int lda, const double* __restrict__ x,
+               const double* __restrict__ sv, const double* __restrict__ inv_lam, double* __restrict__ t) {
+    __shared__ double part[2][2][4];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int cj = warp >> 2, qr = warp & 3;
+    const int j = blockIdx.x * 2 + cj;
+    const int mq = ((m + 3) / 4 + 31) & ~31;                 // rows per quarter, a multiple of 32
     double acc0 = 0.0, acc1 = 0.0;
-    int i = lane;
-    for (; i + 7 * 32 < m; i += 8 * 32) {          // 8 loads in flight per lane, ascending summation order
-        double av[8];
+    if (j < n) {
+        const double* col = A + (size_t)j * lda;
+        const int i1 = min(m, (qr + 1) * mq);
+        int i = qr * mq + lane;
+        for (; i + 7 * 32 < i1; i += 8 * 32) {               // 8 loads in flight per lane, ascending summation order
+            double av[8];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) av[u] = col[i + 32 * u];
+            for (int u = 0; u < 8; ++u) av[u] = col[i + 32 * u];
 #pragma unroll
-        for (int u = 0; u < 8; ++u) { acc0 = fma(av[u], x[i + 32 * u], acc0); acc1 = fma(av[u], sv[i + 32 * u], acc1); }
-    }
-    for (; i < m; i += 32) {
-        const double a = col[i];
-        acc0 = fma(a, x[i], acc0);
-        acc1 = fma(a, sv[i], acc1);
+            for (int u = 0; u < 8; ++u) { acc0 = fma(av[u], x[i + 32 * u], acc0); acc1 = fma(av[u], sv[i + 32 * u], acc1); }
+        }
+        for (; i + 32 < i1; i += 2 * 32) {
+            const double a0 = col[i], a1 = col[i + 32];
+            acc0 = fma(a0, x[i], acc0); acc1 = fma(a0, sv[i], acc1);
+            acc0 = fma(a1, x[i + 32], acc0); acc1 = fma(a1, sv[i + 32], acc1);
+        }
+        for (; i < i1; i += 32) {
+            const double a = col[i];
+            acc0 = fma(a, x[i], acc0);
+            acc1 = fma(a, sv[i], acc1);
+        }
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
         acc0 += __shfl_xor_sync(0xffffffffu, acc0, o);
         acc1 += __shfl_xor_sync(0xffffffffu, acc1, o);
     }
-    if (lane == 0) t[warp] = fma(inv_lam[warp], acc1, acc0);
+    if (lane == 0) { part[cj][0][qr] = acc0; part[cj][1][qr] = acc1; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        const int jj = blockIdx.x * 2 + threadIdx.x;
+        if (jj < n) {
+            const double* p0 = part[threadIdx.x][0];
+            const double* p1 = part[threadIdx.x][1];
+            const double a0 = (p0[0] + p0[1]) + (p0[2] + p0[3]);
+            const double a1 = (p1[0] + p1[1]) + (p1[2] + p1[3]);
+            t[jj] = fma(inv_lam[jj], a1, a0);
+        }
+    }
 }
 
 void sk_sample_step(int m, int n, const double* U, int ldu, const double* t, const double* lam, double eps, double* w,
                     double* xs, cudaStream_t s) {
     if (m <= 0) return;
-    sk_sample_step_kernel<<<cdiv(m, GV_ROWS), GV_WARPS * 32, 0, s>>>(m, n, U, ldu, t, lam, eps, w, xs);
+    sk_sample_step_kernel<<<cdiv(m, SS_ROWS), SS_WARPS * 32, 0, s>>>(m, n, U, ldu, t, lam, eps, w, xs);
     NLE_LAUNCH_CHECK();
 }
 
 void sk_phiT(int m, int n, const double* U, int ldu, const double* x, const double* sv, const double* inv_lam, double* t,
              cudaStream_t s) {
     if (n <= 0) return;
-    sk_phiT_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(m, n, U, ldu, x, sv, inv_lam, t);
+    sk_phiT_kernel<<<cdiv(n, 2), 256, 0, s>>>(m, n, U, ldu, x, sv, inv_lam, t);
     NLE_LAUNCH_CHECK();
 }
 
