@@ -151,16 +151,24 @@ __device__ __forceinline__ void trd_step_vectors(int j, int n, double tau_j, dou
 // matrices too large for the shared memory of the SMs (n > ~1700) get the resident kernel for their last ~1700 columns.
 __global__ void __launch_bounds__(kTrdThreads, 1)
 tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, double* __restrict__ e,
-               double* __restrict__ tau, double* __restrict__ pbuf, int nstop) {
+               double* __restrict__ tau, double* __restrict__ pbuf, int nstop, int qs) {
     cg::grid_group grid = cg::this_grid();
     extern __shared__ double sm[];
     double* v = sm;            // current reflector, global row indexing
     double* w = sm + n;
     double* cn = sm + 2 * (size_t)n;   // updated next column -> next reflector
     double* red = sm + 3 * (size_t)n;  // kTrdRed
+    double* cache = red + kTrdRed;     // qs columns of n rows
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x, b = blockIdx.x;
     int phase = 0;
+    // The trailing matrix lives in L2, and for large n a step is bound by reading and writing it once (~5 TB/s).  The qs
+    // HIGHEST columns this CTA owns (the ones that stay in the trailing matrix longest) are therefore kept in shared memory for
+    // the whole launch: their update + symv pass makes no global access.  A cached column goes back to global memory when
+    // somebody else needs it -- in the step in which it becomes the next column (every CTA reads that one), and at the
+    // hand-over of a partial reduction.  Same operations in the same order as for an uncached column.
+    const int q_cnt = (b < n) ? (n - 1 - b) / G + 1 : 0;      // columns this CTA owns: slots q = 0 .. q_cnt-1
+    const int q_c0 = max(0, q_cnt - qs);                      // slots q >= q_c0 are cached, cache slot q - q_c0
 
     if (n < 3) {
         if (b == 0 && tid == 0) {
@@ -200,6 +208,11 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 
     // symv for owned columns c >= c0: pout[c] = sum_{i >= c0} A[i,c] * vec[i]   (no update)
     // (used once, for the first reflector)
+    for (int q = q_c0; q < q_cnt; ++q) {
+        const double* src = A + (size_t)(b + G * q) * lda;
+        double* dst = cache + (size_t)(q - q_c0) * n;
+        for (int i = tid; i < n; i += kTrdThreads) dst[i] = src[i];
+    }
     double tau_j, beta_j, diag_j;
     {
         for (int i = tid; i < n; i += kTrdThreads) cn[i] = A[i];
@@ -266,6 +279,35 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
             const double wc = w[c], vc = v[c];
             double acc = 0.0;
             int i = j + 2 + lane;
+            if (q >= q_c0) {
+                // cached column: shared memory only; written through to global memory when it is the next column (c == j+2)
+                // or the launch hands over.  Loads in front of the stores (same address space to the compiler).
+                double* sc = cache + (size_t)(q - q_c0) * n;
+                const bool wb = (c == j + 2) || last_partial;
+                for (; i + 3 * 32 < n; i += 4 * 32) {
+                    double a[4], wv[4], vv[4], cv[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ii = i + 32 * u;
+                        a[u] = sc[ii]; wv[u] = w[ii]; vv[u] = v[ii]; cv[u] = cn[ii];
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                        const int ii = i + 32 * u;
+                        a[u] = fma(-wv[u], vc, fma(-vv[u], wc, a[u]));
+                        acc = fma(a[u], cv[u], acc);
+                        sc[ii] = a[u];
+                        if (wb) __stcg(col + ii, a[u]);
+                    }
+                }
+                for (; i < n; i += 32) {
+                    double a = sc[i];
+                    a = fma(-w[i], vc, fma(-v[i], wc, a));
+                    acc = fma(a, cn[i], acc);
+                    sc[i] = a;
+                    if (wb) __stcg(col + i, a);
+                }
+            } else {
             // batches of 16 independent loads to cover the L2 latency (the column is the longest link of the step)
             for (; i + 15 * 32 < n; i += 16 * 32) {
                 double a[16];
@@ -296,6 +338,7 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
                 a = fma(-w[i], vc, fma(-v[i], wc, a));
                 acc = fma(a, cn[i], acc);
                 __stcg(col + i, a);
+            }
             }
             if (has_next) {
                 acc = warp_sum(acc);
@@ -1546,15 +1589,21 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     };
     // grid.sync kernel on the block (Ab, lda = n, m): reflectors [0, nstop) only when nstop < m - 2
     auto launch_gridsync = [&](double* Ab, int m, double* db, double* eb, double* taub, int nstop) {
-        size_t smem = (3 * (size_t)m + kTrdRed) * sizeof(double);
         const void* kfn = (const void*)tridiag_kernel;
         allow_max_dynamic_smem((const void*)kfn);
+        int grid = std::min(sm_count(), m);
+        // as many of a CTA's columns as fit stay in shared memory for the whole launch (the highest ones)
+        const size_t base = (3 * (size_t)m + kTrdRed) * sizeof(double);
+        int qs = 0;
+        if ((size_t)max_smem_trd > base) qs = (int)std::min<size_t>((size_t)cdiv(m, grid), ((size_t)max_smem_trd - base) / ((size_t)m * sizeof(double)));
+        static const bool no_cache = getenv("NLE_B200_TRD_NOCACHE") != nullptr;     // timing comparisons
+        if (no_cache || force_gridsync) qs = 0;       // the cross-check path is the plain L2-resident kernel
+        size_t smem = base + (size_t)qs * m * sizeof(double);
         int per_sm = 0;
         NLE_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kfn, kTrdThreads, smem));
         if (per_sm < 1) throw Unsupported{"eigensolver: tridiagonalisation kernel does not fit on an SM (n=" + std::to_string(m) + ")"};
-        int grid = std::min(sm_count(), m);
         int lda = n;
-        void* args[] = {&Ab, &lda, &m, &db, &eb, &taub, &pbuf, &nstop};
+        void* args[] = {&Ab, &lda, &m, &db, &eb, &taub, &pbuf, &nstop, &qs};
         NLE_CUDA(cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kTrdThreads), args, smem, s));
         ++g_launches;
     };

@@ -294,24 +294,35 @@ sk_reduce_gemm_nb_kernel(AffinityTables t, const double* __restrict__ Hx, int ld
     }
 }
 
-// s[i] = sum_q P[q][i], q = 0 .. nq-1 in ascending order (four interleaved partial sums per sample, combined in a fixed order)
+// s[i] = sum_q P[q][i], q = 0 .. nq-1: eight interleaved chains per sample (warp c of the CTA takes q = c, c + 8, ...; a warp reads 32
+// consecutive samples), eight loads in flight per thread, chains combined in a fixed order.  The partials (nq ~ 130 vectors) come
+// straight from the reduce GEMM, i.e. from L2: the kernel is a chain of dependent load batches between two dependent kernels.
 __global__ void __launch_bounds__(256)
 sk_sum_partials_kernel(const double* __restrict__ P, int nq, int p, double* __restrict__ s_out) {
-    __shared__ double part[4][64];
-    const int i = blockIdx.x * 64 + (threadIdx.x & 63), c = threadIdx.x >> 6;
+    __shared__ double part[8][32];
+    const int lane = threadIdx.x & 31, c = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + lane;
     double acc = 0.0;
     if (i < p) {
         int q = c;
-        for (; q + 12 < nq; q += 16) {
-            const double x0 = P[(size_t)q * p + i], x1 = P[(size_t)(q + 4) * p + i];
-            const double x2 = P[(size_t)(q + 8) * p + i], x3 = P[(size_t)(q + 12) * p + i];
-            acc += x0; acc += x1; acc += x2; acc += x3;
+        for (; q + 56 < nq; q += 64) {
+            double x[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) x[u] = P[(size_t)(q + 8 * u) * p + i];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) acc += x[u];
         }
-        for (; q < nq; q += 4) acc += P[(size_t)q * p + i];
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) x[u] = (q + 8 * u < nq) ? P[(size_t)(q + 8 * u) * p + i] : 0.0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u) acc += x[u];
     }
-    part[c][threadIdx.x & 63] = acc;
+    part[c][lane] = acc;
     __syncthreads();
-    if (threadIdx.x < 64 && i < p) s_out[i] = (part[0][threadIdx.x] + part[1][threadIdx.x]) + (part[2][threadIdx.x] + part[3][threadIdx.x]);
+    if (threadIdx.x < 32 && i < p)
+        s_out[i] = ((part[0][lane] + part[1][lane]) + (part[2][lane] + part[3][lane])) +
+                   ((part[4][lane] + part[5][lane]) + (part[6][lane] + part[7][lane]));
 }
 
 // One CTA per image row.  FH row block: [nC][256] in global memory; on entry F (ignored when w_given == 0:
@@ -689,7 +700,7 @@ void launch_sinkhorn_cells(const AffinityTables& t, const CellIndex* ci, const d
             case 7: launch_red_nb<4, 7, 8>(t, g, Hx, Mpart, s); break;
             default: launch_red_nb<3, 8, 12>(t, g, Hx, Mpart, s); break;
         }
-        sk_sum_partials_kernel<<<cdiv(t.p, 64), 256, 0, s>>>(Mpart, g.nksb * g.lgb, t.p, s_out);
+        sk_sum_partials_kernel<<<cdiv(t.p, 32), 256, 0, s>>>(Mpart, g.nksb * g.lgb, t.p, s_out);
         NLE_LAUNCH_CHECK();
         return;
     }
