@@ -10,12 +10,15 @@
 //   tridiag_kernel        persistent cooperative kernel; ONE pass over the trailing matrix and ONE
 //                         grid.sync per Householder step: the rank-2 update of step j is fused with
 //                         the symmetric matrix-vector product of step j+1 (the next reflector is
-//                         derived redundantly by every CTA from the updated column j+1).
+//                         derived redundantly by every CTA from the updated column j+1).  The matrix lives in L2,
+//                         except for the highest columns of every CTA, which stay in shared memory.  Partial mode:
+//                         stops after nstop reflectors and leaves the trailing block complete in global memory.
 //   tridiag_cluster_kernel   the default for n >= 64: same arithmetic in the same order (bit-identical d, e,
-//                         tau, reflectors), trailing matrix resident in shared memory, flagged-cell exchange instead
-//                         of grid.sync, thread-block clusters of 2 CTAs share the polling through distributed shared
-//                         memory (profiles/r2a_trd_sweep.md: 14-19 % faster than tridiag_kernel at n = 612...1600).
-//                         A matrix whose columns do not fit in the shared memory of 148 SMs (n > ~1700) is reduced by
+//                         tau, reflectors), trailing matrix resident in shared memory, no grid barrier: p = A v and
+//                         the next column travel as flagged 16-byte cells that land in both CTAs of a thread-block
+//                         cluster by ONE TMA multicast copy per vector and step (profiles/r2zb_trd_multicast.md:
+//                         n = 1600 in 7.3 ms against 10.2 ms for tridiag_kernel).
+//                         A matrix whose columns do not fit in the shared memory of 148 SMs (n > ~1610) is reduced by
 //                         tridiag_kernel (partial mode) until the trailing block fits and then handed over; alone,
 //                         tridiag_kernel is the fallback and the cross-check of tests/test_gpu_eig_variants.py.
 //   dc_leaf_kernel        implicit-shift QL on leaves of <= 32 rows, one warp per leaf.
@@ -370,9 +373,9 @@ tridiag_kernel(double* __restrict__ A, int lda, int n, double* __restrict__ d, d
 //     step makes no global loads or stores at all;
 //   * the two vectors every CTA needs at the start of a step -- p = A v and the next column -- are
 //     exchanged through global memory as flagged 16-byte cells {lo, tag, hi, tag} (two 8-byte halves, each
-//     written atomically together with its tag; the low-latency protocol NCCL calls LL): the consumer
-//     polls the cells themselves, so one L2 write + one L2 read replace the store-acknowledge fence,
-//     the barrier atomic, the barrier poll and the separate p / column loads of the grid.sync version;
+//     written atomically together with its tag; the low-latency protocol NCCL calls LL): there is no store-acknowledge
+//     fence, no barrier atomic and no barrier poll; the consumers fetch all cells of a step with one TMA multicast copy
+//     per vector and cluster, validate the tags, and re-poll the few cells that were not yet written;
 //   * cells are double-buffered by the parity of the tag; a cluster leaves the kernel as soon as it owns no
 //     column of the trailing matrix any more, so the CTAs that still exchange data are never more than
 //     one step apart (each waits for cells written by all the others), which is what makes two buffers
@@ -393,15 +396,6 @@ __device__ __forceinline__ uint4 ll_load(const uint4* cell) {
     asm volatile("ld.relaxed.gpu.global.v2.u64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(cell) : "memory");
     r.x = (unsigned)a; r.y = (unsigned)(a >> 32); r.z = (unsigned)b; r.w = (unsigned)(b >> 32);
     return r;
-}
-// Two adjacent cells (one 32-byte sector) with one request: the exchange is bound by the NUMBER of L2 requests (every CTA
-// reads every cell of the step), not by their bytes.  Each 8-byte half still carries its own tag, so nothing beyond 8-byte
-// atomicity is assumed.  SASS: LDG.E.ENL2.256.STRONG.GPU.
-__device__ __forceinline__ void ll_load2(const uint4* cell_pair /* 32-byte aligned */, uint4& c0, uint4& c1) {
-    unsigned long long a, b, c, d;
-    asm volatile("ld.relaxed.gpu.global.v4.u64 {%0, %1, %2, %3}, [%4];" : "=l"(a), "=l"(b), "=l"(c), "=l"(d) : "l"(cell_pair) : "memory");
-    c0.x = (unsigned)a; c0.y = (unsigned)(a >> 32); c0.z = (unsigned)b; c0.w = (unsigned)(b >> 32);
-    c1.x = (unsigned)c; c1.y = (unsigned)(c >> 32); c1.z = (unsigned)d; c1.w = (unsigned)(d >> 32);
 }
 __device__ __forceinline__ double ll_value(const uint4& c) {
     return __longlong_as_double((long long)(((unsigned long long)c.z << 32) | (unsigned long long)c.x));
