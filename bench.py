@@ -563,9 +563,9 @@ def run_b200(args, rank, world, local_rank):
     trd_flops = 4.0 / 3.0 * (float(pp) ** 3 + float(inf.r) ** 3 + float(inf.r2) ** 3)
     trd = tensor_entry("tridiag_cluster_kernel x3 (Householder tridiagonalisation of Ka, Wa, Q-block)", trd_flops, st[8],
                        "(4/3)(p^3 + r^3 + r2^3) flop; BLAS-2 with one grid-wide exchange per Householder column: bound by the "
-                       "latency / L2 bandwidth of that exchange (profiles/r2a_trd_sweep.md), not by the FP64 pipes", peak=dfma_peak)
+                       "latency of that exchange (TMA multicast landing + validation, profiles/r2zb_trd_multicast.md) and of the two block reductions behind it, not by the FP64 pipes", peak=dfma_peak)
     trd["bound"] = "latency"
-    trd["pipe"] = "FP64 FMA pipe (DFMA) + shared memory; per-step exchange through L2"
+    trd["pipe"] = "FP64 FMA pipe (DFMA) + shared memory; per-step exchange of flagged cells through L2, landed by TMA multicast"
     nrows_loc = row1 - row0
     sk_flops = 2.0 * T_SINK * (2 * 2.0 * nrows_loc * 256 * pp + 4.0 * nloc * nC)
     sk = tensor_entry("Sinkhorn half-iterations x2T (sk_dot_gemm + sk_pix_cells + sk_reduce_gemm + sample-side passes)", sk_flops, st[2],
