@@ -450,7 +450,7 @@ train_core(const uint8_t* lum_slab, int rows, int cols, int row0, int row1, cons
     // rather than return anything doubtful, and the full solver then runs as before.
     bool topk_done = false;
     static const bool topk_off = [] { const char* e = getenv("NLE_B200_TOPK"); return e && std::string(e) == "off"; }();   // cross-check only
-    if (!topk_off && sym_eig_topk_supported(r2, nEig)) {
+    if (!topk_off && sym_eig_topk_preferred(r2, nEig)) {
         symmetrize_lower(Mq.p, r2, r2, T2.p, s);                                      // the lower triangle defines M, as in sym_eig
         topk_done = sym_eig_topk(T2.p, r2, nEig, kEps, Zq.p, Sq.p, d_cnt.p, ws, s, &f->topk_products);
         if (!topk_done) f->topk_products = -f->topk_products;                        // < 0: tried and fell back

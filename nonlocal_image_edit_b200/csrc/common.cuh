@@ -206,6 +206,7 @@ void symmetrize_lower(const double* M, int ldm, int n, double* As, cudaStream_t 
 // ---- eig_topk.cu : top-k eigenpairs of a symmetric POSITIVE SEMI-DEFINITE matrix (third eigensolve, filter.cpp:311-316) ----
 // Chebyshev-filtered block subspace iteration, Cholesky-QR, Rayleigh-Ritz; all products on the FP64 tensor pipe.
 int topk_block_width(int k);                 // k + guard columns, multiple of 8
+bool sym_eig_topk_preferred(int n, int k);   // ... and is expected to beat the full solver (the training pipeline's rule)
 bool sym_eig_topk_supported(int n, int k);   // block fits one CTA's shared memory and n is large enough for the method to pay
 // A: n x n, FULL storage (ld n).  Z: n x k (ld n) eigenvectors of the k largest eigenvalues, descending; S: k eigenvalues;
 // d_count: length of the prefix with S >= eps.  false = gave up (Cholesky breakdown, no convergence, k-th eigenvalue < eps):

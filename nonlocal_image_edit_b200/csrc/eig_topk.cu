@@ -210,6 +210,17 @@ bool sym_eig_topk_supported(int n, int k) {
     return m <= kMaxM && n >= 10 * m && n >= 256;
 }
 
+// Policy of the training pipeline (api.cu): is the block method expected to be FASTER than the full solver for eig(Q)?
+// Re-measured after the tridiagonalisation of the full solver got 20-25 % faster (scripts/gpu_topk_switch.py, one B200, the stage
+// "Wa, WW, eig(Wa), Q, eig(Q)" with the block solver / with the full solver): block width 64 (k = 50): n = 855: 13.3 / 14.2 ms,
+// n = 1357: 19.1 / 20.1 ms -- the block method keeps its lead; block width 128 (k = 100): n = 1833: 47.8 / 45.5 ms -- the two
+// or three 128 x 128 Rayleigh-Ritz solves and the Cholesky-QR chains of 2 x 128 dependent pivots cost more than they save.
+bool sym_eig_topk_preferred(int n, int k) {
+    if (!sym_eig_topk_supported(n, k)) return false;
+    const int m = topk_block_width(k);
+    return m <= 64 || n >= 24 * m;
+}
+
 int topk_block_width(int k) {
     const int m = k + std::max(14, k / 4);
     return (m + 7) / 8 * 8;
