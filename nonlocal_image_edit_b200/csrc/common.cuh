@@ -186,6 +186,12 @@ struct EigWorkspace {
     void phase_reset() { pev_used = 0; phase_on = true; }
     void phase_mark(cudaStream_t s);
     void phase_ms(double out[3]);
+    // Side stream of the direct solver: the T factors of the blocked back-transformation depend on the reflectors only, so
+    // bt_tfactor_kernel runs beside the divide & conquer phase (a chain of small kernels that leaves most SMs idle).
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    int side_dev = -1;
+    void side_init();
     ~EigWorkspace();
 };
 // Eigen-decomposition of the symmetric matrix defined by the LOWER triangle of M (n x n, ld ldm).

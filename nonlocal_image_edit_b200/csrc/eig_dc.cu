@@ -1513,6 +1513,22 @@ void EigWorkspace::phase_ms(double out[3]) {
 }
 EigWorkspace::~EigWorkspace() {
     for (cudaEvent_t e : pev) cudaEventDestroy(e);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side) cudaStreamDestroy(side);
+}
+
+void EigWorkspace::side_init() {
+    int dev = 0;
+    NLE_CUDA(cudaGetDevice(&dev));
+    if (side && side_dev == dev) return;
+    if (ev_fork) { cudaEventDestroy(ev_fork); ev_fork = nullptr; }
+    if (ev_join) { cudaEventDestroy(ev_join); ev_join = nullptr; }
+    if (side) { cudaStreamDestroy(side); side = nullptr; }
+    NLE_CUDA(cudaStreamCreateWithFlags(&side, cudaStreamNonBlocking));     // must not synchronise with the legacy default stream
+    NLE_CUDA(cudaEventCreateWithFlags(&ev_fork, cudaEventDisableTiming));
+    NLE_CUDA(cudaEventCreateWithFlags(&ev_join, cudaEventDisableTiming));
+    side_dev = dev;
 }
 
 void EigWorkspace::reserve_dc(int n) {
@@ -1696,6 +1712,20 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
     }
     auto t_trd = tnow();
     ws.phase_mark(s);
+    // T factors of the compact-WY back-transformation: they depend on the reflectors only -> side stream, beside the D&C
+    const int nrefl = n - 2;
+    const int nblocks = cdiv(std::max(nrefl, 1), kWyB);
+    const size_t wy_smem = ((size_t)n * 8 + 8 * kWyB * 8 + 2 * kWyB * 8 + kWyB * (kWyB + 1)) * sizeof(double);
+    const bool wy_path = n >= 64 && wy_smem <= (size_t)max_smem_trd;
+    if (wy_path) {
+        if (ws.wyT.n < (size_t)nblocks * kWyB * kWyB) ws.wyT.alloc((size_t)nblocks * kWyB * kWyB);
+        ws.side_init();
+        NLE_CUDA(cudaEventRecord(ws.ev_fork, s));
+        NLE_CUDA(cudaStreamWaitEvent(ws.side, ws.ev_fork, 0));
+        bt_tfactor_kernel<<<nblocks, 256, 0, ws.side>>>(As, n, n, tau, nrefl, ws.wyT.p);
+        NLE_LAUNCH_CHECK();
+        NLE_CUDA(cudaEventRecord(ws.ev_join, ws.side));
+    }
     // ---- 2. divide & conquer on (d0, e0)
     int depth = 0;
     while (((n + (1 << depth) - 1) >> depth) > kLeaf) ++depth;
@@ -1758,22 +1788,17 @@ bool sym_eig_dc_core(double* As, int n, double eps, int vec_limit, int* order, i
         dc_collist_kernel<<<cdiv(n, 128), 128, 0, s>>>(order, n, collist);
         NLE_LAUNCH_CHECK();
         double* gdot = pbuf;      // the symv exchange buffer of the tridiagonalisation is free again
-        if (n >= 4) {
-            reflector_dots_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(As, n, n, gdot);
-            NLE_LAUNCH_CHECK();
-        }
         // compact-WY blocks on DMMA when the 8-column tile fits in shared memory (else the per-reflector kernel)
-        const int nrefl = n - 2;
-        const int nblocks = cdiv(nrefl, kWyB);
-        const size_t wy_smem = ((size_t)n * 8 + 8 * kWyB * 8 + 2 * kWyB * 8 + kWyB * (kWyB + 1)) * sizeof(double);
-        if (m > 0 && n >= 64 && wy_smem <= (size_t)max_smem) {
-            if (ws.wyT.n < (size_t)nblocks * kWyB * kWyB) ws.wyT.alloc((size_t)nblocks * kWyB * kWyB);
-            bt_tfactor_kernel<<<nblocks, 256, 0, s>>>(As, n, n, tau, nrefl, ws.wyT.p);
-            NLE_LAUNCH_CHECK();
+        if (wy_path) NLE_CUDA(cudaStreamWaitEvent(s, ws.ev_join, 0));      // the T factors (side stream) are complete
+        if (m > 0 && wy_path) {
             allow_max_dynamic_smem((const void*)bt_wy_kernel);
             bt_wy_kernel<<<cdiv(m, 8), 256, wy_smem, s>>>(As, n, n, ws.wyT.p, nblocks, nrefl, Qc, n, collist, count, vec_limit);
             NLE_LAUNCH_CHECK();
         } else if (m > 0) {
+            if (n >= 4) {
+                reflector_dots_kernel<<<cdiv((long long)n * 32, 256), 256, 0, s>>>(As, n, n, gdot);
+                NLE_LAUNCH_CHECK();
+            }
             backtransform_kernel<<<cdiv(m, wpb), wpb * 32, smem, s>>>(As, n, tau, gdot, n, Qc, n, collist, count, vec_limit);
             NLE_LAUNCH_CHECK();
         }
