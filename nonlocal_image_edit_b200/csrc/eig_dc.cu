@@ -456,7 +456,7 @@ __device__ __forceinline__ void trd_cluster_wait() { asm volatile("barrier.clust
 // Clusters: the CTAs of a thread-block cluster receive the cells of a step with ONE L2 read (TMA multicast).  Round 2
 // history (profiles/r2a_trd_sweep.md, r2zb_trd_multicast.md): per-thread polling of all cells by every CTA (n = 1600:
 // 9.5 ms); clusters of 2 whose CTAs poll every second cell with strong 256-bit loads and forward them through distributed
-// shared memory, one cluster.sync per step (8.7 - 9.0 ms); the multicast landing below (7.9 ms): the poll + forward phase
+// shared memory, one cluster.sync per step (8.7 - 9.0 ms); the multicast landing below (7.9 ms; 7.3 with trd_step_vectors): the poll + forward phase
 // of 6.6k cycles per step became 3.7k (copy in flight) + 1.5k (validation); the copy is issued column first because the p
 // cells are the last thing a producer writes.  Unicast copies per CTA measure the same as the multicast (the L2 merges the
 // concurrent reads of a cluster), larger clusters gain < 2 % at n <= 1041 and do not fit at n = 1600.
