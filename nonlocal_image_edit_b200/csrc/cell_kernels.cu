@@ -474,7 +474,7 @@ constexpr int XC_N = 56;          // eigenvector columns per block (7 DMMA n-til
 constexpr int XC_WARPS = 12;       // three warps per sub-core: the 4 x 7 tile fits 168 registers
 constexpr int XC_THREADS = XC_WARPS * 32;
 constexpr int XC_CELLS = XC_WARPS * 32;   // cells per sub-tile of ext_fx_kernel (XC_WARPS warps x 4 m-tiles)
-constexpr int XC_SUB = 8;         // sub-tiles per CTA (the Y slice and the Er rows are staged once for all of them)
+constexpr int XC_SUB = 16;        // sub-tiles per CTA (the Y slice and the Er rows are staged once for all of them)
 constexpr int XC_ERROWS = 64;     // image rows whose Er rows fit the staging area
 
 __global__ void __launch_bounds__(256)
