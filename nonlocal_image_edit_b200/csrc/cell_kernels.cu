@@ -475,7 +475,7 @@ constexpr int XC_WARPS = 12;       // three warps per sub-core: the 4 x 7 tile f
 constexpr int XC_THREADS = XC_WARPS * 32;
 constexpr int XC_CELLS = XC_WARPS * 32;   // cells per sub-tile of ext_fx_kernel (XC_WARPS warps x 4 m-tiles)
 constexpr int XC_SUB = 16;        // sub-tiles per CTA (the Y slice and the Er rows are staged once for all of them)
-constexpr int XC_ERROWS = 64;     // image rows whose Er rows fit the staging area
+constexpr int XC_ERROWS = 256;    // image rows whose Er rows are staged at most (fewer when the sample grid leaves less shared memory)
 
 __global__ void __launch_bounds__(256)
 ext_index_kernel(const uint8_t* __restrict__ lum, int nrows, int W, const int* __restrict__ koff,
@@ -530,14 +530,14 @@ ext_index_kernel(const uint8_t* __restrict__ lum, int nrows, int W, const int* _
 // grid (ceil(cap_cells / (XC_CELLS * XC_SUB)), nC, column blocks); warp = 32 cells (4 m-tiles) x 56 columns (7 n-tiles).
 __global__ void __launch_bounds__(XC_THREADS, 1)
 ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __restrict__ cell_lev,
-              const int* __restrict__ cell_row, const double* __restrict__ Yt, int kp, double* __restrict__ FX) {
+              const int* __restrict__ cell_row, const double* __restrict__ Yt, int kp, double* __restrict__ FX, int erows) {
     extern __shared__ double xsm[];
     const int nR = t.nR, nC = t.nC;
     const int nR4 = (nR + 3) & ~3;
     double* Ys = xsm;                                  // nR4 * XC_N   slice of Y for grid column b
     double* Gs = Ys + (size_t)nR4 * XC_N;              // 256
     int* ysl = reinterpret_cast<int*>(Gs + 256);       // nR4          sample luminances of grid column b
-    double* ErS = reinterpret_cast<double*>(ysl + nR4 + (nR4 & 1));   // XC_ERROWS * nR4: Er rows of the image rows this CTA's cells span
+    double* ErS = reinterpret_cast<double*>(ysl + nR4 + (nR4 & 1));   // erows * nR4: Er rows of the image rows this CTA's cells span
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int g = lane >> 2, tq = lane & 3;
     const int b = blockIdx.y, vb = blockIdx.z;
@@ -551,10 +551,10 @@ ext_fx_kernel(AffinityTables t, const int* __restrict__ koff, const uint8_t* __r
     }
     for (int a = tid; a < nR4; a += XC_THREADS) ysl[a] = a < nR ? (int)t.Ysel[a * nC + b] : 0;
     // cells are ordered by image row: the CTA's cells span rows [row_first, row_last]; their Er rows are staged in shared
-    // memory when there are at most XC_ERROWS of them (ncu: 33 % of the samples sat on the Er look-up in global memory)
+    // memory when there are at most `erows` of them (ncu: 33 % of the samples sat on the Er look-up in global memory)
     const int row_first = cell_row[k0];
     const int row_last = cell_row[min(K, k0 + XC_CELLS * XC_SUB) - 1];
-    const bool er_smem = row_last - row_first < XC_ERROWS;
+    const bool er_smem = row_last - row_first < erows;
     if (er_smem)
         for (int e = tid; e < (row_last - row_first + 1) * nR4; e += XC_THREADS) {
             const int r = e / nR4, a = e - r * nR4;
@@ -799,14 +799,18 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
     NLE_LAUNCH_CHECK();
     const size_t ism = (size_t)(256 * 3 + 260 + 8) * sizeof(int) + ((t.cols + 15) / 16) * 16 + 16;
     const int nR4 = (t.nR + 3) & ~3;
-    const size_t fsm = ((size_t)nR4 * XC_N + 256 + (size_t)XC_ERROWS * nR4) * sizeof(double) + (size_t)(nR4 + 2) * sizeof(int) + 16;
-    if (ism > 227 * 1024 || fsm > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
+    // Er staging: a CTA's 6144 cells span 20-40 image rows on a noisy image and > 100 on a smooth one (few levels per row); stage up to
+    // XC_ERROWS of them, as many as the sample grid leaves room for (beyond that the kernel reads Er from global memory)
+    const size_t fbase = ((size_t)nR4 * XC_N + 256) * sizeof(double) + (size_t)(nR4 + 2) * sizeof(int) + 16;
+    if (ism > 227 * 1024 || fbase + 8 * (size_t)nR4 * sizeof(double) > 227 * 1024) throw Unsupported{"extension: grid/image too large for the cell kernels"};
+    int erows = (int)std::min<size_t>(XC_ERROWS, (227 * 1024 - fbase) / ((size_t)nR4 * sizeof(double)));
+    const size_t fsm = fbase + (size_t)erows * nR4 * sizeof(double);
     allow_max_dynamic_smem((const void*)ext_index_kernel);
     allow_max_dynamic_smem((const void*)ext_fx_kernel);
     if (ci != nullptr && g.rows_batch >= t.nrows) {
         // one batch and the slab's cell index exists already: no second per-row sort
         const int cap_cells = g.capc * t.nrows;
-        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), XC_THREADS, fsm, s>>>(t, ci->koff, ci->lev, ci->row, Yt, g.kp, FX);
+        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), XC_THREADS, fsm, s>>>(t, ci->koff, ci->lev, ci->row, Yt, g.kp, FX, erows);
         NLE_LAUNCH_CHECK();
         ext_pix_kernel<<<sm_count() * 8, 256, 0, s>>>(t, ci->koff, ci->row, ci->pstart, ci->pcount, ci->sorted, c, FX, g.kp, g.nvb, k, V);
         NLE_LAUNCH_CHECK();
@@ -827,7 +831,7 @@ void launch_extension_cells(const AffinityTables& t, const double* c, const doub
                                                                              cell_pstart, cell_pcount, sorted);
         NLE_LAUNCH_CHECK();
         const int cap_cells = g.capc * tb.nrows;
-        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), XC_THREADS, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX);
+        ext_fx_kernel<<<dim3(cdiv(cap_cells, XC_CELLS * XC_SUB), t.nC, g.nvb), XC_THREADS, fsm, s>>>(tb, koff, cell_lev, cell_row, Yt, g.kp, FX, erows);
         NLE_LAUNCH_CHECK();
         ext_pix_kernel<<<sm_count() * 8, 256, 0, s>>>(tb, koff, cell_row, cell_pstart, cell_pcount, sorted, cb, FX, g.kp, g.nvb, k, Vb);
         NLE_LAUNCH_CHECK();
